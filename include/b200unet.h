@@ -1,0 +1,173 @@
+/*
+ * b200unet.h -- C ABI of libb200unet.so: the sm_100a kernels behind the Our_UNet training step.
+ *
+ * The reference (Ulixes-8/UNet-Implementations) has no FFI: its hot path is the Python class surface
+ * `models.unet.UNet` / `models.losses.SimpleLoss` dispatching to stock torch.nn ops (cuDNN/ATen).  Every entry
+ * point below replaces one of those implicit library dispatches; the reference call site it stands in for is
+ * cited per function (paths relative to the reference root).  The Python host (`models/unet.py`,
+ * `models/losses.py` in this repo) binds these with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, ints, floats; no torch types.  Every function returns 0 on success or a
+ *    negative code; `b200unet_last_error()` returns the (thread-local) message.
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); nothing synchronises,
+ *    allocates or frees device memory; no device pointer is retained after return.
+ *  - activations are NHWC bf16.  A tensor argument is (ptr, pitch): element (n,h,w,c) lives at
+ *    ptr[((n*H + h)*W + w)*pitch + c]; pitch >= C lets an operator read or write a channel slice of a wider
+ *    buffer (the decoder concat buffer), which is how torch.cat (unet.py:228) disappears.
+ *  - "stats partial" buffers are fp32 [N][P][C][2] = per-image partial (sum, sum of squares) produced by P
+ *    tiles/blocks per image; they are reduced in fixed order (deterministic, no atomics).
+ */
+#ifndef B200UNET_H_
+#define B200UNET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200UNET_VERSION 100
+
+int b200unet_version(void);
+const char* b200unet_last_error(void);
+/* 1 if the current device is compute capability 10.x, else 0 (negative on error). */
+int b200unet_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3x3 convolution, pad 1, stride 1 or 2 -- replaces nn.Conv2d in ConvBlock (Our_UNet/models/unet.py:106-115)
+ * and its autograd backward (aten::convolution_backward).  Implicit GEMM on tcgen05/TMEM, operands staged by TMA.
+ * The conv bias is not applied: it feeds an InstanceNorm and cancels exactly.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;      /* bf16 NHWC input  [N,H,W,Cin], pitch x_pitch            */
+  int64_t x_pitch;
+  const void* w;      /* bf16 packed weights [Cout][3][3][Cin] (b200unet_pack_conv_weights) */
+  void* y;            /* bf16 NHWC raw conv output [N,OH,OW,Cout], pitch y_pitch */
+  int64_t y_pitch;
+  float* stats;       /* fp32 [N][P][Cout][2] partial sums of y and y*y over valid pixels, or NULL */
+  int N, H, W, Cin, Cout, stride;
+} b200unet_conv_fprop_args;
+/* Number of stat partials per image (P) the fprop kernel writes for an output of OH x OW. */
+int b200unet_conv_fprop_partials(int OH, int OW);
+int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream);
+
+typedef struct {
+  const void* dy;     /* bf16 NHWC gradient wrt raw conv output [N,OH,OW,Cout], pitch dy_pitch */
+  int64_t dy_pitch;
+  const void* wt;     /* bf16 packed transposed weights [Cin][3][3][Cout] */
+  void* dx;           /* bf16 NHWC gradient wrt conv input [N,H,W,Cin], pitch dx_pitch */
+  int64_t dx_pitch;
+  int N, H, W, Cin, Cout, stride; /* H,W = conv INPUT size */
+} b200unet_conv_dgrad_args;
+int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream);
+
+typedef struct {
+  const void* x;      /* bf16 NHWC conv input [N,H,W,Cin], pitch x_pitch */
+  int64_t x_pitch;
+  const void* dy;     /* bf16 NHWC gradient wrt raw conv output [N,OH,OW,Cout], pitch dy_pitch */
+  int64_t dy_pitch;
+  float* dw;          /* fp32 OIHW [Cout][Cin][3][3] (the nn.Conv2d.weight.grad layout) */
+  float* workspace;   /* fp32 scratch, at least b200unet_conv_wgrad_workspace() bytes */
+  int64_t workspace_bytes;
+  int N, H, W, Cin, Cout, stride;
+} b200unet_conv_wgrad_args;
+int64_t b200unet_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int stride);
+int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stream);
+
+/* CUDA-core direct convolutions with the same argument structs: the slow, obviously-correct path used by the
+ * tests to cross-check the tensor-core kernels on the device and for shapes outside their envelope. */
+int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream);
+int b200unet_conv_dgrad_simt(const b200unet_conv_dgrad_args* a, void* stream);
+int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void* stream);
+
+/* fp32 OIHW [Cout][Cin][3][3] -> bf16 [Cout][3][3][Cin] (w_fprop) and bf16 [Cin][3][3][Cout] (w_dgrad, may be NULL) */
+int b200unet_pack_conv_weights(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stem: first conv of encoder stage 0 (Cin = 3, Cout = 32, stride 1), unet.py:106-115 with the trainer's
+ * config (train.py:776-795).  Reads the fp32 NCHW image directly (train.py:630), writes bf16 NHWC + stat partials.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_stem_partials(int H, int W);
+int b200unet_stem_fprop(const float* img_nchw, const float* w_oihw, void* y, int64_t y_pitch, float* stats, int N,
+                        int H, int W, void* stream);
+int64_t b200unet_stem_wgrad_workspace(int N, int H, int W);
+int b200unet_stem_wgrad(const float* img_nchw, const void* dy, int64_t dy_pitch, float* dw_oihw, float* workspace,
+                        int64_t workspace_bytes, int N, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * InstanceNorm2d(eps, affine) + LeakyReLU(slope) + SpatialDropout2d, fused
+ * (unet.py:118-127, SpatialDropout2d.forward unet.py:22-35).
+ *   finalize: partials -> mean, rstd and the folded per-(n,c) affine  a = s*gamma*rstd, b = s*(beta - mean*gamma*rstd)
+ *             where s = drop_scale[n][c] in {0, 1/(1-p)} (NULL = 1).
+ *   apply   : z = leaky_relu(a*y + b)   (valid because s >= 0)
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_in_finalize(const float* stats, int P, const float* gamma, const float* beta, const float* drop_scale,
+                         float eps, float* mean, float* rstd, float* a, float* b, int N, int C, int64_t HW,
+                         void* stream);
+int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
+                      int64_t z_pitch, int N, int64_t HW, int C, void* stream);
+/* Backward (aten::native_batch_norm_backward + leaky_relu_backward + mul in the reference's autograd graph).
+ *   g  = (dz + dz2) * (a*y+b > 0 ? 1 : slope) * s ;  xh = (y - mean)*rstd
+ *   reduce  : partial sums of g and g*xh per (n,c)            -> part [N][P][C][2]
+ *   finalize: S1,S2 per (n,c); dgamma = sum_n S2, dbeta = sum_n S1; coef[N][C][3] = {gamma*rstd, S1/HW, S2/HW}
+ *   apply   : dy = coef0 * (g - coef1 - xh*coef2)
+ */
+int b200unet_in_bwd_partials(int64_t HW, int C);
+int b200unet_in_bwd_reduce(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch, const void* y,
+                           int64_t y_pitch, const float* a, const float* b, const float* mean, const float* rstd,
+                           const float* drop_scale, float slope, float* part, int N, int64_t HW, int C, void* stream);
+int b200unet_in_bwd_finalize(const float* part, int P, const float* gamma, const float* rstd, float* dgamma,
+                             float* dbeta, float* coef, int N, int C, int64_t HW, void* stream);
+int b200unet_in_bwd_apply(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch, const void* y,
+                          int64_t y_pitch, const float* a, const float* b, const float* mean, const float* rstd,
+                          const float* drop_scale, const float* coef, float slope, void* dy, int64_t dy_pitch, int N,
+                          int64_t HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Exact 2x bilinear upsampling, align_corners=False -- F.interpolate in UpBlock.forward (unet.py:219-225) --
+ * written straight into channels [0,C) of the concat buffer (pitch out_pitch), and its backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_upsample2x_fwd(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H, int W, int C,
+                            void* stream); /* H,W = input size; output is 2H x 2W */
+int b200unet_upsample2x_bwd(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H, int W,
+                            int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Segmentation head: 1x1 Conv2d(C -> K) + bias (unet.py:374-381, 430).  Reads bf16 NHWC, writes fp32 NCHW logits.
+ * Backward: dz (bf16 NHWC), dW [K][C], db [K] (two-stage deterministic reduction through `workspace`).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_head_fwd(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw, int N,
+                      int64_t HW, int C, int K, void* stream);
+int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K);
+int b200unet_head_bwd(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
+                      int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
+                      int64_t HW, int C, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SimpleLoss: weight_ce * CE(weight=w, ignore_index) + weight_dice * Dice, 3 classes
+ * (Our_UNet/models/losses.py:24-121).  One reduction pass over logits+target, one elementwise backward pass.
+ *   class_weights: NULL -> dynamic inverse-frequency weights (losses.py:24-62) when dynamic != 0, else uniform;
+ *                  non-NULL and dynamic == 0 -> static weights (device fp32 [3]).
+ *   loss_out[0] = total, [1] = CE, [2] = Dice.   tables: fp32 scratch [3 + 2*3*N] kept for the backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t b200unet_loss_workspace(int N, int64_t HW);
+int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target, const float* class_weights, int dynamic,
+                      float weight_ce, float weight_dice, int ignore_index, float smooth, float* loss_out,
+                      float* tables, float* workspace, int64_t workspace_bytes, int N, int64_t HW, void* stream);
+int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target, const float* tables, const float* grad_out,
+                      float weight_ce, float weight_dice, int ignore_index, float* dlogits_nchw, int N, int64_t HW,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout helpers used by the module-level (per-op) entry points and the tests.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int64_t dst_pitch, int N, int C, int64_t HW,
+                                   void* stream);
+int b200unet_nhwc_bf16_to_nchw_f32(const void* src, int64_t src_pitch, float* dst, int N, int C, int64_t HW,
+                                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UNET_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libb200unet.so (C ABI declared in include/b200unet.h).
+
+There is no fallback: if the shared library is missing or an entry point fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+
+_lib = None
+
+
+class ConvFpropArgs(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("x_pitch", c_int64), ("w", c_void_p), ("y", c_void_p), ("y_pitch", c_int64),
+        ("stats", c_void_p), ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
+        ("stride", c_int),
+    ]
+
+
+class ConvDgradArgs(Structure):
+    _fields_ = [
+        ("dy", c_void_p), ("dy_pitch", c_int64), ("wt", c_void_p), ("dx", c_void_p), ("dx_pitch", c_int64),
+        ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("stride", c_int),
+    ]
+
+
+class ConvWgradArgs(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("x_pitch", c_int64), ("dy", c_void_p), ("dy_pitch", c_int64), ("dw", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64), ("N", c_int), ("H", c_int), ("W", c_int),
+        ("Cin", c_int), ("Cout", c_int), ("stride", c_int),
+    ]
+
+
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+
+# name -> (restype, argtypes); restype c_int means "status code, raise on non-zero"
+SIGNATURES = {
+    "b200unet_version": (c_int, []),
+    "b200unet_last_error": (c_char_p, []),
+    "b200unet_device_ok": (c_int, []),
+    "b200unet_conv_fprop_partials": (c_int, [_I, _I]),
+    "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
+    "b200unet_conv_dgrad": (c_int, [POINTER(ConvDgradArgs), _P]),
+    "b200unet_conv_wgrad_workspace": (c_int64, [_I, _I, _I, _I, _I, _I]),
+    "b200unet_conv_wgrad": (c_int, [POINTER(ConvWgradArgs), _P]),
+    "b200unet_conv_fprop_simt": (c_int, [POINTER(ConvFpropArgs), _P]),
+    "b200unet_conv_dgrad_simt": (c_int, [POINTER(ConvDgradArgs), _P]),
+    "b200unet_conv_wgrad_simt": (c_int, [POINTER(ConvWgradArgs), _P]),
+    "b200unet_pack_conv_weights": (c_int, [_P, _P, _P, _I, _I, _P]),
+    "b200unet_stem_partials": (c_int, [_I, _I]),
+    "b200unet_stem_fprop": (c_int, [_P, _P, _P, _L, _P, _I, _I, _I, _P]),
+    "b200unet_stem_wgrad_workspace": (c_int64, [_I, _I, _I]),
+    "b200unet_stem_wgrad": (c_int, [_P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
+    "b200unet_in_finalize": (c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "b200unet_in_apply": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
+    "b200unet_in_bwd_partials": (c_int, [_L, _I]),
+    "b200unet_in_bwd_reduce": (c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _F, _P, _I, _L, _I, _P]),
+    "b200unet_in_bwd_finalize": (c_int, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "b200unet_in_bwd_apply": (c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
+    "b200unet_upsample2x_fwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_upsample2x_bwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_head_fwd": (c_int, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
+    "b200unet_head_bwd_workspace": (c_int64, [_I, _L, _I, _I]),
+    "b200unet_head_bwd": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
+    "b200unet_loss_workspace": (c_int64, [_I, _L]),
+    "b200unet_loss_fwd": (c_int, [_P, _P, _P, _I, _F, _F, _I, _F, _P, _P, _P, _L, _I, _L, _P]),
+    "b200unet_loss_bwd": (c_int, [_P, _P, _P, _P, _F, _F, _I, _P, _I, _L, _P]),
+    "b200unet_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
+    "b200unet_nhwc_bf16_to_nchw_f32": (c_int, [_P, _L, _P, _I, _I, _L, _P]),
+}
+
+# entry points that return a value rather than a status code
+_VALUE_FUNCS = {
+    "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_conv_fprop_partials",
+    "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
+    "b200unet_in_bwd_partials", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
+}
+
+
+def load():
+    """Load the shared library (once) and declare every signature.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"b200unet: {LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C unet-implementations_b200/csrc`). There is no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().b200unet_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def call(name: str, *args):
+    """Call a status-returning entry point; raise RuntimeError(last_error) on failure."""
+    fn = getattr(load(), name)
+    rc = fn(*args)
+    if name in _VALUE_FUNCS:
+        return rc
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    return 0

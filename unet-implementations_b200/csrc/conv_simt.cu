@@ -1,0 +1,365 @@
+// CUDA-core convolutions: (1) the Cin = 3 stem of encoder stage 0, which is HBM-bound and too narrow for the
+// tensor-core path, and (2) slow direct convolutions with the tensor-core kernels' exact argument structs,
+// used by the tests as an on-device cross-check and for channel counts outside the tcgen05 envelope.
+// Reference call sites: nn.Conv2d in ConvBlock, Our_UNet/models/unet.py:106-115.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------ weight packing
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * 9;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i enumerates the fprop pack [co][tap][ci] so its writes are coalesced
+  const int ci = static_cast<int>(i % Cin);
+  const int64_t r = i / Cin;
+  const int tap = static_cast<int>(r % 9);
+  const int co = static_cast<int>(r / 9);
+  const float v = w[(static_cast<int64_t>(co) * Cin + ci) * 9 + tap];
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  wf[i] = b;
+  if (wd) wd[(static_cast<int64_t>(ci) * 9 + tap) * Cout + co] = b;
+}
+
+// ------------------------------------------------------------------------------------------ generic stats
+// partial (sum, sumsq) of a bf16 NHWC tensor: block (p, n) covers pixels [p*chunk, (p+1)*chunk) of image n
+__global__ void stats_partial_kernel(const __nv_bfloat16* __restrict__ y, int64_t pitch, float* __restrict__ stats,
+                                     int P, int64_t HW, int C, int64_t chunk) {
+  const int p = blockIdx.x, n = blockIdx.y;
+  const int64_t lo = p * chunk;
+  int64_t hi = lo + chunk;
+  if (hi > HW) hi = HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t px = lo; px < hi; ++px) {
+      const float v = __bfloat162float(y[(n * HW + px) * pitch + c]);
+      s1 += v;
+      s2 += v * v;
+    }
+    float* d = stats + ((static_cast<int64_t>(n) * P + p) * C + c) * 2;
+    d[0] = s1;
+    d[1] = s2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ direct convs
+__global__ void conv_fprop_simt_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
+                                       const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int64_t yp,
+                                       int N, int H, int W, int Cin, int Cout, int s, int OH, int OW) {
+  const int64_t total = static_cast<int64_t>(N) * OH * OW * Cout;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % Cout);
+  int64_t r = i / Cout;
+  const int ow = static_cast<int>(r % OW);
+  r /= OW;
+  const int oh = static_cast<int>(r % OH);
+  const int n = static_cast<int>(r / OH);
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh * s + kh - 1;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = ow * s + kw - 1;
+      if (iw < 0 || iw >= W) continue;
+      const __nv_bfloat16* xr = x + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp;
+      const __nv_bfloat16* wr = w + (static_cast<int64_t>(co) * 9 + kh * 3 + kw) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(__bfloat162float(xr[ci]), __bfloat162float(wr[ci]), acc);
+    }
+  }
+  y[((static_cast<int64_t>(n) * OH + oh) * OW + ow) * yp + co] = __float2bfloat16_rn(acc);
+}
+
+__global__ void conv_dgrad_simt_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dyp,
+                                       const __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ dx,
+                                       int64_t dxp, int N, int H, int W, int Cin, int Cout, int s, int OH, int OW) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * Cin;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = static_cast<int>(i % Cin);
+  int64_t r = i / Cin;
+  const int iw = static_cast<int>(r % W);
+  r /= W;
+  const int ih = static_cast<int>(r % H);
+  const int n = static_cast<int>(r / H);
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = ih + 1 - kh;
+    if (th < 0 || th % s != 0) continue;
+    const int oh = th / s;
+    if (oh >= OH) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tw = iw + 1 - kw;
+      if (tw < 0 || tw % s != 0) continue;
+      const int ow = tw / s;
+      if (ow >= OW) continue;
+      const __nv_bfloat16* dr = dy + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * dyp;
+      const __nv_bfloat16* wr = wt + (static_cast<int64_t>(ci) * 9 + kh * 3 + kw) * Cout;
+      for (int co = 0; co < Cout; ++co) acc = fmaf(__bfloat162float(dr[co]), __bfloat162float(wr[co]), acc);
+    }
+  }
+  dx[((static_cast<int64_t>(n) * H + ih) * W + iw) * dxp + ci] = __float2bfloat16_rn(acc);
+}
+
+__global__ void conv_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
+                                       const __nv_bfloat16* __restrict__ dy, int64_t dyp, float* __restrict__ dw, int N,
+                                       int H, int W, int Cin, int Cout, int s, int OH, int OW) {
+  // one warp per (co, ci, tap); lanes stride over pixels, shuffle-reduce
+  const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * 9;
+  if (gw >= total) return;
+  const int tap = static_cast<int>(gw % 9);
+  const int64_t r = gw / 9;
+  const int ci = static_cast<int>(r % Cin);
+  const int co = static_cast<int>(r / Cin);
+  const int kh = tap / 3, kw = tap % 3;
+  float acc = 0.f;
+  const int64_t npx = static_cast<int64_t>(N) * OH * OW;
+  for (int64_t px = lane; px < npx; px += 32) {
+    const int ow = static_cast<int>(px % OW);
+    const int64_t q = px / OW;
+    const int oh = static_cast<int>(q % OH);
+    const int n = static_cast<int>(q / OH);
+    const int ih = oh * s + kh - 1, iw = ow * s + kw - 1;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+    acc = fmaf(__bfloat162float(dy[px * dyp + co]),
+               __bfloat162float(x[((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + ci]), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dw[gw] = acc;  // gw == (co*Cin + ci)*9 + tap, the OIHW offset
+}
+
+// ------------------------------------------------------------------------------------------ stem (Cin=3 -> 32)
+constexpr int kStemCo = 32;
+constexpr int kStemThreads = 256;
+
+__global__ void __launch_bounds__(kStemThreads) stem_fprop_kernel(const float* __restrict__ img,
+                                                                   const float* __restrict__ w_oihw,
+                                                                   __nv_bfloat16* __restrict__ y, int64_t yp,
+                                                                   float* __restrict__ stats, int P, int H, int W) {
+  __shared__ __align__(16) float wsm[27][kStemCo];  // [ci*9 + kh*3 + kw][co]
+  __shared__ float red[kStemThreads / 32][kStemCo][2];
+  const int n = blockIdx.y;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  for (int i = threadIdx.x; i < 27 * kStemCo; i += kStemThreads) {
+    const int co = i % kStemCo, k = i / kStemCo;
+    wsm[k][co] = w_oihw[co * 27 + k];
+  }
+  __syncthreads();
+  const int64_t px = static_cast<int64_t>(blockIdx.x) * kStemThreads + threadIdx.x;
+  const bool valid = px < HW;
+  float acc[kStemCo];
+#pragma unroll
+  for (int c = 0; c < kStemCo; ++c) acc[c] = 0.f;
+  if (valid) {
+    const int h = static_cast<int>(px / W), w = static_cast<int>(px % W);
+    const float* base = img + static_cast<int64_t>(n) * 3 * HW;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = w + kw - 1;
+          float v = 0.f;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(base + ci * HW + static_cast<int64_t>(ih) * W + iw);
+          const float4* wr = reinterpret_cast<const float4*>(wsm[ci * 9 + kh * 3 + kw]);
+#pragma unroll
+          for (int c4 = 0; c4 < kStemCo / 4; ++c4) {
+            const float4 ww = wr[c4];
+            acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
+            acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+          }
+        }
+      }
+    uint4* dst = reinterpret_cast<uint4*>(y + (static_cast<int64_t>(n) * HW + px) * yp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
+                          pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
+  }
+  if (stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float f[32], g[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float v = valid ? bf16_round(acc[c]) : 0.f;
+      f[c] = v;
+      g[c] = v * v;
+    }
+    red[warp][lane][0] = warp_colsum32(f, lane);
+    red[warp][lane][1] = warp_colsum32(g, lane);
+    __syncthreads();
+    if (threadIdx.x < kStemCo * 2) {
+      const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kStemThreads / 32; ++wv) s += red[wv][c][k];
+      stats[((static_cast<int64_t>(n) * P + blockIdx.x) * kStemCo + c) * 2 + k] = s;
+    }
+  }
+}
+
+// dW[co][ci][kh][kw] = sum dy[n,h,w,co] * img[n,ci,h+kh-1,w+kw-1].  lane = co; each block walks row segments of
+// kSegW pixels with the 3-row fp32 input patch staged in shared memory (broadcast reads), 27 accumulators per lane.
+constexpr int kSegW = 256;
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img,
+                                                          const __nv_bfloat16* __restrict__ dy, int64_t dyp,
+                                                          float* __restrict__ partial, int N, int H, int W) {
+  __shared__ float patch[3][3][kSegW + 2];
+  __shared__ float red[8][kStemCo][27];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int segs_w = (W + kSegW - 1) / kSegW;
+  const int64_t total_segs = static_cast<int64_t>(N) * H * segs_w;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  float acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+  for (int64_t seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
+    const int sw = static_cast<int>(seg % segs_w);
+    const int64_t r = seg / segs_w;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const int w0 = sw * kSegW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * (kSegW + 2); i += 256) {
+      const int col = i % (kSegW + 2);
+      const int rr = i / (kSegW + 2);  // ci*3 + kh
+      const int ci = rr / 3, kh = rr % 3;
+      const int ih = h + kh - 1, iw = w0 + col - 1;
+      float v = 0.f;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[(static_cast<int64_t>(n) * 3 + ci) * HW + static_cast<int64_t>(ih) * W + iw];
+      patch[ci][kh][col] = v;
+    }
+    __syncthreads();
+    const int wend = min(kSegW, W - w0);
+    for (int j = warp; j < wend; j += 8) {
+      const float d = __bfloat162float(dy[(static_cast<int64_t>(n) * HW + static_cast<int64_t>(h) * W + w0 + j) * dyp + lane]);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc[ci * 9 + kh * 3 + kw] = fmaf(d, patch[ci][kh][j + kw], acc[ci * 9 + kh * 3 + kw]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) red[warp][lane][k] = acc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kStemCo * 27; i += 256) {
+    const int co = i / 27, k = i % 27;
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][co][k];
+    partial[static_cast<int64_t>(blockIdx.x) * (kStemCo * 27) + i] = s;
+  }
+}
+
+__global__ void stem_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int blocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kStemCo * 27) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += partial[static_cast<int64_t>(b) * (kStemCo * 27) + i];
+  dw[i] = static_cast<float>(s);
+}
+
+static int stem_wgrad_blocks() { return num_sms() * 4; }
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200unet_pack_conv_weights(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin,
+                                          void* stream) {
+  B200_CHECK_ARG(w_oihw && w_fprop, "pack_conv_weights: null pointer");
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * 9;
+  pack_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), Cout, Cin);
+  B200_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop_simt: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_fprop_simt: stride %d unsupported", a->stride);
+  const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(a->N) * OH * OW * a->Cout;
+  conv_fprop_simt_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, static_cast<const __nv_bfloat16*>(a->w),
+      static_cast<__nv_bfloat16*>(a->y), a->y_pitch, a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  B200_LAUNCH_CHECK("conv_fprop_simt_kernel");
+  if (a->stats) {
+    const int P = b200unet_conv_fprop_partials(OH, OW);
+    const int64_t HW = static_cast<int64_t>(OH) * OW;
+    stats_partial_kernel<<<dim3(P, a->N), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->stats, P,
+                                                        HW, a->Cout, ceil_div64(HW, P));
+    B200_LAUNCH_CHECK("stats_partial_kernel");
+  }
+  return 0;
+}
+
+extern "C" int b200unet_conv_dgrad_simt(const b200unet_conv_dgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad_simt: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_dgrad_simt: stride %d unsupported", a->stride);
+  const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  const int64_t total = static_cast<int64_t>(a->N) * a->H * a->W * a->Cin;
+  conv_dgrad_simt_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, static_cast<const __nv_bfloat16*>(a->wt),
+      static_cast<__nv_bfloat16*>(a->dx), a->dx_pitch, a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  B200_LAUNCH_CHECK("conv_dgrad_simt_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->dy && a->dw, "conv_wgrad_simt: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_wgrad_simt: stride %d unsupported", a->stride);
+  const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  const int64_t warps = static_cast<int64_t>(a->Cout) * a->Cin * 9;
+  conv_wgrad_simt_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, a->dw,
+      a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  B200_LAUNCH_CHECK("conv_wgrad_simt_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_stem_partials(int H, int W) {
+  return static_cast<int>(ceil_div64(static_cast<int64_t>(H) * W, kStemThreads));
+}
+
+extern "C" int b200unet_stem_fprop(const float* img_nchw, const float* w_oihw, void* y, int64_t y_pitch, float* stats,
+                                   int N, int H, int W, void* stream) {
+  B200_CHECK_ARG(img_nchw && w_oihw && y, "stem_fprop: null pointer");
+  B200_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= kStemCo, "stem_fprop: bad output pitch");
+  const int P = b200unet_stem_partials(H, W);
+  stem_fprop_kernel<<<dim3(P, N), kStemThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      img_nchw, w_oihw, static_cast<__nv_bfloat16*>(y), y_pitch, stats, P, H, W);
+  B200_LAUNCH_CHECK("stem_fprop_kernel");
+  return 0;
+}
+
+extern "C" int64_t b200unet_stem_wgrad_workspace(int N, int H, int W) {
+  (void)N; (void)H; (void)W;
+  return static_cast<int64_t>(stem_wgrad_blocks()) * kStemCo * 27 * 4;
+}
+
+extern "C" int b200unet_stem_wgrad(const float* img_nchw, const void* dy, int64_t dy_pitch, float* dw_oihw,
+                                   float* workspace, int64_t workspace_bytes, int N, int H, int W, void* stream) {
+  B200_CHECK_ARG(img_nchw && dy && dw_oihw && workspace, "stem_wgrad: null pointer");
+  const int blocks = stem_wgrad_blocks();
+  B200_CHECK_ARG(workspace_bytes >= static_cast<int64_t>(blocks) * kStemCo * 27 * 4, "stem_wgrad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  stem_wgrad_kernel<<<blocks, 256, 0, st>>>(img_nchw, static_cast<const __nv_bfloat16*>(dy), dy_pitch, workspace, N, H, W);
+  B200_LAUNCH_CHECK("stem_wgrad_kernel");
+  stem_wgrad_finalize_kernel<<<ceil_div(kStemCo * 27, 256), 256, 0, st>>>(workspace, dw_oihw, blocks);
+  B200_LAUNCH_CHECK("stem_wgrad_finalize_kernel");
+  return 0;
+}

@@ -1,0 +1,738 @@
+// Implicit-GEMM 3x3 convolutions on tcgen05 / TMEM, operands staged by TMA (sm_100a only).
+//
+// Replaces nn.Conv2d forward and aten::convolution_backward for the ConvBlock convs of the reference
+// (Our_UNet/models/unet.py:106-115).  Activations are NHWC bf16, accumulation fp32 in tensor memory.
+//
+//  gconv_kernel  (fprop and dgrad):  D[128 pixels, BN] = sum over taps, channel chunks of
+//        A_tap[128 pixels, BK channels] (4-D TMA box of the shifted source, zero-filled outside the image = padding)
+//      x W[BN, tap*C + chunk]^T         (2-D TMA box of the packed K-major weight matrix).
+//      A 128-pixel tile is a TH x TW patch of one image of the output lattice.  Stride-2 fprop reads the four
+//      parity sub-lattices of the input through four tensor maps; stride-2 dgrad writes the four parity
+//      sub-lattices of dx through four launches (no scatter, no atomics).
+//  wgrad_kernel:  D[128 = (tap, ci) rows, BN = co] += X_tap^T[rows, 64 pixels] . dY[64 pixels, BN]
+//      both operands MN-major (channels contiguous in NHWC), K = pixels, split over CTAs, fp32 partials reduced
+//      deterministically by wgrad_finalize_kernel into the OIHW gradient.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> smem -> TMA store / global).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct Tap {
+  int map, dh, dw, koff;
+};
+
+struct GConvParams {
+  int N, OH, OW, tiles_w, tiles_h, TW, TH;
+  int ntaps;
+  Tap taps[9];
+  int cin;   // channels per tap on the K side (multiple of BK)
+  int cout;  // total N of the GEMM
+  float* stats;
+};
+
+struct GConvMaps {
+  CUtensorMap src[4];
+  CUtensorMap w;
+  CUtensorMap out;
+};
+
+constexpr int kConvThreads = 192;
+
+template <int BK, int BN, int STAGES>
+struct GConvCfg {
+  static constexpr int kABytes = 128 * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 128 * BN * 2;
+  static constexpr int kPipeBytes = STAGES * kStageBytes > kStagingBytes ? STAGES * kStageBytes : kStagingBytes;
+  static constexpr int kSmemBytes = kPipeBytes + 1024;  // + slack for manual 1024-byte alignment
+  static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
+  static constexpr uint32_t kSbo = 8 * BK * 2;  // 8 rows of BK bf16
+  static constexpr int kOC = BN >= 64 ? 64 : BN;  // channels per TMA-store box
+};
+
+template <int BK, int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads) gconv_kernel(const __grid_constant__ GConvMaps maps,
+                                                              const __grid_constant__ GConvParams p) {
+  using Cfg = GConvCfg<BK, BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+  __shared__ float red[4][BN][2];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  // tile coordinates
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int n_img = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - n_img * tiles_per_img;
+  const int th = t_in / p.tiles_w;
+  const int tw = t_in - th * p.tiles_w;
+  const int h0 = th * p.TH;
+  const int w0 = tw * p.TW;
+  const int n0 = blockIdx.y * BN;
+  const int chunks = p.cin / BK;
+  const int num_kb = p.ntaps * chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_holder, BN < 32 ? 32 : BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.w);
+      tma_prefetch_desc(&maps.src[0]);
+      int kb = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const Tap tap = p.taps[t];
+        for (int c = 0; c < chunks; ++c, ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          tma_load_4d(sa, &maps.src[tap.map], &full_bar[s], c * BK, w0 + tap.dw, h0 + tap.dh, n_img);
+          tma_load_2d(sa + Cfg::kABytes, &maps.w, &full_bar[s], tap.koff + c * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc(sa + k * 32, 16, Cfg::kSbo, Cfg::kSwz);
+          const uint64_t bdesc = umma_smem_desc(sb + k * 32, 16, Cfg::kSbo, Cfg::kSwz);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int r_h = row / p.TW;
+    const int r_w = row - r_h * p.TW;
+    const bool valid = (h0 + r_h < p.OH) && (w0 + r_w < p.OW);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const bool do_stats = p.stats != nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      // staging store (swizzled so that both these writes and the TMA read are conflict-free)
+      uint32_t base;
+      if (Cfg::kOC == 64) {
+        base = smem_u32(smem) + (c0 >> 6) * (128 * 128) + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cj = ((c0 & 63) >> 3) + i;
+          const uint32_t addr = base + (((cj ^ (row & 7)) & 7) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                       : "memory");
+        }
+      } else {
+        base = smem_u32(smem) + row * 64;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t addr = base + (((i ^ ((row >> 1) & 3)) & 3) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                       : "memory");
+        }
+      }
+      if (do_stats) {
+        // statistics of the values as stored (bf16-rounded), fp32 sums; rows outside the image contribute nothing
+        float f[32], g[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = valid ? bf16_round(__uint_as_float(v[j])) : 0.f;
+          f[j] = x;
+          g[j] = x * x;
+        }
+        const float s1 = warp_colsum32(f, lane);
+        const float s2 = warp_colsum32(g, lane);
+        red[q][c0 + lane][0] = s1;
+        red[q][c0 + lane][1] = s2;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    const int et = threadIdx.x - 64;  // 0..127
+    if (et == 0) {
+#pragma unroll
+      for (int jb = 0; jb < BN / Cfg::kOC; ++jb)
+        tma_store_4d(&maps.out, smem + jb * (128 * 128), n0 + jb * Cfg::kOC, w0, h0, n_img);
+      tma_store_commit();
+    }
+    if (do_stats) {
+      float* dst = p.stats + (static_cast<size_t>(n_img) * tiles_per_img + t_in) * p.cout * 2;
+      for (int c = et; c < BN; c += 128) {
+        const float s1 = (red[0][c][0] + red[1][c][0]) + (red[2][c][0] + red[3][c][0]);
+        const float s2 = (red[0][c][1] + red[1][c][1]) + (red[2][c][1] + red[3][c][1]);
+        reinterpret_cast<float2*>(dst)[n0 + c] = make_float2(s1, s2);
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- host side
+static void pick_patch(int OW, int* TW, int* TH) {
+  // 128-pixel patch; widest power-of-two width <= 16 keeps the halo small and divides every level of the UNet
+  (void)OW;
+  *TW = 16;
+  *TH = 8;
+}
+
+static int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int64_t pitch, int N, int H, int W, int C,
+                        int hstep, int wstep, int hoff, int woff, int boxC, int boxW, int boxH) {
+  // 4-D view (C, W', H', N) of the sub-lattice {(hoff + hstep*i, woff + wstep*j)} of an NHWC tensor
+  const int Hs = (H - hoff + hstep - 1) / hstep;
+  const int Ws = (W - woff + wstep - 1) / wstep;
+  if (Hs <= 0 || Ws <= 0) return set_error(kErrInvalid, "empty sub-lattice");
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)(wstep * pitch * 2), (uint64_t)(hstep * (int64_t)W * pitch * 2),
+                         (uint64_t)((int64_t)H * W * pitch * 2)};
+  uint32_t box[4] = {(uint32_t)boxC, (uint32_t)boxW, (uint32_t)boxH, 1};
+  const CUtensorMapSwizzle swz = (boxC * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (boxC * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swz == CU_TENSOR_MAP_SWIZZLE_NONE) return set_error(kErrInvalid, "box channel count %d unsupported", boxC);
+  return make_tmap_bf16(m, base + ((int64_t)hoff * W + woff) * pitch, 4, dims, strides, box, swz);
+}
+
+static int make_weight_map(CUtensorMap* m, const void* w, int rows, int K, int boxK, int boxRows) {
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)K * 2};
+  uint32_t box[2] = {(uint32_t)boxK, (uint32_t)boxRows};
+  return make_tmap_bf16(m, w, 2, dims, strides, box,
+                        boxK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+template <int BK, int BN, int STAGES>
+static int launch_gconv(const GConvMaps& maps, const GConvParams& p, cudaStream_t st) {
+  using Cfg = GConvCfg<BK, BN, STAGES>;
+  auto kern = gconv_kernel<BK, BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * p.N, p.cout / BN);
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("gconv_kernel");
+  return 0;
+}
+
+static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, int BN, cudaStream_t st) {
+#define GC(bk, bn, stg) \
+  if (BK == bk && BN == bn) return launch_gconv<bk, bn, stg>(maps, p, st);
+  GC(64, 256, 2)
+  GC(64, 128, 3)
+  GC(64, 64, 4)
+  GC(64, 32, 4)
+  GC(32, 256, 3)
+  GC(32, 128, 4)
+  GC(32, 64, 4)
+  GC(32, 32, 4)
+#undef GC
+  return set_error(kErrUnsupported, "no gconv instantiation for BK=%d BN=%d", BK, BN);
+}
+
+static int pick_bn(int n_total) {
+  if (n_total % 256 == 0) return 256;
+  if (n_total % 128 == 0) return 128;
+  if (n_total % 64 == 0) return 64;
+  if (n_total % 32 == 0) return 32;
+  return 0;
+}
+static int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 0); }
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200unet_conv_fprop_partials(int OH, int OW) {
+  int TW, TH;
+  pick_patch(OW, &TW, &TH);
+  return ceil_div(OW, TW) * ceil_div(OH, TH);
+}
+
+extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_fprop: stride %d unsupported", a->stride);
+  const int BK = pick_bk(a->Cin), BN = pick_bn(a->Cout);
+  if (!BK || !BN)
+    return set_error(kErrUnsupported, "conv_fprop: Cin=%d Cout=%d outside the tensor-core envelope (multiples of 32)",
+                     a->Cin, a->Cout);
+  B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->y_pitch % 8 == 0, "conv_fprop: pitches must be multiples of 8 elements");
+  const int s = a->stride;
+  const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  GConvParams p{};
+  GConvMaps maps;
+  pick_patch(OW, &p.TW, &p.TH);
+  p.N = a->N;
+  p.OH = OH;
+  p.OW = OW;
+  p.tiles_w = ceil_div(OW, p.TW);
+  p.tiles_h = ceil_div(OH, p.TH);
+  p.cin = a->Cin;
+  p.cout = a->Cout;
+  p.stats = a->stats;
+  p.ntaps = 9;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a->x);
+  int rc;
+  if (s == 1) {
+    if ((rc = make_act_map(&maps.src[0], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, BK, p.TW, p.TH))) return rc;
+    maps.src[1] = maps.src[2] = maps.src[3] = maps.src[0];
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = Tap{0, kh - 1, kw - 1, (kh * 3 + kw) * a->Cin};
+  } else {
+    B200_CHECK_ARG(a->H >= 2 && a->W >= 2, "conv_fprop: stride-2 input must be at least 2x2");
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp)
+        if ((rc = make_act_map(&maps.src[hp * 2 + wp], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 2, 2, hp, wp, BK, p.TW,
+                               p.TH)))
+          return rc;
+    // input row 2*oh + kh - 1:  kh=0 -> parity 1, index oh-1;  kh=1 -> parity 0, index oh;  kh=2 -> parity 1, index oh
+    const int par[3] = {1, 0, 1}, sh[3] = {-1, 0, 0};
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        p.taps[kh * 3 + kw] = Tap{par[kh] * 2 + par[kw], sh[kh], sh[kw], (kh * 3 + kw) * a->Cin};
+  }
+  if ((rc = make_weight_map(&maps.w, a->w, a->Cout, 9 * a->Cin, BK, BN))) return rc;
+  const int OC = BN >= 64 ? 64 : BN;
+  if ((rc = make_act_map(&maps.out, static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->N, OH, OW, a->Cout, 1, 1, 0,
+                         0, OC, p.TW, p.TH)))
+    return rc;
+  return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_dgrad: stride %d unsupported", a->stride);
+  // GEMM: M = input pixels, N = Cin, K = taps * Cout
+  const int BK = pick_bk(a->Cout), BN = pick_bn(a->Cin);
+  if (!BK || !BN)
+    return set_error(kErrUnsupported, "conv_dgrad: Cin=%d Cout=%d outside the tensor-core envelope", a->Cin, a->Cout);
+  B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad: pitches must be multiples of 8 elements");
+  const int s = a->stride;
+  const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);
+  const __nv_bfloat16* dx = static_cast<const __nv_bfloat16*>(a->dx);
+  const int OC = BN >= 64 ? 64 : BN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  GConvMaps maps;
+  if ((rc = make_weight_map(&maps.w, a->wt, a->Cin, 9 * a->Cout, BK, BN))) return rc;
+  if (s == 1) {
+    GConvParams p{};
+    pick_patch(a->W, &p.TW, &p.TH);
+    p.N = a->N;
+    p.OH = a->H;
+    p.OW = a->W;
+    p.tiles_w = ceil_div(a->W, p.TW);
+    p.tiles_h = ceil_div(a->H, p.TH);
+    p.cin = a->Cout;
+    p.cout = a->Cin;
+    p.stats = nullptr;
+    p.ntaps = 9;
+    if ((rc = make_act_map(&maps.src[0], dy, a->dy_pitch, a->N, OH, OW, a->Cout, 1, 1, 0, 0, BK, p.TW, p.TH))) return rc;
+    maps.src[1] = maps.src[2] = maps.src[3] = maps.src[0];
+    // dx[ih,iw] += dy[ih + 1 - kh, iw + 1 - kw] * W[kh,kw]
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = Tap{0, 1 - kh, 1 - kw, (kh * 3 + kw) * a->Cout};
+    if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, p.TW, p.TH))) return rc;
+    return dispatch_gconv(maps, p, BK, BN, st);
+  }
+  // stride 2: one launch per parity class (ph,pw) of the input pixel; ih = 2a + ph receives
+  //   ph = 0: kh = 1 from oh = a;      ph = 1: kh = 0 from oh = a + 1 and kh = 2 from oh = a   (same along w)
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int Hs = (a->H - ph + 1) / 2, Ws = (a->W - pw + 1) / 2;
+      if (Hs <= 0 || Ws <= 0) continue;
+      GConvParams p{};
+      pick_patch(Ws, &p.TW, &p.TH);
+      p.N = a->N;
+      p.OH = Hs;
+      p.OW = Ws;
+      p.tiles_w = ceil_div(Ws, p.TW);
+      p.tiles_h = ceil_div(Hs, p.TH);
+      p.cin = a->Cout;
+      p.cout = a->Cin;
+      p.stats = nullptr;
+      if ((rc = make_act_map(&maps.src[0], dy, a->dy_pitch, a->N, OH, OW, a->Cout, 1, 1, 0, 0, BK, p.TW, p.TH)))
+        return rc;
+      maps.src[1] = maps.src[2] = maps.src[3] = maps.src[0];
+      int khs[2], dhs[2], nkh, kws[2], dws[2], nkw;
+      if (ph == 0) { nkh = 1; khs[0] = 1; dhs[0] = 0; } else { nkh = 2; khs[0] = 0; dhs[0] = 1; khs[1] = 2; dhs[1] = 0; }
+      if (pw == 0) { nkw = 1; kws[0] = 1; dws[0] = 0; } else { nkw = 2; kws[0] = 0; dws[0] = 1; kws[1] = 2; dws[1] = 0; }
+      p.ntaps = 0;
+      for (int i = 0; i < nkh; ++i)
+        for (int j = 0; j < nkw; ++j) p.taps[p.ntaps++] = Tap{0, dhs[i], dws[j], (khs[i] * 3 + kws[j]) * a->Cout};
+      if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, OC, p.TW, p.TH)))
+        return rc;
+      if ((rc = dispatch_gconv(maps, p, BK, BN, st))) return rc;
+    }
+  return 0;
+}
+
+// ====================================================================================================== wgrad
+namespace b200 {
+
+struct WTap {
+  int map, dh, dw;
+};
+
+struct WgradParams {
+  int N, OH, OW, blocks_w, blocks_h, TWk, THk;
+  int total_kb, kb_per_split;
+  WTap taps[9];
+  int cin, cout;
+  int units_per_tap, total_units;
+  int G;  // M-groups (of 128 rows) per CTA
+  float* partial;  // [S][9][cin][cout]
+};
+
+struct WgradMaps {
+  CUtensorMap src[4];
+  CUtensorMap dy;
+};
+
+constexpr int kWgStages = 3;
+
+// U  = channels per unit on the M side (64 -> 128B-swizzled blocks, 32 -> 64B-swizzled blocks)
+// BN = output-channel tile (N side); 32 uses one 64B-swizzled block, otherwise BN/64 128B-swizzled blocks
+template <int U, int BN>
+__global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_constant__ WgradMaps maps,
+                                                                 const __grid_constant__ WgradParams p) {
+  constexpr int UPG = 128 / U;                      // units per M-group
+  constexpr int kUnitBytes = 64 * U * 2;            // 64 pixels x U channels
+  constexpr int kGroupBytes = UPG * kUnitBytes;     // 16 KB
+  constexpr int kDyBlockCh = BN >= 64 ? 64 : BN;    // channels per dY block
+  constexpr int kDyBlocks = BN / kDyBlockCh;
+  constexpr int kDyBlockBytes = 64 * kDyBlockCh * 2;
+  constexpr int kDyBytes = kDyBlocks * kDyBlockBytes;
+  constexpr uint32_t kSwzA = (U == 64) ? kSwz128 : kSwz64;
+  constexpr uint32_t kSwzB = (kDyBlockCh == 64) ? kSwz128 : kSwz64;
+  constexpr uint32_t kRowA = U * 2, kRowB = kDyBlockCh * 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWgStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int G = p.G;
+  const int stage_bytes = kDyBytes + G * kGroupBytes;
+  const int split = blockIdx.x;
+  const int group0 = blockIdx.y * G;
+  const int n0 = blockIdx.z * BN;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  const int num_kb = kb_end - kb_begin;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(G * BN)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_holder, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  // units of this CTA that exist (the last group of a layer may be partially filled)
+  int valid_units = p.total_units - group0 * UPG;
+  if (valid_units > G * UPG) valid_units = G * UPG;
+  if (valid_units < 0) valid_units = 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int blocks_per_img = p.blocks_w * p.blocks_h;
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb_begin + i;
+        const int n_img = kb / blocks_per_img;
+        const int b_in = kb - n_img * blocks_per_img;
+        const int bh = b_in / p.blocks_w;
+        const int bw = b_in - bh * p.blocks_w;
+        const int h0 = bh * p.THk, w0 = bw * p.TWk;
+        const int s = i % kWgStages;
+        const uint32_t ph = (i / kWgStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], kDyBytes + valid_units * kUnitBytes);
+        uint8_t* sb = smem + s * stage_bytes;
+#pragma unroll
+        for (int jb = 0; jb < kDyBlocks; ++jb)
+          tma_load_4d(sb + jb * kDyBlockBytes, &maps.dy, &full_bar[s], n0 + jb * kDyBlockCh, w0, h0, n_img);
+        for (int u = 0; u < valid_units; ++u) {
+          const int unit = group0 * UPG + u;
+          const int tap = unit / p.units_per_tap;
+          const int c0 = (unit - tap * p.units_per_tap) * U;
+          const WTap t = p.taps[tap];
+          tma_load_4d(sb + kDyBytes + u * kUnitBytes, &maps.src[t.map], &full_bar[s], c0, w0 + t.dw, h0 + t.dh, n_img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      const int groups = (valid_units + UPG - 1) / UPG;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kWgStages;
+        const uint32_t ph = (i / kWgStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + s * stage_bytes);
+        for (int g = 0; g < groups; ++g) {
+          const uint32_t sa = sb + kDyBytes + g * kGroupBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major canonical layout: LBO = byte stride between channel blocks, SBO = 8 pixel rows
+            const uint64_t adesc = umma_smem_desc(sa + k * 16 * kRowA, kUnitBytes, 8 * kRowA, kSwzA);
+            const uint64_t bdesc = umma_smem_desc(sb + k * 16 * kRowB, kDyBlockBytes, 8 * kRowB, kSwzB);
+            umma_bf16(tmem_base + g * BN, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const int groups = (valid_units + UPG - 1) / UPG;
+    for (int g = 0; g < groups; ++g) {
+      const int u = g * UPG + row / U;
+      const int unit = group0 * UPG + u;
+      const bool uvalid = u < valid_units;
+      int tap = 0, ci = 0;
+      if (uvalid) {
+        tap = unit / p.units_per_tap;
+        ci = (unit - tap * p.units_per_tap) * U + (row % U);
+      }
+      float* dst = p.partial + ((static_cast<size_t>(split) * 9 + tap) * p.cin + ci) * p.cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        if (num_kb > 0) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        }
+        if (uvalid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dw[co][ci][tap] = sum_s partial[s][tap][ci][co]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int cin,
+                                      int cout) {
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % cout);
+  const int64_t r = i / cout;
+  const int ci = static_cast<int>(r % cin);
+  const int tap = static_cast<int>(r / cin);
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += partial[static_cast<int64_t>(s) * total + i];
+  dw[(static_cast<int64_t>(co) * cin + ci) * 9 + tap] = acc;
+}
+
+struct WgradPlan {
+  int U, BN, G, S, gy, gz, total_kb, kb_per_split, TWk, THk, blocks_w, blocks_h, OH, OW;
+  int64_t smem_bytes, partial_floats;
+};
+
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int stride, WgradPlan* pl) {
+  pl->U = pick_bk(Cin);
+  pl->BN = pick_bn(Cout);
+  if (!pl->U || !pl->BN) return set_error(kErrUnsupported, "conv_wgrad: Cin=%d Cout=%d outside the envelope", Cin, Cout);
+  pl->OH = (H - 1) / stride + 1;
+  pl->OW = (W - 1) / stride + 1;
+  pl->TWk = 16;
+  pl->THk = 4;
+  pl->blocks_w = ceil_div(pl->OW, pl->TWk);
+  pl->blocks_h = ceil_div(pl->OH, pl->THk);
+  pl->total_kb = N * pl->blocks_w * pl->blocks_h;
+  const int upg = 128 / pl->U;
+  const int total_units = 9 * (Cin / pl->U);
+  const int groups_total = ceil_div(total_units, upg);
+  int G = 512 / pl->BN;
+  const int dy_bytes = 64 * pl->BN * 2;
+  const int gsm = (70 * 1024 - dy_bytes) / 16384;  // keep a stage under ~70 KB so three stages fit
+  if (G > gsm) G = gsm;
+  if (G > groups_total) G = groups_total;
+  if (G < 1) G = 1;
+  pl->G = G;
+  pl->gy = ceil_div(groups_total, G);
+  pl->gz = Cout / pl->BN;
+  const int base_ctas = pl->gy * pl->gz;
+  int S = ceil_div(num_sms(), base_ctas);
+  if (S > pl->total_kb) S = pl->total_kb;
+  if (S < 1) S = 1;
+  pl->kb_per_split = ceil_div(pl->total_kb, S);
+  pl->S = ceil_div(pl->total_kb, pl->kb_per_split);
+  pl->smem_bytes = static_cast<int64_t>(kWgStages) * (dy_bytes + G * 16384) + 1024;
+  pl->partial_floats = static_cast<int64_t>(pl->S) * 9 * Cin * Cout;
+  return 0;
+}
+
+template <int U, int BN>
+static int launch_wgrad(const WgradMaps& maps, const WgradParams& p, const WgradPlan& pl, cudaStream_t st) {
+  auto kern = wgrad_kernel<U, BN>;
+  static int attr_bytes = 0;
+  if (attr_bytes < pl.smem_bytes) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    attr_bytes = (int)pl.smem_bytes;
+  }
+  dim3 grid(pl.S, pl.gy, pl.gz);
+  kern<<<grid, kConvThreads, pl.smem_bytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("wgrad_kernel");
+  return 0;
+}
+
+}  // namespace b200
+
+extern "C" int64_t b200unet_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int stride) {
+  WgradPlan pl;
+  if (plan_wgrad(N, H, W, Cin, Cout, stride, &pl)) return -1;
+  return pl.partial_floats * 4;
+}
+
+extern "C" int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_wgrad: stride %d unsupported", a->stride);
+  B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_wgrad: pitches must be multiples of 8 elements");
+  WgradPlan pl;
+  int rc;
+  if ((rc = plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->stride, &pl))) return rc;
+  B200_CHECK_ARG(a->workspace_bytes >= pl.partial_floats * 4, "conv_wgrad: workspace too small (%lld < %lld)",
+                 (long long)a->workspace_bytes, (long long)(pl.partial_floats * 4));
+  WgradParams p{};
+  WgradMaps maps;
+  p.N = a->N;
+  p.OH = pl.OH;
+  p.OW = pl.OW;
+  p.blocks_w = pl.blocks_w;
+  p.blocks_h = pl.blocks_h;
+  p.TWk = pl.TWk;
+  p.THk = pl.THk;
+  p.total_kb = pl.total_kb;
+  p.kb_per_split = pl.kb_per_split;
+  p.cin = a->Cin;
+  p.cout = a->Cout;
+  p.units_per_tap = a->Cin / pl.U;
+  p.total_units = 9 * p.units_per_tap;
+  p.G = pl.G;
+  p.partial = a->workspace;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a->x);
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);
+  if (a->stride == 1) {
+    if ((rc = make_act_map(&maps.src[0], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, pl.U, pl.TWk, pl.THk)))
+      return rc;
+    maps.src[1] = maps.src[2] = maps.src[3] = maps.src[0];
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = WTap{0, kh - 1, kw - 1};
+  } else {
+    B200_CHECK_ARG(a->H >= 2 && a->W >= 2, "conv_wgrad: stride-2 input must be at least 2x2");
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp)
+        if ((rc = make_act_map(&maps.src[hp * 2 + wp], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 2, 2, hp, wp, pl.U,
+                               pl.TWk, pl.THk)))
+          return rc;
+    const int par[3] = {1, 0, 1}, sh[3] = {-1, 0, 0};
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = WTap{par[kh] * 2 + par[kw], sh[kh], sh[kw]};
+  }
+  const int dyc = pl.BN >= 64 ? 64 : pl.BN;
+  if ((rc = make_act_map(&maps.dy, dy, a->dy_pitch, a->N, pl.OH, pl.OW, a->Cout, 1, 1, 0, 0, dyc, pl.TWk, pl.THk)))
+    return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define WG(u, bn) \
+  if (pl.U == u && pl.BN == bn) rc = launch_wgrad<u, bn>(maps, p, pl, st); else
+  WG(64, 256) WG(64, 128) WG(64, 64) WG(64, 32) WG(32, 256) WG(32, 128) WG(32, 64) WG(32, 32)
+  rc = set_error(kErrUnsupported, "no wgrad instantiation for U=%d BN=%d", pl.U, pl.BN);
+#undef WG
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(9) * a->Cin * a->Cout;
+  wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(a->workspace, a->dw, pl.S, a->Cin, a->Cout);
+  B200_LAUNCH_CHECK("wgrad_finalize_kernel");
+  return 0;
+}

@@ -1,0 +1,385 @@
+// Segmentation head (1x1 conv, unet.py:374-381) and SimpleLoss (Our_UNet/models/losses.py:24-121).
+//
+// Loss forward is ONE pass over (logits fp32 NCHW, target int64): per pixel softmax over 3 classes, accumulating
+//   n_c      = #valid pixels of class c                       (class weights, losses.py:36-60)
+//   S_c      = sum_{valid, t=c} -log p_t                       (weighted CE numerator, nn.CrossEntropyLoss)
+//   I_bc, P_bc = sum p_c [t=c], sum p_c over valid pixels      (Dice, losses.py:98-113)
+// per block, then a one-block finalize reduces in fixed order (double) and emits the loss and the small tables the
+// elementwise backward needs.  Nothing synchronises with the host (the reference's three `if class_pixels[c] == 0`
+// host syncs at losses.py:53 become a device-side clamp).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kNC = 3;            // classes (losses.py:40 hard-codes 3)
+constexpr int kLossThreads = 256;
+constexpr int kLossPxPerThread = 8;
+constexpr int kLossVals = 4 * kNC;  // per block: cnt[3], S[3], I[3], P[3]
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  // deterministic: shuffle tree inside the warp, then warp 0 sums the warp results in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += scratch[w];
+  return s;  // valid on thread 0
+}
+
+// grid (blocks_per_image, N)
+__global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(const float* __restrict__ logits,
+                                                                 const int64_t* __restrict__ target, int ignore_index,
+                                                                 float* __restrict__ part, int64_t HW) {
+  __shared__ float scratch[kLossThreads / 32];
+  const int n = blockIdx.y;
+  const float* z0 = logits + static_cast<int64_t>(n) * kNC * HW;
+  const int64_t* tg = target + static_cast<int64_t>(n) * HW;
+  float cnt[kNC] = {0.f, 0.f, 0.f}, S[kNC] = {0.f, 0.f, 0.f}, I[kNC] = {0.f, 0.f, 0.f}, Pp[kNC] = {0.f, 0.f, 0.f};
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kLossThreads * kLossPxPerThread;
+#pragma unroll
+  for (int k = 0; k < kLossPxPerThread; ++k) {
+    const int64_t px = base + static_cast<int64_t>(k) * kLossThreads + threadIdx.x;
+    if (px >= HW) continue;
+    const int64_t t = tg[px];
+    if (t == ignore_index) continue;
+    const float a0 = z0[px], a1 = z0[HW + px], a2 = z0[2 * HW + px];
+    const float m = fmaxf(a0, fmaxf(a1, a2));
+    const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+    const float se = e0 + e1 + e2;
+    const float inv = 1.f / se;
+    const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+    const float lse = m + logf(se);
+    Pp[0] += p0;
+    Pp[1] += p1;
+    Pp[2] += p2;
+    if (t == 0) { cnt[0] += 1.f; S[0] += lse - a0; I[0] += p0; }
+    else if (t == 1) { cnt[1] += 1.f; S[1] += lse - a1; I[1] += p1; }
+    else if (t == 2) { cnt[2] += 1.f; S[2] += lse - a2; I[2] += p2; }
+  }
+  float* dst = part + (static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * kLossVals;
+#pragma unroll
+  for (int c = 0; c < kNC; ++c) {
+    float v;
+    v = block_sum(cnt[c], scratch); if (threadIdx.x == 0) dst[c] = v;
+    v = block_sum(S[c], scratch);   if (threadIdx.x == 0) dst[kNC + c] = v;
+    v = block_sum(I[c], scratch);   if (threadIdx.x == 0) dst[2 * kNC + c] = v;
+    v = block_sum(Pp[c], scratch);  if (threadIdx.x == 0) dst[3 * kNC + c] = v;
+  }
+}
+
+// tables layout: [0..2] = w_c / W (CE weight over normaliser); then per image b: A[b][3], Bq[b][3]
+//   dDice/dp_{ic} = A_bc*[t_i=c] + Bq_bc  for valid pixels, with
+//   A = -(2/(C*B)) / (U+eps),  Bq = (1/(C*B)) * (2I+eps) / (U+eps)^2,  U = P + T
+__global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks, const float* __restrict__ class_w,
+                                     int dynamic, float weight_ce, float weight_dice, float smooth,
+                                     float* __restrict__ loss_out, float* __restrict__ tables, int N) {
+  // one block; thread (b*12 + v) reduces value v of image b
+  extern __shared__ double sred[];  // [N][12]
+  for (int i = threadIdx.x; i < N * kLossVals; i += blockDim.x) {
+    const int b = i / kLossVals, v = i - b * kLossVals;
+    double s = 0.0;
+    for (int k = 0; k < blocks; ++k) s += part[(static_cast<int64_t>(b) * blocks + k) * kLossVals + v];
+    sred[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double cnt[kNC] = {0, 0, 0}, S[kNC] = {0, 0, 0};
+  for (int b = 0; b < N; ++b)
+    for (int c = 0; c < kNC; ++c) {
+      cnt[c] += sred[b * kLossVals + c];
+      S[c] += sred[b * kLossVals + kNC + c];
+    }
+  // class weights (fp32 arithmetic mirrors losses.py:44-60)
+  float w[kNC];
+  if (class_w && !dynamic) {
+    for (int c = 0; c < kNC; ++c) w[c] = class_w[c];
+  } else if (dynamic) {
+    const float total = static_cast<float>(cnt[0] + cnt[1] + cnt[2]);
+    float wsum = 0.f;
+    for (int c = 0; c < kNC; ++c) {
+      const float px = cnt[c] == 0.0 ? 1.f : static_cast<float>(cnt[c]);
+      w[c] = total / px;
+      wsum += w[c];
+    }
+    for (int c = 0; c < kNC; ++c) w[c] = w[c] * (static_cast<float>(kNC) / wsum);
+  } else {
+    for (int c = 0; c < kNC; ++c) w[c] = 1.f;
+  }
+  double num = 0.0, den = 0.0;
+  for (int c = 0; c < kNC; ++c) {
+    num += static_cast<double>(w[c]) * S[c];
+    den += static_cast<double>(w[c]) * cnt[c];
+  }
+  const double ce = num / den;  // 0/0 -> NaN, like nn.CrossEntropyLoss on an all-ignored batch
+  double dice_loss = 0.0;
+  for (int c = 0; c < kNC; ++c) {
+    double dsum = 0.0;
+    for (int b = 0; b < N; ++b) {
+      const double T = sred[b * kLossVals + c];
+      const double I = sred[b * kLossVals + 2 * kNC + c];
+      const double Pc = sred[b * kLossVals + 3 * kNC + c];
+      const double U = Pc + T + smooth;
+      const double two_i = 2.0 * I + smooth;
+      dsum += two_i / U;
+      tables[kNC + (b * 2 + 0) * kNC + c] = static_cast<float>(-(2.0 / (kNC * static_cast<double>(N))) / U);
+      tables[kNC + (b * 2 + 1) * kNC + c] = static_cast<float>((1.0 / (kNC * static_cast<double>(N))) * two_i / (U * U));
+    }
+    dice_loss += 1.0 - dsum / N;
+  }
+  dice_loss /= kNC;
+  for (int c = 0; c < kNC; ++c) tables[c] = static_cast<float>(w[c] / den);
+  loss_out[0] = static_cast<float>(weight_ce * ce + weight_dice * dice_loss);
+  loss_out[1] = static_cast<float>(ce);
+  loss_out[2] = static_cast<float>(dice_loss);
+}
+
+__global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const float* __restrict__ logits,
+                                                                 const int64_t* __restrict__ target,
+                                                                 const float* __restrict__ tables,
+                                                                 const float* __restrict__ grad_out, float weight_ce,
+                                                                 float weight_dice, int ignore_index,
+                                                                 float* __restrict__ dlogits, int64_t HW) {
+  const int n = blockIdx.y;
+  const float gs = grad_out ? grad_out[0] : 1.f;
+  const float wn0 = tables[0], wn1 = tables[1], wn2 = tables[2];
+  const float* tb = tables + kNC + n * 2 * kNC;
+  const float A0 = tb[0], A1 = tb[1], A2 = tb[2], B0 = tb[3], B1 = tb[4], B2 = tb[5];
+  const float* z0 = logits + static_cast<int64_t>(n) * kNC * HW;
+  float* d0 = dlogits + static_cast<int64_t>(n) * kNC * HW;
+  const int64_t* tg = target + static_cast<int64_t>(n) * HW;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kLossThreads * kLossPxPerThread;
+#pragma unroll
+  for (int k = 0; k < kLossPxPerThread; ++k) {
+    const int64_t px = base + static_cast<int64_t>(k) * kLossThreads + threadIdx.x;
+    if (px >= HW) continue;
+    const int64_t t = tg[px];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (t != ignore_index) {
+      const float a0 = z0[px], a1 = z0[HW + px], a2 = z0[2 * HW + px];
+      const float m = fmaxf(a0, fmaxf(a1, a2));
+      const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+      const float inv = 1.f / (e0 + e1 + e2);
+      const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+      const float wt = t == 0 ? wn0 : (t == 1 ? wn1 : (t == 2 ? wn2 : 0.f));
+      // dDice/dp_c
+      const float G0 = B0 + (t == 0 ? A0 : 0.f), G1 = B1 + (t == 1 ? A1 : 0.f), G2 = B2 + (t == 2 ? A2 : 0.f);
+      const float gp = G0 * p0 + G1 * p1 + G2 * p2;
+      g0 = weight_ce * wt * (p0 - (t == 0 ? 1.f : 0.f)) + weight_dice * p0 * (G0 - gp);
+      g1 = weight_ce * wt * (p1 - (t == 1 ? 1.f : 0.f)) + weight_dice * p1 * (G1 - gp);
+      g2 = weight_ce * wt * (p2 - (t == 2 ? 1.f : 0.f)) + weight_dice * p2 * (G2 - gp);
+    }
+    d0[px] = g0 * gs;
+    d0[HW + px] = g1 * gs;
+    d0[2 * HW + px] = g2 * gs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head
+constexpr int kHeadMaxC = 64;
+constexpr int kHeadMaxK = 4;
+
+// one thread per pixel: logits[k] = b[k] + sum_c W[k][c] * z[c]
+template <int C, int K>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ z, int64_t zp,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ logits, int64_t HW) {
+  __shared__ float ws[K][C];
+  __shared__ float bs[K];
+  for (int i = threadIdx.x; i < K * C; i += 256) ws[i / C][i % C] = w[i];
+  if (threadIdx.x < K) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (px >= HW) return;
+  const uint4* src = reinterpret_cast<const uint4*>(z + (static_cast<int64_t>(n) * HW + px) * zp);
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = bs[k];
+#pragma unroll
+  for (int j = 0; j < C / 8; ++j) {
+    const uint4 u = src[j];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        acc[k] = fmaf(ws[k][8 * j + 2 * i], t.x, acc[k]);
+        acc[k] = fmaf(ws[k][8 * j + 2 * i + 1], t.y, acc[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) logits[(static_cast<int64_t>(n) * K + k) * HW + px] = acc[k];
+}
+
+// grid-stride over pixels; thread accumulates dW[K][C] and db[K] privately, block-reduces, writes one partial row.
+template <int C, int K>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ z,
+                                                        int64_t zp, const float* __restrict__ w,
+                                                        __nv_bfloat16* __restrict__ dz, int64_t dzp,
+                                                        float* __restrict__ partial, int N, int64_t HW) {
+  __shared__ float ws[K][C];
+  __shared__ float red[8][K * C + K];
+  for (int i = threadIdx.x; i < K * C; i += 256) ws[i / C][i % C] = w[i];
+  __syncthreads();
+  float aw[K][C];
+  float ab[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ab[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) aw[k][c] = 0.f;
+  }
+  const int64_t total = static_cast<int64_t>(N) * HW;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * 256) {
+    const int n = static_cast<int>(g / HW);
+    const int64_t px = g - static_cast<int64_t>(n) * HW;
+    float d[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      d[k] = dl[(static_cast<int64_t>(n) * K + k) * HW + px];
+      ab[k] += d[k];
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(z + g * zp);
+    uint4* dst = reinterpret_cast<uint4*>(dz + g * dzp);
+#pragma unroll
+    for (int j = 0; j < C / 8; ++j) {
+      const uint4 u = src[j];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      float zf[8], o[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        zf[2 * i] = t.x;
+        zf[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          s = fmaf(ws[k][8 * j + i], d[k], s);
+          aw[k][8 * j + i] = fmaf(d[k], zf[i], aw[k][8 * j + i]);
+        }
+        o[i] = s;
+      }
+      dst[j] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                          pack_bf16x2(o[6], o[7]));
+    }
+  }
+  // block reduction: shuffle tree per value, then across the 8 warps in order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float v = aw[k][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][k * C + c] = v;
+    }
+    float v = ab[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][K * C + k] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C + K; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
+    partial[static_cast<int64_t>(blockIdx.x) * (K * C + K) + i] = s;
+  }
+}
+
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int KC, int K,
+                                         float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KC + K) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += partial[static_cast<int64_t>(b) * (KC + K) + i];
+  if (i < KC) dw[i] = static_cast<float>(s);
+  else db[i - KC] = static_cast<float>(s);
+}
+
+static int head_bwd_blocks() { return num_sms() * 4; }
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200unet_loss_workspace(int N, int64_t HW) {
+  const int64_t blocks = ceil_div64(HW, kLossThreads * kLossPxPerThread);
+  return static_cast<int64_t>(N) * blocks * kLossVals * 4;
+}
+
+extern "C" int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target, const float* class_weights,
+                                 int dynamic, float weight_ce, float weight_dice, int ignore_index, float smooth,
+                                 float* loss_out, float* tables, float* workspace, int64_t workspace_bytes, int N,
+                                 int64_t HW, void* stream) {
+  B200_CHECK_ARG(logits_nchw && target && loss_out && tables && workspace, "loss_fwd: null pointer");
+  B200_CHECK_ARG(N > 0 && HW > 0, "loss_fwd: empty batch");
+  B200_CHECK_ARG(workspace_bytes >= b200unet_loss_workspace(N, HW), "loss_fwd: workspace too small");
+  const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  loss_fwd_kernel<<<dim3(blocks, N), kLossThreads, 0, st>>>(logits_nchw, target, ignore_index, workspace, HW);
+  B200_LAUNCH_CHECK("loss_fwd_kernel");
+  const size_t smem = static_cast<size_t>(N) * kLossVals * sizeof(double);
+  B200_CHECK_ARG(smem <= 48 * 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
+  loss_finalize_kernel<<<1, 256, smem, st>>>(workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
+                                             loss_out, tables, N);
+  B200_LAUNCH_CHECK("loss_finalize_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target, const float* tables,
+                                 const float* grad_out, float weight_ce, float weight_dice, int ignore_index,
+                                 float* dlogits_nchw, int N, int64_t HW, void* stream) {
+  B200_CHECK_ARG(logits_nchw && target && tables && dlogits_nchw, "loss_bwd: null pointer");
+  const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
+  loss_bwd_kernel<<<dim3(blocks, N), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits_nchw, target, tables, grad_out, weight_ce, weight_dice, ignore_index, dlogits_nchw, HW);
+  B200_LAUNCH_CHECK("loss_bwd_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_head_fwd(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw,
+                                 int N, int64_t HW, int C, int K, void* stream) {
+  B200_CHECK_ARG(z && w && bias && logits_nchw, "head_fwd: null pointer");
+  B200_CHECK_ARG(z_pitch % 8 == 0, "head_fwd: pitch must be a multiple of 8");
+  if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_fwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
+  dim3 grid((unsigned)ceil_div64(HW, 256), N);
+  head_fwd_kernel<32, 3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z), z_pitch, w, bias, logits_nchw, HW);
+  B200_LAUNCH_CHECK("head_fwd_kernel");
+  return 0;
+}
+
+extern "C" int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K) {
+  (void)N; (void)HW;
+  return static_cast<int64_t>(head_bwd_blocks()) * (K * C + K) * 4;
+}
+
+extern "C" int b200unet_head_bwd(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
+                                 int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes,
+                                 int N, int64_t HW, int C, int K, void* stream) {
+  B200_CHECK_ARG(dlogits_nchw && z && w && dz && dw && db && workspace, "head_bwd: null pointer");
+  B200_CHECK_ARG(z_pitch % 8 == 0 && dz_pitch % 8 == 0, "head_bwd: pitches must be multiples of 8");
+  if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_bwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
+  const int blocks = head_bwd_blocks();
+  B200_CHECK_ARG(workspace_bytes >= b200unet_head_bwd_workspace(N, HW, C, K), "head_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  head_bwd_kernel<32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const __nv_bfloat16*>(z), z_pitch, w,
+                                                 static_cast<__nv_bfloat16*>(dz), dz_pitch, workspace, N, HW);
+  B200_LAUNCH_CHECK("head_bwd_kernel");
+  head_bwd_finalize_kernel<<<1, 128, 0, st>>>(workspace, blocks, K * C, K, dw, db);
+  B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
+  return 0;
+}

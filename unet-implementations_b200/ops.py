@@ -1,0 +1,268 @@
+"""Operator layer: torch tensors in, C-ABI kernel launches out.
+
+Every function here enqueues work on torch's current CUDA stream through libb200unet.so and returns torch tensors
+that own the memory.  Activations are NHWC bf16 tensors of logical shape [N, H, W, C]; a tensor may be a channel
+slice of a wider buffer (its W-stride is the "pitch"), which is how the decoder concat buffer is filled in place.
+No function falls back to torch math: if the library is missing or the device is not sm_100 the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDgradArgs, ConvFpropArgs, ConvWgradArgs
+
+BF16 = torch.bfloat16
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pitch_of(t: torch.Tensor) -> int:
+    """Pixel pitch (elements) of an NHWC bf16 tensor or channel-slice view; validates the layout."""
+    assert t.dim() == 4 and t.dtype == BF16 and t.is_cuda, "expected a CUDA bf16 [N,H,W,C] tensor"
+    n, h, w, c = t.shape
+    pitch = t.stride(2)
+    assert t.stride(3) == 1 and pitch >= c, f"channels must be contiguous (strides {t.stride()})"
+    assert (h == 1 or t.stride(1) == w * pitch) and (n == 1 or t.stride(0) == h * w * pitch), (
+        f"not a pitched NHWC view: shape {tuple(t.shape)} strides {t.stride()}"
+    )
+    assert pitch % 8 == 0 and t.data_ptr() % 16 == 0, "pitch must be a multiple of 8 elements, base 16-byte aligned"
+    return pitch
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    return t
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200unet: no CUDA device; this path has no CPU fallback")
+    if _lib.call("b200unet_device_ok") != 1:
+        raise RuntimeError("b200unet: the current device is not compute capability 10.x (B200, sm_100a)")
+
+
+# ----------------------------------------------------------------------------------------------------- convolution
+def pack_conv_weights(w_oihw: torch.Tensor, need_dgrad: bool = True):
+    """fp32 [Cout,Cin,3,3] -> (bf16 [Cout,3,3,Cin], bf16 [Cin,3,3,Cout] or None)."""
+    w = _f32(w_oihw.detach())
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    wf = torch.empty((cout, 3, 3, cin), dtype=BF16, device=w.device)
+    wd = torch.empty((cin, 3, 3, cout), dtype=BF16, device=w.device) if need_dgrad else None
+    _lib.call("b200unet_pack_conv_weights", _p(w), _p(wf), _p(wd), cout, cin, _stream())
+    return wf, wd
+
+
+def conv_out_hw(h: int, w: int, stride: int):
+    return (h - 1) // stride + 1, (w - 1) // stride + 1
+
+
+def conv_fprop(x, w_fprop, stride=1, out=None, want_stats=True, simt=False):
+    """3x3/pad 1 conv.  Returns (y [N,OH,OW,Cout] bf16, stats fp32 [N,P,Cout,2] or None)."""
+    n, h, w, cin = x.shape
+    cout = w_fprop.shape[0]
+    assert w_fprop.shape == (cout, 3, 3, cin) and w_fprop.dtype == BF16 and w_fprop.is_contiguous()
+    oh, ow = conv_out_hw(h, w, stride)
+    y = out if out is not None else torch.empty((n, oh, ow, cout), dtype=BF16, device=x.device)
+    assert tuple(y.shape) == (n, oh, ow, cout)
+    stats = None
+    if want_stats:
+        parts = _lib.call("b200unet_conv_fprop_partials", oh, ow)
+        stats = torch.empty((n, parts, cout, 2), dtype=torch.float32, device=x.device)
+    a = ConvFpropArgs(_p(x), pitch_of(x), _p(w_fprop), _p(y), pitch_of(y), _p(stats), n, h, w, cin, cout, stride)
+    _lib.call("b200unet_conv_fprop_simt" if simt else "b200unet_conv_fprop", ctypes.byref(a), _stream())
+    return y, stats
+
+
+def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
+    """Gradient wrt the conv input.  dy [N,OH,OW,Cout]; w_dgrad [Cin,3,3,Cout]; returns dx [N,H,W,Cin] bf16."""
+    n, oh, ow, cout = dy.shape
+    cin = w_dgrad.shape[0]
+    h, w = in_hw
+    assert w_dgrad.shape == (cin, 3, 3, cout) and w_dgrad.dtype == BF16 and w_dgrad.is_contiguous()
+    assert conv_out_hw(h, w, stride) == (oh, ow)
+    dx = out if out is not None else torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    a = ConvDgradArgs(_p(dy), pitch_of(dy), _p(w_dgrad), _p(dx), pitch_of(dx), n, h, w, cin, cout, stride)
+    _lib.call("b200unet_conv_dgrad_simt" if simt else "b200unet_conv_dgrad", ctypes.byref(a), _stream())
+    return dx
+
+
+def conv_wgrad(x, dy, stride=1, simt=False):
+    """Weight gradient in the nn.Conv2d layout: fp32 [Cout,Cin,3,3]."""
+    n, h, w, cin = x.shape
+    _, oh, ow, cout = dy.shape
+    assert conv_out_hw(h, w, stride) == (oh, ow)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    if simt:
+        a = ConvWgradArgs(_p(x), pitch_of(x), _p(dy), pitch_of(dy), _p(dw), None, 0, n, h, w, cin, cout, stride)
+        _lib.call("b200unet_conv_wgrad_simt", ctypes.byref(a), _stream())
+        return dw
+    nbytes = _lib.call("b200unet_conv_wgrad_workspace", n, h, w, cin, cout, stride)
+    if nbytes < 0:
+        raise RuntimeError(f"conv_wgrad: unsupported shape: {_lib.last_error()}")
+    ws = torch.empty((max(nbytes, 4) // 4,), dtype=torch.float32, device=x.device)
+    a = ConvWgradArgs(_p(x), pitch_of(x), _p(dy), pitch_of(dy), _p(dw), _p(ws), nbytes, n, h, w, cin, cout, stride)
+    _lib.call("b200unet_conv_wgrad", ctypes.byref(a), _stream())
+    return dw
+
+
+def stem_fprop(img_nchw, w_oihw, out=None, want_stats=True):
+    """Cin=3 -> 32 stem conv reading the fp32 NCHW image.  Returns (y [N,H,W,32] bf16, stats)."""
+    img = _f32(img_nchw)
+    n, c, h, w = img.shape
+    assert c == 3 and tuple(w_oihw.shape) == (32, 3, 3, 3)
+    y = out if out is not None else torch.empty((n, h, w, 32), dtype=BF16, device=img.device)
+    stats = None
+    if want_stats:
+        parts = _lib.call("b200unet_stem_partials", h, w)
+        stats = torch.empty((n, parts, 32, 2), dtype=torch.float32, device=img.device)
+    _lib.call("b200unet_stem_fprop", _p(img), _p(_f32(w_oihw.detach())), _p(y), pitch_of(y), _p(stats), n, h, w,
+              _stream())
+    return y, stats
+
+
+def stem_wgrad(img_nchw, dy):
+    img = _f32(img_nchw)
+    n, c, h, w = img.shape
+    nbytes = _lib.call("b200unet_stem_wgrad_workspace", n, h, w)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=img.device)
+    dw = torch.empty((32, 3, 3, 3), dtype=torch.float32, device=img.device)
+    _lib.call("b200unet_stem_wgrad", _p(img), _p(dy), pitch_of(dy), _p(dw), _p(ws), nbytes, n, h, w, _stream())
+    return dw
+
+
+# ------------------------------------------------------------------------------------- InstanceNorm + LeakyReLU + drop
+def in_finalize(stats, gamma, beta, drop_scale, eps, hw):
+    """stats [N,P,C,2] -> (mean, rstd, a, b), each fp32 [N,C]."""
+    n, parts, c, _ = stats.shape
+    out = torch.empty((4, n, c), dtype=torch.float32, device=stats.device)
+    mean, rstd, a, b = out[0], out[1], out[2], out[3]
+    _lib.call("b200unet_in_finalize", _p(stats), parts, _p(_f32(gamma.detach())), _p(_f32(beta.detach())),
+              _p(drop_scale), float(eps), _p(mean), _p(rstd), _p(a), _p(b), n, c, hw, _stream())
+    return mean, rstd, a, b
+
+
+def in_apply(y, a, b, slope, out=None):
+    n, h, w, c = y.shape
+    z = out if out is not None else torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    assert tuple(z.shape) == (n, h, w, c)
+    _lib.call("b200unet_in_apply", _p(y), pitch_of(y), _p(a), _p(b), float(slope), _p(z), pitch_of(z), n, h * w, c,
+              _stream())
+    return z
+
+
+def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
+    """Backward of z = lrelu(IN(y))*drop.  dz2 (optional) is a second gradient contribution added to dz.
+    Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C])."""
+    n, h, w, c = y.shape
+    hw = h * w
+    parts = _lib.call("b200unet_in_bwd_partials", hw, c)
+    part = torch.empty((n, parts, c, 2), dtype=torch.float32, device=y.device)
+    dz2p = pitch_of(dz2) if dz2 is not None else 0
+    _lib.call("b200unet_in_bwd_reduce", _p(dz), pitch_of(dz), _p(dz2), dz2p, _p(y), pitch_of(y), _p(a), _p(b),
+              _p(mean), _p(rstd), _p(drop_scale), float(slope), _p(part), n, hw, c, _stream())
+    dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
+    coef = torch.empty((n, c, 3), dtype=torch.float32, device=y.device)
+    _lib.call("b200unet_in_bwd_finalize", _p(part), parts, _p(_f32(gamma.detach())), _p(rstd), _p(dgb[0]), _p(dgb[1]),
+              _p(coef), n, c, hw, _stream())
+    dy = torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    _lib.call("b200unet_in_bwd_apply", _p(dz), pitch_of(dz), _p(dz2), dz2p, _p(y), pitch_of(y), _p(a), _p(b), _p(mean),
+              _p(rstd), _p(drop_scale), _p(coef), float(slope), _p(dy), pitch_of(dy), n, hw, c, _stream())
+    return dy, dgb[0], dgb[1]
+
+
+# ------------------------------------------------------------------------------------------------------- resampling
+def upsample2x(x, out):
+    """Bilinear 2x of x [N,H,W,C] into out [N,2H,2W,C] (typically the leading channel slice of a concat buffer)."""
+    n, h, w, c = x.shape
+    assert tuple(out.shape) == (n, 2 * h, 2 * w, c)
+    _lib.call("b200unet_upsample2x_fwd", _p(x), pitch_of(x), _p(out), pitch_of(out), n, h, w, c, _stream())
+    return out
+
+
+def upsample2x_backward(dout, out=None):
+    n, oh, ow, c = dout.shape
+    assert oh % 2 == 0 and ow % 2 == 0
+    dx = out if out is not None else torch.empty((n, oh // 2, ow // 2, c), dtype=BF16, device=dout.device)
+    _lib.call("b200unet_upsample2x_bwd", _p(dout), pitch_of(dout), _p(dx), pitch_of(dx), n, oh // 2, ow // 2, c,
+              _stream())
+    return dx
+
+
+def nchw_to_nhwc(x_nchw, out=None):
+    x = _f32(x_nchw)
+    n, c, h, w = x.shape
+    y = out if out is not None else torch.empty((n, h, w, c), dtype=BF16, device=x.device)
+    _lib.call("b200unet_nchw_f32_to_nhwc_bf16", _p(x), _p(y), y.stride(2), n, c, h * w, _stream())
+    return y
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.call("b200unet_nhwc_bf16_to_nchw_f32", _p(x), x.stride(2), _p(y), n, c, h * w, _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------ head + loss
+def head_forward(z, weight, bias):
+    """1x1 conv C->K on bf16 NHWC z; returns fp32 NCHW logits."""
+    n, h, w, c = z.shape
+    k = weight.shape[0]
+    logits = torch.empty((n, k, h, w), dtype=torch.float32, device=z.device)
+    _lib.call("b200unet_head_fwd", _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))),
+              _p(_f32(bias.detach())), _p(logits), n, h * w, c, k, _stream())
+    return logits
+
+
+def head_backward(dlogits, z, weight):
+    """Returns (dz bf16 NHWC, dW [K,C,1,1], db [K])."""
+    n, h, w, c = z.shape
+    k = weight.shape[0]
+    dl = _f32(dlogits.contiguous())
+    nbytes = _lib.call("b200unet_head_bwd_workspace", n, h * w, c, k)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=z.device)
+    dz = torch.empty((n, h, w, c), dtype=BF16, device=z.device)
+    dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=z.device)
+    db = torch.empty((k,), dtype=torch.float32, device=z.device)
+    _lib.call("b200unet_head_bwd", _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
+              pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
+    return dz, dw, db
+
+
+def loss_forward(logits, target, class_weights, dynamic, weight_ce, weight_dice, ignore_index, smooth):
+    """Returns (loss_out fp32 [3] = total/CE/Dice, tables) -- see b200unet_loss_fwd."""
+    lg = _f32(logits)
+    n, k, h, w = lg.shape
+    assert k == 3, "SimpleLoss kernels are built for 3 classes (losses.py:40)"
+    assert target.dtype == torch.int64 and target.is_cuda and target.is_contiguous()
+    assert tuple(target.shape) == (n, h, w)
+    hw = h * w
+    nbytes = _lib.call("b200unet_loss_workspace", n, hw)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=lg.device)
+    out = torch.empty((3,), dtype=torch.float32, device=lg.device)
+    tables = torch.empty((3 + 6 * n,), dtype=torch.float32, device=lg.device)
+    cw = _f32(class_weights) if class_weights is not None else None
+    _lib.call("b200unet_loss_fwd", _p(lg), _p(target), _p(cw), int(bool(dynamic)), float(weight_ce),
+              float(weight_dice), int(ignore_index), float(smooth), _p(out), _p(tables), _p(ws), nbytes, n, hw,
+              _stream())
+    return out, tables
+
+
+def loss_backward(logits, target, tables, grad_out, weight_ce, weight_dice, ignore_index):
+    lg = _f32(logits)
+    n, k, h, w = lg.shape
+    dl = torch.empty_like(lg)
+    go = _f32(grad_out.reshape(1).contiguous()) if grad_out is not None else None
+    _lib.call("b200unet_loss_bwd", _p(lg), _p(target), _p(tables), _p(go), float(weight_ce), float(weight_dice),
+              int(ignore_index), _p(dl), n, h * w, _stream())
+    return dl
