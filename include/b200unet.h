@@ -31,6 +31,8 @@ extern "C" {
 
 int b200unet_version(void);
 const char* b200unet_last_error(void);
+/* Number of kernels this library has launched in this process (monotonic; bench.py reports the delta). */
+long long b200unet_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (negative on error). */
 int b200unet_device_ok(void);
 

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200unet_version": (c_int, []),
     "b200unet_last_error": (c_char_p, []),
     "b200unet_device_ok": (c_int, []),
+    "b200unet_launch_count": (c_int64, []),
     "b200unet_conv_fprop_partials": (c_int, [_I, _I]),
     "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
     "b200unet_conv_dgrad": (c_int, [POINTER(ConvDgradArgs), _P]),
@@ -77,7 +78,7 @@ SIGNATURES = {
 
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
-    "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_conv_fprop_partials",
+    "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
     "b200unet_in_bwd_partials", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
 }
@@ -107,10 +108,35 @@ def last_error() -> str:
     return msg.decode("utf-8", "replace") if msg else ""
 
 
+class EventProfiler:
+    """Optional per-entry-point device timing with CUDA events on torch's current stream (bench.py's roofline leg).
+    Recording an event pair costs about a microsecond on the host and nothing on the device."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    def totals_ms(self):
+        """name -> (total ms, calls); call after a synchronize."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.pairs.items()}
+
+
+PROFILER = None  # set to an EventProfiler to time every entry point
+
+
 def call(name: str, *args):
     """Call a status-returning entry point; raise RuntimeError(last_error) on failure."""
     fn = getattr(load(), name)
-    rc = fn(*args)
+    prof = PROFILER
+    if prof is not None and name not in _VALUE_FUNCS:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        prof.pairs.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
     if name in _VALUE_FUNCS:
         return rc
     if rc != 0:

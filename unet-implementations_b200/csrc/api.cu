@@ -6,6 +6,7 @@
 namespace b200 {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -81,6 +82,10 @@ int num_sms() {
 extern "C" {
 
 int b200unet_version(void) { return B200UNET_VERSION; }
+
+long long b200unet_launch_count(void) {
+  return static_cast<long long>(__atomic_load_n(&b200::g_launches, __ATOMIC_RELAXED));
+}
 
 const char* b200unet_last_error(void) { return b200::g_err; }
 

@@ -27,8 +27,11 @@ int set_error(int code, const char* fmt, ...);  // defined in api.cu (thread-loc
                                __LINE__);                                                                   \
   } while (0)
 
+extern unsigned long long g_launches;  // kernels launched by this library in this process (api.cu)
+
 #define B200_LAUNCH_CHECK(name)                                                                            \
   do {                                                                                                     \
+    __atomic_fetch_add(&::b200::g_launches, 1ull, __ATOMIC_RELAXED);                                       \
     cudaError_t _e = cudaGetLastError();                                                                   \
     if (_e != cudaSuccess)                                                                                 \
       return ::b200::set_error(::b200::kErrCuda, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \

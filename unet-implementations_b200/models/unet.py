@@ -1,0 +1,531 @@
+"""B200-native drop-in for the reference's `models.unet` (Ulixes-8/UNet-Implementations, Our_UNet/models/unet.py).
+
+Same classes, constructor arguments, attribute tree and `state_dict` as the reference (`SpatialDropout2d`
+unet.py:13-35, `ConvBlock` :37-141, `UpBlock` :143-231, `UNet` :233-432), so `src/train.py` / `src/evaluate.py`
+construct, checkpoint and call it unchanged.  What differs is everything below the module surface:
+`UNet.forward` runs as ONE `torch.autograd.Function` whose forward and backward enqueue the hand-written sm_100a
+kernels of libb200unet.so (include/b200unet.h) on torch's current stream:
+
+    conv 3x3 (tcgen05 implicit GEMM, raw bf16 output + InstanceNorm partial sums in the epilogue)
+      -> finalize (per-(n,c) mean/rstd folded with gamma, beta and the SpatialDropout scale)
+      -> apply (normalise + LeakyReLU + channel dropout in one pass, written straight into its consumer's buffer:
+                the next conv's input or the skip half of a decoder concat buffer -- torch.cat never runs)
+    bilinear 2x upsample written into the other half of the concat buffer; 1x1 head -> fp32 NCHW logits.
+
+Activations live as NHWC bf16; parameters stay fp32 OIHW `nn.Parameter`s and receive fp32 `.grad`s.
+There is no torch/cuDNN/CPU fallback on this path: without the CUDA library or an sm_100 device it raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple, Type, Union
+
+import torch
+import torch.nn as nn
+
+try:  # package import (unet_implementations_b200.models.unet)
+    from .. import ops
+except ImportError:  # imported as top-level `models.unet` through the drop-in shim directory
+    from unet_implementations_b200 import ops
+
+BF16 = torch.bfloat16
+
+
+class SpatialDropout2d(nn.Module):
+    """Channel dropout of the reference (unet.py:13-35): one Bernoulli(1-p) draw per (sample, channel), kept
+    channels scaled by 1/(1-p).  Inside `UNet.forward` the draw below is made with the reference's exact call
+    (`draw`), and the resulting [N,C] scale is folded into the fused normalise kernel."""
+
+    def __init__(self, drop_prob):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def draw(self, like: torch.Tensor, batch: int, channels: int) -> torch.Tensor:
+        # the reference's call, verbatim in shape/dtype/device so that the same seed gives the same mask (unet.py:30-31)
+        mask = like.new_empty(batch, channels, 1, 1).bernoulli_(1 - self.drop_prob)
+        return mask.div_(1 - self.drop_prob)
+
+    def forward(self, x):
+        if not self.training or self.drop_prob == 0:
+            return x
+        mask = self.draw(x, x.size(0), x.size(1))
+        return x * mask.expand_as(x)
+
+
+class ConvBlock(nn.Module):
+    """[Conv2d 3x3 (stride on the first conv only) -> InstanceNorm2d -> LeakyReLU -> SpatialDropout2d] x n_convs in
+    one `nn.Sequential` called `.block`, built in the reference's order (unet.py:97-134) so that parameter
+    names, shapes and the RNG consumed by construction are identical."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, int]],
+                 stride: Union[int, Tuple[int, int]], n_convs: int = 2, padding: Optional[int] = None,
+                 norm_op: Type[nn.Module] = nn.InstanceNorm2d, norm_op_kwargs: Dict = None,
+                 dropout_op: Optional[Type[nn.Module]] = None, dropout_op_kwargs: Dict = None,
+                 nonlin: Type[nn.Module] = nn.LeakyReLU, nonlin_kwargs: Dict = None, conv_bias: bool = True,
+                 spatial_dropout_rate: float = 0.0):
+        super().__init__()
+        norm_op_kwargs = {"eps": 1e-5, "affine": True} if norm_op_kwargs is None else norm_op_kwargs
+        nonlin_kwargs = {"inplace": True} if nonlin_kwargs is None else nonlin_kwargs
+        dropout_op_kwargs = {} if dropout_op_kwargs is None else dropout_op_kwargs
+        if padding is None:
+            padding = kernel_size // 2 if isinstance(kernel_size, int) else (kernel_size[0] // 2, kernel_size[1] // 2)
+        layers: List[nn.Module] = []
+        ch = in_channels
+        for i in range(n_convs):
+            layers.append(nn.Conv2d(ch, out_channels, kernel_size, stride if i == 0 else 1, padding, bias=conv_bias))
+            if norm_op is not None:
+                layers.append(norm_op(out_channels, **norm_op_kwargs))
+            if nonlin is not None:
+                layers.append(nonlin(**nonlin_kwargs))
+            if spatial_dropout_rate > 0:
+                layers.append(SpatialDropout2d(spatial_dropout_rate))
+            if dropout_op is not None:
+                layers.append(dropout_op(**dropout_op_kwargs))
+            ch = out_channels
+        self.block = nn.Sequential(*layers)
+
+    def units(self):
+        """The block parsed into fused units: [(conv, norm, nonlin, spatial_dropout or None), ...].  Raises for a
+        composition the kernels do not implement (anything but the trainer's, train.py:776-795)."""
+        mods = list(self.block)
+        out, i = [], 0
+        while i < len(mods):
+            conv = mods[i]
+            norm = mods[i + 1] if i + 1 < len(mods) else None
+            act = mods[i + 2] if i + 2 < len(mods) else None
+            if not (isinstance(conv, nn.Conv2d) and isinstance(norm, nn.InstanceNorm2d) and isinstance(act, nn.LeakyReLU)):
+                raise NotImplementedError(
+                    "b200unet implements ConvBlock = [Conv2d 3x3 -> InstanceNorm2d(affine) -> LeakyReLU -> "
+                    f"SpatialDropout2d]; got {[type(m).__name__ for m in mods]}")
+            i += 3
+            drop = None
+            if i < len(mods) and isinstance(mods[i], SpatialDropout2d):
+                drop = mods[i]
+                i += 1
+            if tuple(conv.kernel_size) != (3, 3) or tuple(conv.padding) != (1, 1) or conv.stride[0] != conv.stride[1] \
+                    or conv.stride[0] not in (1, 2) or conv.groups != 1 or tuple(conv.dilation) != (1, 1):
+                raise NotImplementedError(f"b200unet: unsupported conv {conv}")
+            if not norm.affine or norm.track_running_stats:
+                raise NotImplementedError("b200unet: InstanceNorm2d must be affine without running stats")
+            out.append((conv, norm, act, drop))
+        return out
+
+    def forward(self, x):
+        """Stand-alone use (NCHW fp32 in and out); `UNet.forward` does not go through here."""
+        return _run_block_standalone(self, x)
+
+
+class UpBlock(nn.Module):
+    """Bilinear upsample to the skip's size, cat([x, skip], 1), ConvBlock (unet.py:143-231)."""
+
+    def __init__(self, in_channels: int, skip_channels: int, out_channels: int,
+                 kernel_size: Union[int, Tuple[int, int]], n_convs: int = 2,
+                 norm_op: Type[nn.Module] = nn.InstanceNorm2d, norm_op_kwargs: Dict = None,
+                 dropout_op: Optional[Type[nn.Module]] = None, dropout_op_kwargs: Dict = None,
+                 nonlin: Type[nn.Module] = nn.LeakyReLU, nonlin_kwargs: Dict = None, conv_bias: bool = True,
+                 spatial_dropout_rate: float = 0.0):
+        super().__init__()
+        self.conv_block = ConvBlock(in_channels + skip_channels, out_channels, kernel_size, stride=1, n_convs=n_convs,
+                                    padding=None, norm_op=norm_op, norm_op_kwargs=norm_op_kwargs,
+                                    dropout_op=dropout_op, dropout_op_kwargs=dropout_op_kwargs, nonlin=nonlin,
+                                    nonlin_kwargs=nonlin_kwargs, conv_bias=conv_bias,
+                                    spatial_dropout_rate=spatial_dropout_rate)
+
+    def forward(self, x, skip):
+        raise NotImplementedError(
+            "b200unet: UpBlock runs only inside UNet.forward, where the upsample writes straight into the concat "
+            "buffer; there is no stand-alone NCHW path for it")
+
+
+class UNet(nn.Module):
+    """The reference's 6-stage encoder-decoder (unet.py:233-432) with its constructor, attributes and state_dict."""
+
+    def __init__(self, in_channels: int = 3, num_classes: int = 3, n_stages: int = 6,
+                 features_per_stage: List[int] = None, kernel_sizes: List[Tuple[int, int]] = None,
+                 strides: List[Tuple[int, int]] = None, n_conv_per_stage: List[int] = None,
+                 n_conv_per_stage_decoder: List[int] = None, conv_bias: bool = True,
+                 norm_op: Type[nn.Module] = nn.InstanceNorm2d, norm_op_kwargs: Dict = None,
+                 dropout_op: Optional[Type[nn.Module]] = None, dropout_op_kwargs: Dict = None,
+                 nonlin: Type[nn.Module] = nn.LeakyReLU, nonlin_kwargs: Dict = None,
+                 encoder_dropout_rates: List[float] = None, decoder_dropout_rates: List[float] = None):
+        super().__init__()
+        if features_per_stage is None:
+            features_per_stage = [32, 64, 128, 256, 512, 512]
+        if kernel_sizes is None:
+            kernel_sizes = [[3, 3]] * n_stages
+        if strides is None:
+            strides = [[1, 1]] + [[2, 2]] * (n_stages - 1)
+        if n_conv_per_stage is None:
+            n_conv_per_stage = [2] * n_stages
+        if n_conv_per_stage_decoder is None:
+            n_conv_per_stage_decoder = [2] * (n_stages - 1)
+        if norm_op_kwargs is None:
+            norm_op_kwargs = {"eps": 1e-5, "affine": True}
+        if nonlin_kwargs is None:
+            nonlin_kwargs = {"inplace": True}
+        if encoder_dropout_rates is None:
+            encoder_dropout_rates = [0.0, 0.0, 0.1, 0.2, 0.3, 0.3]
+        if decoder_dropout_rates is None:
+            decoder_dropout_rates = [0.3, 0.2, 0.2, 0.1, 0.0]
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.n_stages = n_stages
+        self.features_per_stage = features_per_stage
+
+        common = dict(norm_op=norm_op, norm_op_kwargs=norm_op_kwargs, dropout_op=dropout_op,
+                      dropout_op_kwargs=dropout_op_kwargs, nonlin=nonlin, nonlin_kwargs=nonlin_kwargs,
+                      conv_bias=conv_bias)
+        self.encoder_stages = nn.ModuleList()
+        ch = in_channels
+        for s in range(n_stages):
+            self.encoder_stages.append(ConvBlock(ch, features_per_stage[s], kernel_sizes[s], strides[s],
+                                                 n_convs=n_conv_per_stage[s],
+                                                 spatial_dropout_rate=encoder_dropout_rates[s], **common))
+            ch = features_per_stage[s]
+        self.decoder_stages = nn.ModuleList()
+        for j in range(n_stages - 1):
+            d = n_stages - 2 - j
+            self.decoder_stages.append(UpBlock(features_per_stage[d + 1], features_per_stage[d], features_per_stage[d],
+                                               kernel_sizes[d], n_convs=n_conv_per_stage_decoder[d],
+                                               spatial_dropout_rate=decoder_dropout_rates[j], **common))
+        self.segmentation_output = nn.Conv2d(features_per_stage[0], num_classes, kernel_size=1, stride=1, padding=0,
+                                             bias=True)
+        self.initialize_weights()
+        # test/DDP hooks (not part of the reference surface)
+        self._mask_override: Optional[List[torch.Tensor]] = None  # inject dropout masks instead of drawing them
+        self.last_dropout_masks: List[torch.Tensor] = []          # [N,C] scales used by the last training forward
+        self._grad_sink = None                                    # callable(param, grad) fired as backward produces grads
+        self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
+
+    def initialize_weights(self):
+        """kaiming_normal_(fan_out, leaky_relu) on conv weights, zero conv biases, IN weight 1 / bias 0 (unet.py:386-397)."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="leaky_relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.InstanceNorm2d):
+                if m.weight is not None:
+                    nn.init.constant_(m.weight, 1)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    # ------------------------------------------------------------------------------------------------ plan
+    def _layers(self):
+        """Flat list of fused units in forward order with their role in the graph."""
+        layers = []
+        for s, stage in enumerate(self.encoder_stages):
+            us = stage.units()
+            if len(us) < 1:
+                raise NotImplementedError("b200unet: a stage needs at least one conv")
+            for i, u in enumerate(us):
+                layers.append(dict(kind="enc", stage=s, idx=i, last=(i == len(us) - 1), unit=u))
+        for j, up in enumerate(self.decoder_stages):
+            us = up.conv_block.units()
+            for i, u in enumerate(us):
+                layers.append(dict(kind="dec", stage=j, idx=i, last=(i == len(us) - 1), unit=u))
+        return layers
+
+    def _packed(self, conv: nn.Conv2d, need_dgrad: bool):
+        """bf16 repacks of a conv weight for the implicit-GEMM kernels, cached on the parameter's version counter."""
+        w = conv.weight
+        key = id(w)
+        ver = w._version
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == ver and hit[1].device == w.device and (hit[2] is not None or not need_dgrad) \
+                and hit[3] == w.data_ptr():
+            return hit[1], hit[2]
+        wf, wd = ops.pack_conv_weights(w, need_dgrad=need_dgrad)
+        self._pack_cache[key] = (ver, wf, wd, w.data_ptr())
+        return wf, wd
+
+    def forward(self, x):
+        if x.dim() != 4 or x.size(1) != self.in_channels:
+            raise ValueError(f"UNet.forward expects [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("b200unet: UNet.forward needs a CUDA tensor on an sm_100 device; there is no CPU path")
+        params = [p for p in self.parameters()]
+        return _UNetFunction.apply(self, x, *params)
+
+
+# ====================================================================================================================
+# The fused forward/backward
+# ====================================================================================================================
+def _use_tc(cin: int, cout: int) -> bool:
+    return cin % 32 == 0 and cout % 32 == 0
+
+
+def _conv_fwd(x, wf, stride, out=None):
+    cout, cin = wf.shape[0], wf.shape[3]
+    return ops.conv_fprop(x, wf, stride, out=out, want_stats=True, simt=not _use_tc(cin, cout))
+
+
+class _UNetFunction(torch.autograd.Function):
+    """forward(model, image, *parameters) -> fp32 NCHW logits.  One autograd node for the whole network: the saved
+    state is the NHWC bf16 arena (raw conv outputs, post-activation tensors, concat buffers) plus [N,C] statistics."""
+
+    @staticmethod
+    def forward(ctx, model: UNet, x: torch.Tensor, *params):
+        ops.require_device()
+        with torch.cuda.device(x.device):
+            return _forward_impl(ctx, model, x, params)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        with torch.cuda.device(dlogits.device):
+            grads = _backward_impl(ctx, dlogits)
+        return (None, None) + tuple(grads)
+
+
+def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    B, _, H, W = x.shape
+    n = model.n_stages
+    feats = list(model.features_per_stage)
+    layers = model._layers()
+    training = model.training
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    dev = x.device
+
+    # spatial size per encoder level
+    sizes = []
+    h, w = H, W
+    for s in range(n):
+        st = model.encoder_stages[s].block[0].stride[0]
+        h, w = ops.conv_out_hw(h, w, st)
+        sizes.append((h, w))
+    for d in range(n - 1):
+        if sizes[d] != (2 * sizes[d + 1][0], 2 * sizes[d + 1][1]):
+            raise NotImplementedError(
+                f"b200unet: the upsample kernel is the exact 2x case of F.interpolate (unet.py:220-225); level {d} is "
+                f"{sizes[d]} over {sizes[d + 1]} -- use an input size divisible by {2 ** (n - 1)}")
+
+    # decoder concat buffers: cat[d] = [upsampled level d+1 (feats[d+1]) | skip of level d (feats[d])]
+    cat = [torch.empty((B, sizes[d][0], sizes[d][1], feats[d + 1] + feats[d]), dtype=BF16, device=dev)
+           for d in range(n - 1)]
+
+    # dropout scales, drawn in the reference's order with the reference's call
+    override = list(model._mask_override) if model._mask_override is not None else None
+    used_masks = []
+
+    def draw(drop: Optional[SpatialDropout2d], c: int):
+        if drop is None or not training or drop.drop_prob == 0:
+            return None
+        if override is not None:
+            m = override.pop(0).to(device=dev, dtype=torch.float32)
+        else:
+            m = drop.draw(x, B, c)
+        m = m.reshape(B, c).contiguous()
+        used_masks.append(m)
+        return m
+
+    saved = []  # per layer dict
+    cur = None  # current NHWC bf16 activation
+    for L in layers:
+        conv, norm, act, drop = L["unit"]
+        cin, cout = conv.in_channels, conv.out_channels
+        stride = conv.stride[0]
+        rec = dict(L=L, stride=stride)
+        if L["kind"] == "dec" and L["idx"] == 0:
+            d = n - 2 - L["stage"]
+            c_low = feats[d + 1]
+            ops.upsample2x(cur, cat[d][..., :c_low])
+            rec["low"] = cur  # only its shape matters in backward
+            cur = cat[d]
+        first = L["kind"] == "enc" and L["stage"] == 0 and L["idx"] == 0
+        if first:
+            if cin == 3 and cout == 32 and stride == 1:
+                y, stats = ops.stem_fprop(x, conv.weight)
+                rec["stem"] = True
+            else:
+                xin = ops.nchw_to_nhwc(x, out=_padded_nhwc(B, H, W, cin, dev))
+                wf, wd = model._packed(conv, False)
+                y, stats = _conv_fwd(xin, wf, stride)
+                rec["xin"] = xin
+                rec["stem"] = False
+        else:
+            wf, wd = model._packed(conv, need_grad)
+            y, stats = _conv_fwd(cur, wf, stride)
+            rec["xin"] = cur
+            rec["wd"] = wd
+        scale = draw(drop, cout)
+        oh, ow = y.shape[1], y.shape[2]
+        mean, rstd, a, b = ops.in_finalize(stats, norm.weight, norm.bias, scale, norm.eps, oh * ow)
+        # destination of the activated tensor: the skip half of a concat buffer for the last unit of an encoder stage
+        dst = None
+        if L["kind"] == "enc" and L["last"] and L["stage"] < n - 1:
+            d = L["stage"]
+            dst = cat[d][..., feats[d + 1]:]
+        z = ops.in_apply(y, a, b, act.negative_slope, out=dst)
+        rec.update(y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale, slope=act.negative_slope, conv=conv, norm=norm)
+        saved.append(rec)
+        cur = z
+    head = model.segmentation_output
+    if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
+        raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
+    logits = ops.head_forward(cur, head.weight, head.bias)
+    model.last_dropout_masks = used_masks
+    if need_grad:
+        ctx.model = model
+        ctx.saved = saved
+        ctx.image = x
+        ctx.z_last = cur
+        ctx.cat = cat
+        ctx.sizes = sizes
+        ctx.param_ids = {id(p): i for i, p in enumerate(params)}
+        ctx.param_req = [p.requires_grad for p in params]
+        ctx.n_params = len(params)
+    else:
+        ctx.saved = None
+    return logits
+
+
+def _padded_nhwc(B, H, W, C, dev):
+    pitch = (C + 7) // 8 * 8
+    buf = torch.zeros((B, H, W, pitch), dtype=BF16, device=dev)
+    return buf[..., :C]
+
+
+def _backward_impl(ctx, dlogits):
+    if ctx.saved is None:
+        raise RuntimeError("b200unet: backward called on a forward that ran without grad")
+    model: UNet = ctx.model
+    saved = ctx.saved
+    n = model.n_stages
+    feats = list(model.features_per_stage)
+    grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
+    ids = ctx.param_ids
+    req = ctx.param_req
+    sink = model._grad_sink
+
+    def put(p: Optional[nn.Parameter], g_fn):
+        """Store the gradient of parameter p (computed lazily, only if it requires grad)."""
+        if p is None:
+            return
+        i = ids[id(p)]
+        if not req[i]:
+            return
+        g = g_fn()
+        if sink is not None:
+            g = sink(p, g)
+        grads[i] = g
+
+    # the earliest layer (forward order) that still has a trainable parameter: backward stops there
+    first_needed = len(saved)
+    for li, rec in enumerate(saved):
+        ps = [rec["conv"].weight, rec["conv"].bias, rec["norm"].weight, rec["norm"].bias]
+        if any(p is not None and req[ids[id(p)]] for p in ps):
+            first_needed = li
+            break
+
+    head = model.segmentation_output
+    if dlogits.dtype != torch.float32:
+        dlogits = dlogits.float()
+    dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight)
+    put(head.weight, lambda: dwh)
+    put(head.bias, lambda: dbh)
+
+    dskip: Dict[int, torch.Tensor] = {}  # encoder level -> gradient view of the skip half of dcat
+    dz2 = None
+    for li in range(len(saved) - 1, -1, -1):
+        if li < first_needed:
+            break
+        rec = saved[li]
+        L = rec["L"]
+        conv, norm = rec["conv"], rec["norm"]
+        if L["kind"] == "enc" and L["last"] and L["stage"] < n - 1:
+            dz2 = dskip.pop(L["stage"])
+        else:
+            dz2 = None
+        dy, dgamma, dbeta = ops.in_backward(dz, dz2, rec["y"], rec["a"], rec["b"], rec["mean"], rec["rstd"], rec["scale"],
+                                            norm.weight, rec["slope"])
+        rec["y"] = None
+        put(norm.weight, lambda: dgamma)
+        put(norm.bias, lambda: dbeta)
+        # the conv bias feeds an InstanceNorm: its exact gradient is zero
+        put(conv.bias, lambda: torch.zeros_like(conv.bias))
+        stride = rec["stride"]
+        cin, cout = conv.in_channels, conv.out_channels
+        simt = not _use_tc(cin, cout)
+        if rec.get("stem") is True:
+            put(conv.weight, lambda: ops.stem_wgrad(ctx.image, dy))
+            break
+        xin = rec["xin"]
+        put(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt))
+        if li == first_needed or rec.get("stem") is False:
+            break
+        wd = rec["wd"]
+        dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
+        rec["xin"] = None
+        if L["kind"] == "dec" and L["idx"] == 0:
+            d = n - 2 - L["stage"]
+            c_low = feats[d + 1]
+            dskip[d] = dx[..., c_low:]
+            dz = ops.upsample2x_backward(dx[..., :c_low])
+        else:
+            dz = dx
+    if sink is not None and hasattr(sink, "finish"):
+        sink.finish()
+    ctx.saved = None
+    ctx.cat = None
+    ctx.z_last = None
+    return grads
+
+
+# ====================================================================================================================
+# Stand-alone ConvBlock (NCHW fp32 boundary) -- used when a block is called outside UNet.forward
+# ====================================================================================================================
+class _BlockFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, block: ConvBlock, x, *params):
+        ops.require_device()
+        units = block.units()
+        xin = ops.nchw_to_nhwc(x.detach().float().contiguous(),
+                               out=_padded_nhwc(x.size(0), x.size(2), x.size(3), x.size(1), x.device))
+        cur = xin
+        recs = []
+        need_grad = torch.is_grad_enabled()
+        for conv, norm, act, drop in units:
+            wf, wd = ops.pack_conv_weights(conv.weight, need_dgrad=need_grad)
+            y, stats = _conv_fwd(cur, wf, conv.stride[0])
+            scale = None
+            if drop is not None and block.training and drop.drop_prob > 0:
+                scale = drop.draw(x, x.size(0), conv.out_channels).reshape(x.size(0), -1).float().contiguous()
+            mean, rstd, a, b = ops.in_finalize(stats, norm.weight, norm.bias, scale, norm.eps, y.shape[1] * y.shape[2])
+            z = ops.in_apply(y, a, b, act.negative_slope)
+            recs.append(dict(xin=cur, y=y, wd=wd, mean=mean, rstd=rstd, a=a, b=b, scale=scale, conv=conv, norm=norm,
+                             slope=act.negative_slope))
+            cur = z
+        ctx.recs = recs if need_grad else None
+        ctx.x_needs = x.requires_grad
+        ctx.params = params
+        return ops.nhwc_to_nchw(cur)
+
+    @staticmethod
+    def backward(ctx, dout):
+        recs = ctx.recs
+        dz = ops.nchw_to_nhwc(dout.float().contiguous())
+        pg = {}
+        for i in range(len(recs) - 1, -1, -1):
+            r = recs[i]
+            conv, norm = r["conv"], r["norm"]
+            dy, dg, db = ops.in_backward(dz, None, r["y"], r["a"], r["b"], r["mean"], r["rstd"], r["scale"], norm.weight,
+                                         r["slope"])
+            simt = not _use_tc(conv.in_channels, conv.out_channels)
+            pg[id(norm.weight)], pg[id(norm.bias)] = dg, db
+            pg[id(conv.weight)] = ops.conv_wgrad(r["xin"], dy, conv.stride[0], simt=simt)
+            if conv.bias is not None:
+                pg[id(conv.bias)] = torch.zeros_like(conv.bias)
+            if i > 0 or ctx.x_needs:
+                xin = r["xin"]
+                dxp = _padded_nhwc(xin.shape[0], xin.shape[1], xin.shape[2], xin.shape[3], xin.device)
+                dz = ops.conv_dgrad(dy, r["wd"], (xin.shape[1], xin.shape[2]), conv.stride[0], out=dxp, simt=simt)
+        dx = ops.nhwc_to_nchw(dz) if ctx.x_needs else None
+        return (None, dx) + tuple(pg.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+def _run_block_standalone(block: ConvBlock, x: torch.Tensor):
+    if not x.is_cuda:
+        raise RuntimeError("b200unet: ConvBlock needs a CUDA tensor on an sm_100 device; there is no CPU path")
+    return _BlockFunction.apply(block, x, *list(block.parameters()))
