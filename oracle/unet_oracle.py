@@ -69,11 +69,37 @@ def draw_dropout_masks(cfg: UNetConfig, batch: int, like: torch.Tensor) -> List[
     return [like.new_empty(batch, c, 1, 1).bernoulli_(1 - p).div_(1 - p) for (c, p) in dropout_sites(cfg)]
 
 
-def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: float, cfg: UNetConfig, masks, training):
+class _RoundBF16(torch.autograd.Function):
+    """Storage emulation for the `bf16_storage` mode: the value is rounded to bf16 on the way forward and its
+    gradient is rounded to bf16 on the way back -- the two places where the CUDA path keeps a tensor in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def rb(x: torch.Tensor, on: bool) -> torch.Tensor:
+    return _RoundBF16.apply(x) if on else x
+
+
+def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: float, cfg: UNetConfig, masks, training,
+               bf16_storage: bool = False, fp32_first_weight: bool = False):
     """ConvBlock.forward (unet.py:97-141): [Conv2d 3x3 pad 1 (stride on the first conv only, :103) ->
-    InstanceNorm2d(eps, affine) (:118-119) -> LeakyReLU (:122-123) -> SpatialDropout2d (:126-127)] x n_convs."""
+    InstanceNorm2d(eps, affine) (:118-119) -> LeakyReLU (:122-123) -> SpatialDropout2d (:126-127)] x n_convs.
+    `bf16_storage` mirrors the CUDA path's precision policy on top of the same arithmetic: conv operands (input
+    activation, weights) and the raw conv output are bf16-rounded, everything else stays fp32."""
     for i, (ck, nk) in enumerate(block_keys(prefix, rate, cfg.n_convs)):
-        x = F.conv2d(x, sd[ck + ".weight"], sd.get(ck + ".bias"), stride=stride if i == 0 else 1, padding=1)
+        w = sd[ck + ".weight"]
+        if bf16_storage:
+            if not (fp32_first_weight and i == 0):  # the Cin=3 stem reads the fp32 image with fp32 weights
+                w = w + (w.detach().bfloat16().float() - w.detach())  # bf16 value, straight-through gradient
+                x = rb(x, True)
+        x = F.conv2d(x, w, sd.get(ck + ".bias"), stride=stride if i == 0 else 1, padding=1)
+        x = rb(x, bf16_storage)
         x = F.instance_norm(x, weight=sd[nk + ".weight"], bias=sd[nk + ".bias"], eps=cfg.eps)
         x = F.leaky_relu(x, cfg.negative_slope)
         if rate > 0 and training:
@@ -82,26 +108,30 @@ def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: f
 
 
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: UNetConfig = UNetConfig(),
-                 masks: Optional[List[torch.Tensor]] = None, training: bool = True) -> torch.Tensor:
+                 masks: Optional[List[torch.Tensor]] = None, training: bool = True,
+                 bf16_storage: bool = False) -> torch.Tensor:
     """UNet.forward (unet.py:399-432): encoder with 5 skips, bottleneck, 5 UpBlocks (bilinear to the skip's size,
     cat([x, skip], 1), ConvBlock -- unet.py:203-231), 1x1 head (:430).  `masks` = draw_dropout_masks(...) when
     training (consumed in order); eval mode ignores dropout (unet.py:23-24)."""
     masks = list(masks) if (masks is not None and training) else []
     if training and not masks and dropout_sites(cfg):
         raise ValueError("training forward needs the dropout masks (draw_dropout_masks)")
+    q = bf16_storage
     skips = []
     for s in range(cfg.n_stages - 1):
-        x = conv_block(x, sd, f"encoder_stages.{s}", cfg.strides[s], cfg.encoder_dropout[s], cfg, masks, training)
-        skips.append(x)
+        x = conv_block(x, sd, f"encoder_stages.{s}", cfg.strides[s], cfg.encoder_dropout[s], cfg, masks, training, q,
+                       fp32_first_weight=(s == 0))
+        skips.append(rb(x, q))  # the activated tensor is stored once (bf16); each consumer's gradient is stored separately
     s = cfg.n_stages - 1
-    x = conv_block(x, sd, f"encoder_stages.{s}", cfg.strides[s], cfg.encoder_dropout[s], cfg, masks, training)
+    x = conv_block(x, sd, f"encoder_stages.{s}", cfg.strides[s], cfg.encoder_dropout[s], cfg, masks, training, q)
     for j in range(cfg.n_stages - 1):
         skip = skips[len(skips) - 1 - j]
+        x = rb(x, q)
         if x.shape[2:] != skip.shape[2:]:
             x = F.interpolate(x, size=skip.shape[2:], mode="bilinear", align_corners=False)  # unet.py:220-225
-        x = torch.cat([x, skip], dim=1)  # unet.py:228 -- upsampled first, skip second
-        x = conv_block(x, sd, f"decoder_stages.{j}.conv_block", 1, cfg.decoder_dropout[j], cfg, masks, training)
-    return F.conv2d(x, sd["segmentation_output.weight"], sd["segmentation_output.bias"])
+        x = torch.cat([rb(x, q), skip], dim=1)  # unet.py:228 -- upsampled first, skip second
+        x = conv_block(x, sd, f"decoder_stages.{j}.conv_block", 1, cfg.decoder_dropout[j], cfg, masks, training, q)
+    return F.conv2d(rb(x, q), sd["segmentation_output.weight"], sd["segmentation_output.bias"])
 
 
 def class_weights(target: torch.Tensor, ignore_index: int = 255) -> torch.Tensor:
@@ -194,18 +224,16 @@ def synthetic_batch(batch: int, size: int = 512, seed: int = 0, variant: str = "
 
 def training_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, target: torch.Tensor, cfg: UNetConfig = UNetConfig(),
                   masks: Optional[List[torch.Tensor]] = None, training: bool = True, loss_kwargs: Optional[dict] = None,
-                  bf16_weights: bool = False):
+                  bf16_storage: bool = False):
     """One reference training step on CPU fp32 (train.py:654-663: forward, SimpleLoss, backward) through the
     restatement above, differentiated by torch autograd.  Returns dict(logits, loss, ce, dice, grads).
-    `bf16_weights` rounds the conv weights to bf16 first (what the tensor-core path consumes) -- used by tests that
-    want to separate operand rounding from kernel error; the default is the reference's fp32."""
+    `bf16_storage=True` keeps the arithmetic but rounds to bf16 exactly where the CUDA path stores bf16 (conv
+    operands, raw conv outputs, activations, upsampled tensors and their gradients): the matched-precision oracle
+    that separates kernel error from the cost of bf16 storage.  The default is the reference's fp32."""
     leaves = {}
     for k, v in sd.items():
-        t = v.detach().clone().float()
-        if bf16_weights and t.dim() == 4 and t.shape[-1] == 3:
-            t = t.bfloat16().float()
-        leaves[k] = t.requires_grad_(True)
-    logits = unet_forward(leaves, x.float(), cfg, masks, training)
+        leaves[k] = v.detach().clone().float().requires_grad_(True)
+    logits = unet_forward(leaves, x.float(), cfg, masks, training, bf16_storage)
     total, ce, dice = simple_loss(logits, target, parts=True, **(loss_kwargs or {}))
     total.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}

@@ -85,12 +85,22 @@ def main():
     loss = loss_fn(logits_train, target)
     loss.backward()
     grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    # the reference's own bf16 behaviour (torch.autocast on the CPU): the yardstick for what 16-bit storage costs
+    model.zero_grad()
+    torch.manual_seed(99)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        logits_bf16 = model(x)
+        loss_bf16 = loss_fn(logits_bf16, target)
+    loss_bf16.backward()
+    grads_bf16 = {k: p.grad.clone() for k, p in model.named_parameters()}
     model.eval()
     with torch.no_grad():
         logits_eval = model(x)
     torch.save({"cfg": cfg, "state_dict": {k: v.clone() for k, v in model.state_dict().items()}, "x": x,
                 "target": target, "dropout_seed": 99, "logits_train": logits_train.detach(), "loss": loss.detach(),
-                "grads": grads, "logits_eval": logits_eval}, os.path.join(HERE, "small_unet.pt"))
+                "grads": grads, "logits_eval": logits_eval, "logits_train_bf16": logits_bf16.detach().float(),
+                "loss_bf16": loss_bf16.detach().float(),
+                "grads_bf16": {k: v.bfloat16() for k, v in grads_bf16.items()}}, os.path.join(HERE, "small_unet.pt"))
 
     # ---- 2. default UNet(): init hash, small-input logits/loss, per-parameter gradient norms
     torch.manual_seed(1234)

@@ -285,7 +285,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     feats = list(model.features_per_stage)
     layers = model._layers()
     training = model.training
-    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside Function.forward; this is the autograd truth
     dev = x.device
 
     # spatial size per encoder level
@@ -485,7 +485,7 @@ class _BlockFunction(torch.autograd.Function):
                                out=_padded_nhwc(x.size(0), x.size(2), x.size(3), x.size(1), x.device))
         cur = xin
         recs = []
-        need_grad = torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad)
         for conv, norm, act, drop in units:
             wf, wd = ops.pack_conv_weights(conv.weight, need_dgrad=need_grad)
             y, stats = _conv_fwd(cur, wf, conv.stride[0])
