@@ -86,6 +86,9 @@ def rb(x: torch.Tensor, on: bool) -> torch.Tensor:
     return _RoundBF16.apply(x) if on else x
 
 
+TRACE: Optional[list] = None  # debug: set to a list to collect (raw conv output, activation) per conv unit
+
+
 def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: float, cfg: UNetConfig, masks, training,
                bf16_storage: bool = False, fp32_first_weight: bool = False):
     """ConvBlock.forward (unet.py:97-141): [Conv2d 3x3 pad 1 (stride on the first conv only, :103) ->
@@ -98,12 +101,22 @@ def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: f
             if not (fp32_first_weight and i == 0):  # the Cin=3 stem reads the fp32 image with fp32 weights
                 w = w + (w.detach().bfloat16().float() - w.detach())  # bf16 value, straight-through gradient
                 x = rb(x, True)
-        x = F.conv2d(x, w, sd.get(ck + ".bias"), stride=stride if i == 0 else 1, padding=1)
-        x = rb(x, bf16_storage)
+        bias = sd.get(ck + ".bias")
+        if bf16_storage:
+            # the CUDA path stores the bias-free conv output: the bias feeds an InstanceNorm and cancels exactly
+            # (SURVEY.md 8a), so it is added after the rounding, where it changes nothing but its own (zero) gradient
+            x = rb(F.conv2d(x, w, None, stride=stride if i == 0 else 1, padding=1), True)
+            if bias is not None:
+                x = x + bias.view(1, -1, 1, 1)
+        else:
+            x = F.conv2d(x, w, bias, stride=stride if i == 0 else 1, padding=1)
+        y_raw = x
         x = F.instance_norm(x, weight=sd[nk + ".weight"], bias=sd[nk + ".bias"], eps=cfg.eps)
         x = F.leaky_relu(x, cfg.negative_slope)
         if rate > 0 and training:
             x = x * masks.pop(0).expand_as(x)  # unet.py:34
+        if TRACE is not None:
+            TRACE.append((y_raw.detach(), x.detach()))
     return x
 
 

@@ -193,6 +193,7 @@ class UNet(nn.Module):
         # test/DDP hooks (not part of the reference surface)
         self._mask_override: Optional[List[torch.Tensor]] = None  # inject dropout masks instead of drawing them
         self.last_dropout_masks: List[torch.Tensor] = []          # [N,C] scales used by the last training forward
+        self._trace = None                                        # debug: list collecting (raw conv out, activation) per unit
         self._grad_sink = None                                    # callable(param, grad) fired as backward produces grads
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
 
@@ -361,6 +362,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         rec.update(y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale, slope=act.negative_slope, conv=conv, norm=norm)
         saved.append(rec)
         cur = z
+        if model._trace is not None:
+            model._trace.append((y, z))
     head = model.segmentation_output
     if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
         raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
