@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-entry-point CUDA-event timing")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used for ncu captures)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,8 +275,11 @@ def main():
         loss = step(img, msk)
         return loss.item()
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    if args.no_e2e:
+        ms_e2e = float("nan")
+    else:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
     h2d = image_h.numel() * 4 + mask_h.numel() * 8
 
