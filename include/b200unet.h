@@ -109,22 +109,37 @@ int b200unet_in_finalize(const float* stats, int P, const float* gamma, const fl
                          void* stream);
 int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
                       int64_t z_pitch, int N, int64_t HW, int C, void* stream);
-/* Backward (aten::native_batch_norm_backward + leaky_relu_backward + mul in the reference's autograd graph).
+/* Backward (aten::native_batch_norm_backward + leaky_relu_backward + mul in the reference's autograd graph), one call:
  *   g  = (dz + dz2) * (a*y+b > 0 ? 1 : slope) * s ;  xh = (y - mean)*rstd
- *   reduce  : partial sums of g and g*xh per (n,c)            -> part [N][P][C][2]
- *   finalize: S1,S2 per (n,c); dgamma = sum_n S2, dbeta = sum_n S1; coef[N][C][3] = {gamma*rstd, S1/HW, S2/HW}
- *   apply   : dy = coef0 * (g - coef1 - xh*coef2)
- */
-int b200unet_in_bwd_partials(int64_t HW, int C);
-int b200unet_in_bwd_reduce(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch, const void* y,
-                           int64_t y_pitch, const float* a, const float* b, const float* mean, const float* rstd,
-                           const float* drop_scale, float slope, float* part, int N, int64_t HW, int C, void* stream);
-int b200unet_in_bwd_finalize(const float* part, int P, const float* gamma, const float* rstd, float* dgamma,
-                             float* dbeta, float* coef, int N, int C, int64_t HW, void* stream);
-int b200unet_in_bwd_apply(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch, const void* y,
-                          int64_t y_pitch, const float* a, const float* b, const float* mean, const float* rstd,
-                          const float* drop_scale, const float* coef, float slope, void* dy, int64_t dy_pitch, int N,
-                          int64_t HW, int C, void* stream);
+ *   dy = gamma*rstd * (g - mean_hw(g) - xh*mean_hw(g*xh)) ;  dgamma = sum g*xh ;  dbeta = sum g
+ * Runs reduce -> finalize -> apply over chunks of images small enough that the apply pass re-reads dz and y from
+ * L2 rather than HBM.  All reductions are in fixed order (deterministic). */
+typedef struct {
+  const void* dz;      /* bf16 NHWC gradient wrt the activated output [N,H,W,C], pitch dz_pitch */
+  int64_t dz_pitch;
+  const void* dz2;     /* optional second contribution (skip connection), or NULL */
+  int64_t dz2_pitch;
+  const void* y;       /* bf16 NHWC raw conv output saved by the forward */
+  int64_t y_pitch;
+  const float* a;      /* fp32 [N,C] from b200unet_in_finalize */
+  const float* b;
+  const float* mean;
+  const float* rstd;
+  const float* drop_scale; /* fp32 [N,C] or NULL */
+  const float* gamma;  /* fp32 [C] */
+  float slope;
+  void* dy;            /* bf16 NHWC gradient wrt the raw conv output, pitch dy_pitch */
+  int64_t dy_pitch;
+  float* dgamma;       /* fp32 [C] */
+  float* dbeta;        /* fp32 [C] */
+  float* workspace;    /* at least b200unet_in_backward_workspace() bytes */
+  int64_t workspace_bytes;
+  int N;
+  int64_t HW;
+  int C;
+} b200unet_in_bwd_args;
+int64_t b200unet_in_backward_workspace(int N, int64_t HW, int C);
+int b200unet_in_backward(const b200unet_in_bwd_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Exact 2x bilinear upsampling, align_corners=False -- F.interpolate in UpBlock.forward (unet.py:219-225) --

@@ -37,6 +37,16 @@ class ConvWgradArgs(Structure):
     ]
 
 
+class InBwdArgs(Structure):
+    _fields_ = [
+        ("dz", c_void_p), ("dz_pitch", c_int64), ("dz2", c_void_p), ("dz2_pitch", c_int64), ("y", c_void_p),
+        ("y_pitch", c_int64), ("a", c_void_p), ("b", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
+        ("drop_scale", c_void_p), ("gamma", c_void_p), ("slope", c_float), ("dy", c_void_p), ("dy_pitch", c_int64),
+        ("dgamma", c_void_p), ("dbeta", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("N", c_int), ("HW", c_int64), ("C", c_int),
+    ]
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
 # name -> (restype, argtypes); restype c_int means "status code, raise on non-zero"
@@ -60,10 +70,8 @@ SIGNATURES = {
     "b200unet_stem_wgrad": (c_int, [_P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
     "b200unet_in_finalize": (c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _L, _P]),
     "b200unet_in_apply": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
-    "b200unet_in_bwd_partials": (c_int, [_L, _I]),
-    "b200unet_in_bwd_reduce": (c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _F, _P, _I, _L, _I, _P]),
-    "b200unet_in_bwd_finalize": (c_int, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _L, _P]),
-    "b200unet_in_bwd_apply": (c_int, [_P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
+    "b200unet_in_backward_workspace": (c_int64, [_I, _L, _I]),
+    "b200unet_in_backward": (c_int, [POINTER(InBwdArgs), _P]),
     "b200unet_upsample2x_fwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "b200unet_upsample2x_bwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "b200unet_head_fwd": (c_int, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
@@ -80,7 +88,7 @@ SIGNATURES = {
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
-    "b200unet_in_bwd_partials", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
+    "b200unet_in_backward_workspace", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
 }
 
 

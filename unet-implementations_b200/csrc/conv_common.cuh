@@ -1,0 +1,53 @@
+// Host helpers shared by the tensor-core convolution translation units: TMA descriptors over (pitched) NHWC
+// activations and packed weight matrices, tile-shape selection.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kConvThreads = 192;  // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
+
+static inline int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int64_t pitch, int N, int H, int W, int C,
+                        int hstep, int wstep, int hoff, int woff, int boxC, int boxW, int boxH) {
+  // 4-D view (C, W', H', N) of the sub-lattice {(hoff + hstep*i, woff + wstep*j)} of an NHWC tensor
+  const int Hs = (H - hoff + hstep - 1) / hstep;
+  const int Ws = (W - woff + wstep - 1) / wstep;
+  if (Hs <= 0 || Ws <= 0) return set_error(kErrInvalid, "empty sub-lattice");
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)(wstep * pitch * 2), (uint64_t)(hstep * (int64_t)W * pitch * 2),
+                         (uint64_t)((int64_t)H * W * pitch * 2)};
+  uint32_t box[4] = {(uint32_t)boxC, (uint32_t)boxW, (uint32_t)boxH, 1};
+  const CUtensorMapSwizzle swz = (boxC * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (boxC * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swz == CU_TENSOR_MAP_SWIZZLE_NONE) return set_error(kErrInvalid, "box channel count %d unsupported", boxC);
+  return make_tmap_bf16(m, base + ((int64_t)hoff * W + woff) * pitch, 4, dims, strides, box, swz);
+}
+
+static inline int make_weight_map(CUtensorMap* m, const void* w, int rows, int K, int boxK, int boxRows) {
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)K * 2};
+  uint32_t box[2] = {(uint32_t)boxK, (uint32_t)boxRows};
+  return make_tmap_bf16(m, w, 2, dims, strides, box,
+                        boxK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static inline int pick_bn(int n_total) {
+  if (n_total % 256 == 0) return 256;
+  if (n_total % 128 == 0) return 128;
+  if (n_total % 64 == 0) return 64;
+  if (n_total % 32 == 0) return 32;
+  return 0;
+}
+static inline int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 0); }
+
+
+// fp32 split-K partials [S][9][cin][cout] -> OIHW gradient (conv_tc.cu)
+int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st);
+
+// Narrow-output weight gradient (conv_wgrad_narrow.cu): stride 1, Cout in {32, 64}, Cin a multiple of 32.
+bool wgradn_supported(int Cin, int Cout, int stride);
+int64_t wgradn_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int wgradn_launch(const b200unet_conv_wgrad_args* a, cudaStream_t st);
+
+}  // namespace b200

@@ -17,6 +17,7 @@
 // warps 2..5 = epilogue (TMEM -> registers -> smem -> TMA store / global).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "conv_common.cuh"
 
 namespace b200 {
 
@@ -39,7 +40,6 @@ struct GConvMaps {
   CUtensorMap out;
 };
 
-constexpr int kConvThreads = 192;
 
 template <int BK, int BN, int STAGES>
 struct GConvCfg {
@@ -227,31 +227,6 @@ static void pick_patch(int OW, int* TW, int* TH) {
   *TH = 8;
 }
 
-static int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int64_t pitch, int N, int H, int W, int C,
-                        int hstep, int wstep, int hoff, int woff, int boxC, int boxW, int boxH) {
-  // 4-D view (C, W', H', N) of the sub-lattice {(hoff + hstep*i, woff + wstep*j)} of an NHWC tensor
-  const int Hs = (H - hoff + hstep - 1) / hstep;
-  const int Ws = (W - woff + wstep - 1) / wstep;
-  if (Hs <= 0 || Ws <= 0) return set_error(kErrInvalid, "empty sub-lattice");
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)N};
-  uint64_t strides[3] = {(uint64_t)(wstep * pitch * 2), (uint64_t)(hstep * (int64_t)W * pitch * 2),
-                         (uint64_t)((int64_t)H * W * pitch * 2)};
-  uint32_t box[4] = {(uint32_t)boxC, (uint32_t)boxW, (uint32_t)boxH, 1};
-  const CUtensorMapSwizzle swz = (boxC * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : (boxC * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
-  if (swz == CU_TENSOR_MAP_SWIZZLE_NONE) return set_error(kErrInvalid, "box channel count %d unsupported", boxC);
-  return make_tmap_bf16(m, base + ((int64_t)hoff * W + woff) * pitch, 4, dims, strides, box, swz);
-}
-
-static int make_weight_map(CUtensorMap* m, const void* w, int rows, int K, int boxK, int boxRows) {
-  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
-  uint64_t strides[1] = {(uint64_t)K * 2};
-  uint32_t box[2] = {(uint32_t)boxK, (uint32_t)boxRows};
-  return make_tmap_bf16(m, w, 2, dims, strides, box,
-                        boxK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
-}
-
 template <int BK, int BN, int STAGES>
 static int launch_gconv(const GConvMaps& maps, const GConvParams& p, cudaStream_t st) {
   using Cfg = GConvCfg<BK, BN, STAGES>;
@@ -281,15 +256,6 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
 #undef GC
   return set_error(kErrUnsupported, "no gconv instantiation for BK=%d BN=%d", BK, BN);
 }
-
-static int pick_bn(int n_total) {
-  if (n_total % 256 == 0) return 256;
-  if (n_total % 128 == 0) return 128;
-  if (n_total % 64 == 0) return 64;
-  if (n_total % 32 == 0) return 32;
-  return 0;
-}
-static int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 0); }
 
 }  // namespace b200
 
@@ -615,6 +581,13 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* 
   dw[(static_cast<int64_t>(co) * cin + ci) * 9 + tap] = acc;
 }
 
+int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+  wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, dw, S, cin, cout);
+  B200_LAUNCH_CHECK("wgrad_finalize_kernel");
+  return 0;
+}
+
 struct WgradPlan {
   int U, BN, G, S, gy, gz, total_kb, kb_per_split, TWk, THk, blocks_w, blocks_h, OH, OW;
   int64_t smem_bytes, partial_floats;
@@ -671,6 +644,7 @@ static int launch_wgrad(const WgradMaps& maps, const WgradParams& p, const Wgrad
 }  // namespace b200
 
 extern "C" int64_t b200unet_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int stride) {
+  if (wgradn_supported(Cin, Cout, stride)) return wgradn_workspace_bytes(N, H, W, Cin, Cout);
   WgradPlan pl;
   if (plan_wgrad(N, H, W, Cin, Cout, stride, &pl)) return -1;
   return pl.partial_floats * 4;
@@ -680,6 +654,7 @@ extern "C" int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stre
   B200_CHECK_ARG(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_wgrad: stride %d unsupported", a->stride);
   B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_wgrad: pitches must be multiples of 8 elements");
+  if (wgradn_supported(a->Cin, a->Cout, a->stride)) return wgradn_launch(a, static_cast<cudaStream_t>(stream));
   WgradPlan pl;
   int rc;
   if ((rc = plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->stride, &pl))) return rc;
@@ -731,8 +706,5 @@ extern "C" int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stre
   rc = set_error(kErrUnsupported, "no wgrad instantiation for U=%d BN=%d", pl.U, pl.BN);
 #undef WG
   if (rc) return rc;
-  const int64_t total = static_cast<int64_t>(9) * a->Cin * a->Cout;
-  wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(a->workspace, a->dw, pl.S, a->Cin, a->Cout);
-  B200_LAUNCH_CHECK("wgrad_finalize_kernel");
-  return 0;
+  return launch_wgrad_finalize(a->workspace, a->dw, pl.S, a->Cin, a->Cout, st);
 }

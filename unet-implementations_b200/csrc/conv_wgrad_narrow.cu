@@ -1,0 +1,296 @@
+// Weight gradient of the 3x3 / stride-1 convolutions with a NARROW output (Cout = 32 or 64): the 512^2 and 256^2
+// levels of the UNet (encoder 0/1, decoder 3/4), where K = N*H*W is in the millions and Cout is too small to fill
+// the tensor-core array (a tcgen05.mma costs max(64, N/2) cycles on B200: N = 32 runs at 25 % -- DESIGN.md 3).
+// Replaces the weight-gradient half of aten::convolution_backward for nn.Conv2d (Our_UNet/models/unet.py:106-115).
+//
+// Formulation.  dW[co, kh, kw, ci] = sum_{n,oh,w'} X[n, oh+kh-1, w', ci] * dY[n, oh, w'-kw+1, co]   (zero outside).
+//   The kh shift is put on X and the kw shift on dY, so that each operand is loaded ONCE per pixel block instead of
+//   once per tap, and both the M and the N side of the MMA are widened by a factor 3:
+//     A (MN-major, straight from NHWC): one X patch of (R+3) image rows x 16 pixels per channel chunk.  The M = 128
+//        rows of an MMA are 128/CH "kh slots" of CH channels; slot j is the same patch advanced by j image rows, so
+//        the slots are addressed by the descriptor's leading-dimension stride -- no extra loads.
+//     B (MN-major): three dY tiles of R rows x 16 pixels, shifted by kw-1 pixels (three cheap TMA loads of the narrow
+//        tensor), laid out back to back so that N = 3*Cout = (kw, co).
+//     D[(kh, ci), (kw, co)] += A^T B accumulates in TMEM over the CTA's whole pixel range (split-K over the grid);
+//        one K = 16 MMA per image row of the block.  fp32 partials per split are reduced in fixed order by
+//        wgrad_finalize_kernel (deterministic).
+// L2->SM traffic per 128-pixel block drops from 9 X loads + 1 dY load to 1.4 X loads + 3 dY loads, and the MMA count
+// from 9*Cin/32 to Cin/32 (CH = 32) per image row.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "conv_common.cuh"
+
+namespace b200 {
+
+struct WgradNParams {
+  int N, OH, OW, blocks_w, blocks_h;
+  int total_kb, kb_per_split;
+  int cin, cout;
+  int chunks_per_cta;  // CPB: channel chunks (of CH) whose accumulators live in this CTA's TMEM
+  int stages;
+  float* partial;      // [S][9][cin][cout]
+};
+
+struct WgradNMaps {
+  CUtensorMap x;   // box (CH, 16, R+3, 1)
+  CUtensorMap dy;  // box (CO, 16, R, 1)
+};
+
+constexpr int kWnR = 8;         // image rows per pixel block (K = 16*R = 128 pixels per stage)
+constexpr int kWnMaxStages = 4;
+
+template <int CH, int CO>
+struct WnCfg {
+  static constexpr int kSlots = 128 / CH;              // kh slots per MMA (4 or 2)
+  static constexpr int kGroups = (3 + kSlots - 1) / kSlots;  // MMAs per (row, chunk): 1 (CH=32) or 2 (CH=64)
+  static constexpr int kRowA = CH * 2, kRowB = CO * 2;  // bytes per pixel row in smem
+  static constexpr int kXBytes = (kWnR + 3) * 16 * kRowA;  // one chunk's patch
+  static constexpr int kDyBytes = kWnR * 16 * kRowB;        // one shifted dY tile
+  static constexpr int kNcols = 3 * CO;                     // accumulator columns per MMA group
+  static constexpr uint32_t kSwzA = (CH == 64) ? kSwz128 : kSwz64;
+  static constexpr uint32_t kSwzB = (CO == 64) ? kSwz128 : kSwz64;
+};
+
+template <int CH, int CO>
+__global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_constant__ WgradNMaps maps,
+                                                                  const __grid_constant__ WgradNParams p) {
+  using Cfg = WnCfg<CH, CO>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWnMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWnMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int CPB = p.chunks_per_cta;
+  const int STAGES = p.stages;
+  const int stage_bytes = CPB * Cfg::kXBytes + 3 * Cfg::kDyBytes;
+  const int split = blockIdx.x;
+  const int chunk0 = blockIdx.y * CPB;  // first channel chunk of this CTA
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  const int num_kb = kb_end - kb_begin;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(CPB * Cfg::kGroups * Cfg::kNcols)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_holder, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.x);
+      tma_prefetch_desc(&maps.dy);
+      const int blocks_per_img = p.blocks_w * p.blocks_h;
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb_begin + i;
+        const int n_img = kb / blocks_per_img;
+        const int b_in = kb - n_img * blocks_per_img;
+        const int bh = b_in / p.blocks_w;
+        const int bw = b_in - bh * p.blocks_w;
+        const int h0 = bh * kWnR, w0 = bw * 16;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        uint8_t* sb = smem + s * stage_bytes;
+        // B: dY shifted by kw - 1 pixels: B_kw[oh, w'] = dY[oh, w' - kw + 1]
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_4d(sb + kw * Cfg::kDyBytes, &maps.dy, &full_bar[s], 0, w0 + 1 - kw, h0, n_img);
+        // A: X patch rows [h0 - 1, h0 + R + 2) of each channel chunk
+        for (int j = 0; j < CPB; ++j)
+          tma_load_4d(sb + 3 * Cfg::kDyBytes + j * Cfg::kXBytes, &maps.x, &full_bar[s], (chunk0 + j) * CH, w0, h0 - 1,
+                      n_img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kNcols, 1, 1);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + s * stage_bytes);
+        const uint32_t sx = sb + 3 * Cfg::kDyBytes;
+#pragma unroll 1
+        for (int r = 0; r < kWnR; ++r) {
+          // B: 16 pixels of image row r, three (kw) blocks Cfg::kDyBytes apart; SBO = 8 pixel rows
+          const uint64_t bdesc = umma_smem_desc(sb + r * 16 * Cfg::kRowB, Cfg::kDyBytes, 8 * Cfg::kRowB, Cfg::kSwzB);
+          for (int j = 0; j < CPB; ++j) {
+#pragma unroll
+            for (int g = 0; g < Cfg::kGroups; ++g) {
+              // A: kh slot t of this group = patch row r + g*kSlots + t  ->  leading-dimension stride = one image row
+              const uint64_t adesc = umma_smem_desc(sx + j * Cfg::kXBytes + (r + g * Cfg::kSlots) * 16 * Cfg::kRowA,
+                                                    16 * Cfg::kRowA, 8 * Cfg::kRowA, Cfg::kSwzA);
+              umma_bf16(tmem_base + (j * Cfg::kGroups + g) * Cfg::kNcols, adesc, bdesc, idesc, (i | r) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: TMEM -> fp32 partials
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int slot = row / CH;
+    const int ci_l = row - slot * CH;
+    if (num_kb > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int j = 0; j < CPB; ++j) {
+      const int ci = (chunk0 + j) * CH + ci_l;
+#pragma unroll 1
+      for (int g = 0; g < Cfg::kGroups; ++g) {
+        const int kh = g * Cfg::kSlots + slot;
+#pragma unroll 1
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < CO; c0 += 32) {
+            uint32_t v[32];
+            if (num_kb > 0) {
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (j * Cfg::kGroups + g) * Cfg::kNcols +
+                                kw * CO + c0,
+                            v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) v[t] = 0;
+            }
+            if (kh < 3) {
+              float* dst = p.partial + ((static_cast<size_t>(split) * 9 + kh * 3 + kw) * p.cin + ci) * p.cout + c0;
+              float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                d4[t] = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]),
+                                    __uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+struct WgradNPlan {
+  int CH, CO, CPB, gy, S, stages, blocks_w, blocks_h, total_kb, kb_per_split;
+  int64_t smem_bytes, partial_floats;
+};
+
+static void plan_wgradn(int N, int H, int W, int Cin, int Cout, WgradNPlan* pl) {
+  pl->CO = Cout;
+  pl->CH = (Cin % 64 == 0) ? 64 : 32;
+  const int slots = 128 / pl->CH;
+  const int groups = (3 + slots - 1) / slots;
+  const int chunks = Cin / pl->CH;
+  const int ncols = 3 * Cout;
+  int cpb = 512 / (groups * ncols);  // accumulators that fit in TMEM
+  if (cpb < 1) cpb = 1;
+  if (cpb > chunks) cpb = chunks;
+  // shared memory: at least 2 stages must fit
+  const int xbytes = (kWnR + 3) * 16 * pl->CH * 2, dybytes = kWnR * 16 * Cout * 2;
+  while (cpb > 1 && 2 * (cpb * xbytes + 3 * dybytes) > 200 * 1024) --cpb;
+  while (chunks % cpb != 0) --cpb;  // every CTA gets the same number of chunks
+  pl->CPB = cpb;
+  pl->gy = chunks / cpb;
+  const int stage = cpb * xbytes + 3 * dybytes;
+  int stages = (200 * 1024) / stage;
+  if (stages > kWnMaxStages) stages = kWnMaxStages;
+  if (stages < 2) stages = 2;
+  pl->stages = stages;
+  pl->smem_bytes = static_cast<int64_t>(stages) * stage + 1024;
+  pl->blocks_w = ceil_div(W, 16);
+  pl->blocks_h = ceil_div(H, kWnR);
+  pl->total_kb = N * pl->blocks_w * pl->blocks_h;
+  int S = num_sms() / pl->gy;
+  if (S < 1) S = 1;
+  if (S > pl->total_kb) S = pl->total_kb;
+  pl->kb_per_split = ceil_div(pl->total_kb, S);
+  pl->S = ceil_div(pl->total_kb, pl->kb_per_split);
+  pl->partial_floats = static_cast<int64_t>(pl->S) * 9 * Cin * Cout;
+}
+
+bool wgradn_supported(int Cin, int Cout, int stride) {
+  return stride == 1 && (Cout == 32 || Cout == 64) && Cin % 32 == 0 && Cin > 0;
+}
+
+int64_t wgradn_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
+  WgradNPlan pl;
+  plan_wgradn(N, H, W, Cin, Cout, &pl);
+  return pl.partial_floats * 4;
+}
+
+template <int CH, int CO>
+static int launch_wgradn(const WgradNMaps& maps, const WgradNParams& p, const WgradNPlan& pl, cudaStream_t st) {
+  auto kern = wgradn_kernel<CH, CO>;
+  static int attr_bytes = 0;
+  if (attr_bytes < pl.smem_bytes) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    attr_bytes = (int)pl.smem_bytes;
+  }
+  kern<<<dim3(pl.S, pl.gy), kConvThreads, pl.smem_bytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("wgradn_kernel");
+  return 0;
+}
+
+int wgradn_launch(const b200unet_conv_wgrad_args* a, cudaStream_t st) {
+  WgradNPlan pl;
+  plan_wgradn(a->N, a->H, a->W, a->Cin, a->Cout, &pl);
+  B200_CHECK_ARG(a->workspace_bytes >= pl.partial_floats * 4, "conv_wgrad: workspace too small (%lld < %lld)",
+                 (long long)a->workspace_bytes, (long long)(pl.partial_floats * 4));
+  WgradNParams p{};
+  WgradNMaps maps;
+  p.N = a->N;
+  p.OH = a->H;
+  p.OW = a->W;
+  p.blocks_w = pl.blocks_w;
+  p.blocks_h = pl.blocks_h;
+  p.total_kb = pl.total_kb;
+  p.kb_per_split = pl.kb_per_split;
+  p.cin = a->Cin;
+  p.cout = a->Cout;
+  p.chunks_per_cta = pl.CPB;
+  p.stages = pl.stages;
+  p.partial = a->workspace;
+  int rc;
+  if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0,
+                         0, pl.CH, 16, kWnR + 3)))
+    return rc;
+  if ((rc = make_act_map(&maps.dy, static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, a->N, a->H, a->W, a->Cout, 1,
+                         1, 0, 0, pl.CO, 16, kWnR)))
+    return rc;
+  if (pl.CH == 32 && pl.CO == 32) rc = launch_wgradn<32, 32>(maps, p, pl, st);
+  else if (pl.CH == 32 && pl.CO == 64) rc = launch_wgradn<32, 64>(maps, p, pl, st);
+  else if (pl.CH == 64 && pl.CO == 32) rc = launch_wgradn<64, 32>(maps, p, pl, st);
+  else rc = launch_wgradn<64, 64>(maps, p, pl, st);
+  if (rc) return rc;
+  return launch_wgrad_finalize(a->workspace, a->dw, pl.S, a->Cin, a->Cout, st);
+}
+
+}  // namespace b200

@@ -35,20 +35,74 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
   return r;
 }
 
-__global__ void in_finalize_kernel(const float* __restrict__ stats, int P, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ drop, float eps,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ a,
-                                   float* __restrict__ b, int N, int C, double inv_hw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i - n * C;
+
+// ---------------------------------------------------------------------------------------------- thread mapping
+// A block owns a contiguous pixel range of one image.  Thread t owns the FIXED channel octet c0 = 8*(t % c8n) for
+// every pixel it visits (lane = t / c8n strides over pixels), so all per-channel parameters live in registers:
+// the kernels issue no shared-memory loads per element and are bound by HBM, not by the LSU.
+struct PixelMap {
+  int c8n;      // threads per pixel = C / 8
+  int threads;  // c8n * lanes  (<= kNormThreads)
+  int lanes;    // pixels per sweep
+};
+static PixelMap make_map(int C) {
+  PixelMap m;
+  m.c8n = C >> 3;
+  m.lanes = kNormThreads / m.c8n;
+  if (m.lanes < 1) m.lanes = 1;
+  m.threads = m.lanes * m.c8n;
+  return m;
+}
+// pixels per block so that the whole launch is ~8 blocks per SM, rounded to a multiple of 4 sweeps
+static int64_t pixels_per_block(int64_t HW, int N, const PixelMap& m) {
+  int64_t per_img = ceil_div64(static_cast<int64_t>(num_sms()) * 8, N);
+  if (per_img < 1) per_img = 1;
+  int64_t chunk = ceil_div64(HW, per_img);
+  const int64_t q = static_cast<int64_t>(m.lanes) * 4;
+  chunk = ceil_div64(chunk, q) * q;
+  return chunk;
+}
+
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+  const float4 u = *reinterpret_cast<const float4*>(p);
+  const float4 v = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+// grid (N, C/32), 256 threads: thread (pg = t/32, c = t%32) sums partials p = pg, pg+8, ... in double; fixed-order
+// combine across the 8 groups.  Coalesced: 32 channels x (sum, sumsq) = 256 contiguous bytes per partial.
+__global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restrict__ stats, int P,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ drop, float eps,
+                                                           float* __restrict__ mean, float* __restrict__ rstd,
+                                                           float* __restrict__ a, float* __restrict__ b, int C,
+                                                           double inv_hw) {
+  __shared__ double red[8][32][2];
+  const int n = blockIdx.x;
+  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  const float2* sp = reinterpret_cast<const float2*>(stats) + static_cast<int64_t>(n) * P * C + c;
-  for (int p = 0; p < P; ++p) {
-    const float2 v = sp[static_cast<int64_t>(p) * C];
-    s1 += v.x;
-    s2 += v.y;
+  if (c < C) {
+    const float2* sp = reinterpret_cast<const float2*>(stats) + static_cast<int64_t>(n) * P * C + c;
+    for (int p = pg; p < P; p += 8) {
+      const float2 v = __ldg(sp + static_cast<int64_t>(p) * C);
+      s1 += v.x;
+      s2 += v.y;
+    }
   }
+  red[pg][cl][0] = s1;
+  red[pg][cl][1] = s2;
+  __syncthreads();
+  if (pg != 0 || c >= C) return;
+  s1 = s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s1 += red[k][cl][0];
+    s2 += red[k][cl][1];
+  }
+  const int i = n * C + c;
   const double m = s1 * inv_hw;
   double var = s2 * inv_hw - m * m;
   if (var < 0.0) var = 0.0;
@@ -61,205 +115,242 @@ __global__ void in_finalize_kernel(const float* __restrict__ stats, int P, const
   b[i] = static_cast<float>(s * (static_cast<double>(beta[c]) - m * gr));
 }
 
-// grid (blocks_per_image, N); shared: a[C], b[C]
+// grid (blocks_per_image, N)
 __global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const __nv_bfloat16* __restrict__ y, int64_t yp,
                                                                  const float* __restrict__ a,
                                                                  const float* __restrict__ b, float slope,
                                                                  __nv_bfloat16* __restrict__ z, int64_t zp, int64_t HW,
-                                                                 int C) {
-  extern __shared__ float sm[];
-  float* sa = sm;
-  float* sb = sm + C;
+                                                                 int C, int c8n, int lanes, int64_t chunk) {
   const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += kNormThreads) {
-    sa[c] = a[n * C + c];
-    sb[c] = b[n * C + c];
-  }
-  __syncthreads();
-  const int c8n = C >> 3;
-  const int64_t items = HW * c8n;
-  const __nv_bfloat16* yb = y + static_cast<int64_t>(n) * HW * yp;
-  __nv_bfloat16* zb = z + static_cast<int64_t>(n) * HW * zp;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kNormThreads + threadIdx.x; i < items;
-       i += static_cast<int64_t>(gridDim.x) * kNormThreads) {
-    const int64_t px = i / c8n;
-    const int c0 = static_cast<int>(i - px * c8n) << 3;
-    float f[8];
-    unpack8(ld_stream(yb + px * yp + c0), f);
+  const int c0 = (threadIdx.x % c8n) << 3;
+  const int lane = threadIdx.x / c8n;
+  float ra[8], rb[8];
+  ld8f(a + n * C + c0, ra);
+  ld8f(b + n * C + c0, rb);
+  const int64_t lo = blockIdx.x * chunk;
+  int64_t hi = lo + chunk;
+  if (hi > HW) hi = HW;
+  const __nv_bfloat16* yb = y + static_cast<int64_t>(n) * HW * yp + c0;
+  __nv_bfloat16* zb = z + static_cast<int64_t>(n) * HW * zp + c0;
+  for (int64_t px = lo + lane; px < hi; px += 4 * lanes) {
+    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = fmaf(sa[c0 + j], f[j], sb[c0 + j]);
-      f[j] = t > 0.f ? t : t * slope;
+    for (int u = 0; u < 4; ++u)
+      if (px + u * lanes < hi) v[u] = ld_stream(yb + (px + u * lanes) * yp);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (px + u * lanes >= hi) break;
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(ra[j], f[j], rb[j]);
+        f[j] = t > 0.f ? t : t * slope;
+      }
+      *reinterpret_cast<uint4*>(zb + (px + u * lanes) * zp) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(zb + px * zp + c0) = pack8(f);
   }
 }
 
-struct InBwdArgs {
+// ---------------------------------------------------------------------------------------------- backward
+struct InBwdK {
   const __nv_bfloat16* dz;
   int64_t dzp;
   const __nv_bfloat16* dz2;
   int64_t dz2p;
   const __nv_bfloat16* y;
   int64_t yp;
-  const float *a, *b, *mean, *rstd, *drop;
+  const float *a, *b, *mean;
   float slope;
   int64_t HW;
-  int C;
+  int C, c8n, lanes;
+  int64_t chunk;
+  int n0;  // first image of this launch
 };
 
-__device__ __forceinline__ void in_bwd_g_xh(const InBwdArgs& A, const float* sa, const float* sb, const float* sm_,
-                                            const float* sr, const float* ss, int n, int64_t px, int c0,
-                                            float (&g)[8], float (&xh)[8]) {
-  float yv[8], d[8];
-  unpack8(ld_stream(A.y + (static_cast<int64_t>(n) * A.HW + px) * A.yp + c0), yv);
-  unpack8(ld_stream(A.dz + (static_cast<int64_t>(n) * A.HW + px) * A.dzp + c0), d);
-  if (A.dz2) {
-    float d2[8];
-    unpack8(ld_stream(A.dz2 + (static_cast<int64_t>(n) * A.HW + px) * A.dz2p + c0), d2);
+// T1 = sum dz*m, T2 = sum dz*m*(y - mean) over the block's pixels, m = lrelu'(a*y+b).   grid (P, images)
+__global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, float* __restrict__ part, int P) {
+  extern __shared__ float red[];  // [lanes][c8n][16]
+  const int n = K.n0 + blockIdx.y;
+  const int c8 = threadIdx.x % K.c8n;
+  const int c0 = c8 << 3;
+  const int lane = threadIdx.x / K.c8n;
+  float ra[8], rb[8], rm[8];
+  ld8f(K.a + n * K.C + c0, ra);
+  ld8f(K.b + n * K.C + c0, rb);
+  ld8f(K.mean + n * K.C + c0, rm);
+  float t1[8], t2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] += d2[j];
-  }
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  const int64_t lo = blockIdx.x * K.chunk;
+  int64_t hi = lo + K.chunk;
+  if (hi > K.HW) hi = K.HW;
+  const __nv_bfloat16* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
+  const __nv_bfloat16* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
+  const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  const int lanes = K.lanes;
+  for (int64_t px = lo + lane; px < hi; px += 2 * lanes) {
+    uint4 vy[2], vd[2], vd2[2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float pre = fmaf(sa[c0 + j], yv[j], sb[c0 + j]);
-    g[j] = d[j] * (pre > 0.f ? 1.f : A.slope) * ss[c0 + j];
-    xh[j] = (yv[j] - sm_[c0 + j]) * sr[c0 + j];
-  }
-}
-
-// grid (P, N): block p of image n reduces pixels [p*chunk, (p+1)*chunk) for every channel.
-// shared: 5 parameter vectors [C] + reduction scratch [kNormThreads][16]
-__global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdArgs A, float* __restrict__ part, int P,
-                                                                      int64_t chunk) {
-  extern __shared__ float sm[];
-  const int C = A.C;
-  float* sa = sm;
-  float* sb = sa + C;
-  float* smn = sb + C;
-  float* sr = smn + C;
-  float* ss = sr + C;
-  float* red = ss + C;  // [kNormThreads][16]
-  const int n = blockIdx.y, p = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += kNormThreads) {
-    sa[c] = A.a[n * C + c];
-    sb[c] = A.b[n * C + c];
-    smn[c] = A.mean[n * C + c];
-    sr[c] = A.rstd[n * C + c];
-    ss[c] = A.drop ? A.drop[n * C + c] : 1.f;
-  }
-  __syncthreads();
-  const int c8n = C >> 3;                 // threads per pixel
-  const int lanes = kNormThreads / c8n;   // pixels per sweep (C <= 8*kNormThreads, checked on the host)
-  const int my_c8 = threadIdx.x % c8n;
-  const int my_lane = threadIdx.x / c8n;
-  const int c0 = my_c8 << 3;
-  float s1[8], s2[8];
+    for (int u = 0; u < 2; ++u)
+      if (px + u * lanes < hi) {
+        vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
+        vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
+        if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
+      }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const int64_t lo = p * chunk;
-  int64_t hi = lo + chunk;
-  if (hi > A.HW) hi = A.HW;
-  if (my_lane < lanes) {
-    for (int64_t px = lo + my_lane; px < hi; px += lanes) {
-      float g[8], xh[8];
-      in_bwd_g_xh(A, sa, sb, smn, sr, ss, n, px, c0, g, xh);
+    for (int u = 0; u < 2; ++u) {
+      if (px + u * lanes >= hi) break;
+      float yv[8], d[8];
+      unpack8(vy[u], yv);
+      unpack8(vd[u], d);
+      if (d2b) {
+        float d2[8];
+        unpack8(vd2[u], d2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s1[j] += g[j];
-        s2[j] = fmaf(g[j], xh[j], s2[j]);
+        const float pre = fmaf(ra[j], yv[j], rb[j]);
+        const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
+        t1[j] += gm;
+        t2[j] = fmaf(gm, yv[j] - rm[j], t2[j]);
       }
     }
   }
+  float* mine = red + static_cast<size_t>(threadIdx.x) * 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[threadIdx.x * 16 + j] = s1[j];
-    red[threadIdx.x * 16 + 8 + j] = s2[j];
+    mine[j] = t1[j];
+    mine[8 + j] = t2[j];
   }
   __syncthreads();
-  // thread t < C*2 sums column (c, k) over the pixel lanes in fixed order
-  for (int t = threadIdx.x; t < C * 2; t += kNormThreads) {
+  // thread t < 2C sums value (c, k) over the pixel lanes in fixed order
+  for (int t = threadIdx.x; t < K.C * 2; t += blockDim.x) {
     const int c = t >> 1, k = t & 1;
-    const int c8 = c >> 3, j = c & 7;
+    const int cc8 = c >> 3, j = c & 7;
     float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[(l * c8n + c8) * 16 + k * 8 + j];
-    part[((static_cast<int64_t>(n) * P + p) * C + c) * 2 + k] = s;
+    for (int l = 0; l < lanes; ++l) s += red[(l * K.c8n + cc8) * 16 + k * 8 + j];
+    part[((static_cast<int64_t>(n) * P + blockIdx.x) * K.C + c) * 2 + k] = s;
   }
 }
 
-__global__ void in_bwd_finalize_kernel(const float* __restrict__ part, int P, const float* __restrict__ gamma,
-                                       const float* __restrict__ rstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef, int N, int C,
-                                       double inv_hw) {
+// per (n, c):  S1 = s*T1 = sum g,  S2 = s*rstd*T2 = sum g*xh;  dy = A1*m*dz - A2*(y - mean) - A3 with
+//   A1 = gamma*rstd*s,  A2 = gamma*rstd*rstd*S2/HW,  A3 = gamma*rstd*S1/HW.    grid (images, C/32), 256 threads
+__global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __restrict__ part, int P,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ drop,
+                                                               float* __restrict__ coef, float* __restrict__ imgsum,
+                                                               int C, int n0, double inv_hw) {
+  __shared__ double red[8][32][2];
+  const int n = n0 + blockIdx.x;
+  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;
+  double t1 = 0.0, t2 = 0.0;
+  if (c < C) {
+    const float2* sp = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(n) * P * C + c;
+    for (int p = pg; p < P; p += 8) {
+      const float2 v = sp[static_cast<int64_t>(p) * C];
+      t1 += v.x;
+      t2 += v.y;
+    }
+  }
+  red[pg][cl][0] = t1;
+  red[pg][cl][1] = t2;
+  __syncthreads();
+  if (pg != 0 || c >= C) return;
+  t1 = t2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    t1 += red[k][cl][0];
+    t2 += red[k][cl][1];
+  }
+  const int i = n * C + c;
+  const double s = drop ? static_cast<double>(drop[i]) : 1.0;
+  const double r = rstd[i];
+  const double S1 = s * t1, S2 = s * r * t2;
+  const double gr = static_cast<double>(gamma[c]) * r;
+  float4 k4;
+  k4.x = static_cast<float>(gr * s);
+  k4.y = static_cast<float>(gr * r * S2 * inv_hw);
+  k4.z = static_cast<float>(gr * S1 * inv_hw);
+  k4.w = 0.f;
+  reinterpret_cast<float4*>(coef)[i] = k4;
+  imgsum[i * 2 + 0] = static_cast<float>(S1);
+  imgsum[i * 2 + 1] = static_cast<float>(S2);
+}
+
+// dgamma[c] = sum_n S2, dbeta[c] = sum_n S1 (fixed order)
+__global__ void in_bwd_param_kernel(const float* __restrict__ imgsum, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double dg = 0.0, db = 0.0;
   for (int n = 0; n < N; ++n) {
-    double s1 = 0.0, s2 = 0.0;
-    const float2* sp = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(n) * P * C + c;
-    for (int p = 0; p < P; ++p) {
-      const float2 v = sp[static_cast<int64_t>(p) * C];
-      s1 += v.x;
-      s2 += v.y;
-    }
-    db += s1;
-    dg += s2;
-    float* co = coef + (static_cast<int64_t>(n) * C + c) * 3;
-    co[0] = gamma[c] * rstd[n * C + c];
-    co[1] = static_cast<float>(s1 * inv_hw);
-    co[2] = static_cast<float>(s2 * inv_hw);
+    db += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 0];
+    dg += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 1];
   }
   dgamma[c] = static_cast<float>(dg);
   dbeta[c] = static_cast<float>(db);
 }
 
-// grid (blocks_per_image, N); shared: 5 parameter vectors [C] + coef [C][3]
-__global__ void __launch_bounds__(kNormThreads) in_bwd_apply_kernel(InBwdArgs A, const float* __restrict__ coef,
+// grid (blocks_per_image, images)
+__global__ void __launch_bounds__(kNormThreads) in_bwd_apply_kernel(InBwdK K, const float* __restrict__ coef,
                                                                      __nv_bfloat16* __restrict__ dy, int64_t dyp) {
-  extern __shared__ float sm[];
-  const int C = A.C;
-  float* sa = sm;
-  float* sb = sa + C;
-  float* smn = sb + C;
-  float* sr = smn + C;
-  float* ss = sr + C;
-  float* sc = ss + C;  // [C][3]
-  const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += kNormThreads) {
-    sa[c] = A.a[n * C + c];
-    sb[c] = A.b[n * C + c];
-    smn[c] = A.mean[n * C + c];
-    sr[c] = A.rstd[n * C + c];
-    ss[c] = A.drop ? A.drop[n * C + c] : 1.f;
-    sc[c * 3 + 0] = coef[(static_cast<int64_t>(n) * C + c) * 3 + 0];
-    sc[c * 3 + 1] = coef[(static_cast<int64_t>(n) * C + c) * 3 + 1];
-    sc[c * 3 + 2] = coef[(static_cast<int64_t>(n) * C + c) * 3 + 2];
-  }
-  __syncthreads();
-  const int c8n = C >> 3;
-  const int64_t items = A.HW * c8n;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kNormThreads + threadIdx.x; i < items;
-       i += static_cast<int64_t>(gridDim.x) * kNormThreads) {
-    const int64_t px = i / c8n;
-    const int c0 = static_cast<int>(i - px * c8n) << 3;
-    float g[8], xh[8], o[8];
-    in_bwd_g_xh(A, sa, sb, smn, sr, ss, n, px, c0, g, xh);
+  const int n = K.n0 + blockIdx.y;
+  const int c0 = (threadIdx.x % K.c8n) << 3;
+  const int lane = threadIdx.x / K.c8n;
+  float ra[8], rb[8], rm[8], k1[8], k2[8], k3[8];
+  ld8f(K.a + n * K.C + c0, ra);
+  ld8f(K.b + n * K.C + c0, rb);
+  ld8f(K.mean + n * K.C + c0, rm);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float* k = sc + (c0 + j) * 3;
-      o[j] = k[0] * (g[j] - k[1] - xh[j] * k[2]);
-    }
-    *reinterpret_cast<uint4*>(dy + (static_cast<int64_t>(n) * A.HW + px) * dyp + c0) = pack8(o);
+  for (int j = 0; j < 8; ++j) {
+    const float4 k = reinterpret_cast<const float4*>(coef)[n * K.C + c0 + j];
+    k1[j] = k.x;
+    k2[j] = k.y;
+    k3[j] = k.z;
   }
-}
-
-static int elementwise_blocks(int64_t items, int N) {
-  // enough blocks for ~8 waves over the chip, each thread doing several 16-byte items
-  int64_t b = ceil_div64(items, static_cast<int64_t>(kNormThreads) * 4);
-  const int64_t cap = ceil_div64(static_cast<int64_t>(num_sms()) * 16, N);
-  if (b > cap) b = cap;
-  if (b < 1) b = 1;
-  return static_cast<int>(b);
+  const int64_t lo = blockIdx.x * K.chunk;
+  int64_t hi = lo + K.chunk;
+  if (hi > K.HW) hi = K.HW;
+  const __nv_bfloat16* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
+  const __nv_bfloat16* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
+  const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  __nv_bfloat16* ob = dy + static_cast<int64_t>(n) * K.HW * dyp + c0;
+  const int lanes = K.lanes;
+  for (int64_t px = lo + lane; px < hi; px += 2 * lanes) {
+    uint4 vy[2], vd[2], vd2[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (px + u * lanes < hi) {
+        vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
+        vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
+        if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (px + u * lanes >= hi) break;
+      float yv[8], d[8], o[8];
+      unpack8(vy[u], yv);
+      unpack8(vd[u], d);
+      if (d2b) {
+        float d2[8];
+        unpack8(vd2[u], d2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(ra[j], yv[j], rb[j]);
+        const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
+        o[j] = fmaf(k1[j], gm, -fmaf(k2[j], yv[j] - rm[j], k3[j]));
+      }
+      *reinterpret_cast<uint4*>(ob + (px + u * lanes) * dyp) = pack8(o);
+    }
+  }
 }
 
 static int check_nhwc(const char* what, int C, int64_t p0, int64_t p1, int64_t p2) {
@@ -276,9 +367,9 @@ extern "C" int b200unet_in_finalize(const float* stats, int P, const float* gamm
                                     const float* drop_scale, float eps, float* mean, float* rstd, float* a, float* b,
                                     int N, int C, int64_t HW, void* stream) {
   B200_CHECK_ARG(stats && gamma && beta && mean && rstd && a && b, "in_finalize: null pointer");
-  B200_CHECK_ARG(P > 0 && HW > 0, "in_finalize: bad sizes");
-  in_finalize_kernel<<<ceil_div(N * C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, P, gamma, beta, drop_scale, eps, mean, rstd, a, b, N, C, 1.0 / static_cast<double>(HW));
+  B200_CHECK_ARG(P > 0 && HW > 0 && N > 0 && C > 0, "in_finalize: bad sizes");
+  in_finalize_kernel<<<dim3(N, ceil_div(C, 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, P, gamma, beta, drop_scale, eps, mean, rstd, a, b, C, 1.0 / static_cast<double>(HW));
   B200_LAUNCH_CHECK("in_finalize_kernel");
   return 0;
 }
@@ -288,84 +379,88 @@ extern "C" int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a,
   B200_CHECK_ARG(y && a && b && z, "in_apply: null pointer");
   int rc = check_nhwc("in_apply", C, y_pitch, z_pitch, 0);
   if (rc) return rc;
-  const int blocks = elementwise_blocks(HW * (C / 8), N);
-  in_apply_kernel<<<dim3(blocks, N), kNormThreads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), y_pitch, a, b, slope, static_cast<__nv_bfloat16*>(z), z_pitch, HW, C);
+  const PixelMap m = make_map(C);
+  const int64_t chunk = pixels_per_block(HW, N, m);
+  in_apply_kernel<<<dim3((unsigned)ceil_div64(HW, chunk), N), m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), y_pitch, a, b, slope, static_cast<__nv_bfloat16*>(z), z_pitch, HW, C, m.c8n,
+      m.lanes, chunk);
   B200_LAUNCH_CHECK("in_apply_kernel");
   return 0;
 }
 
-extern "C" int b200unet_in_bwd_partials(int64_t HW, int C) {
+// Images per launch group.  Splitting the batch into L2-sized groups (so the apply pass re-reads dz and y from L2)
+// was measured SLOWER on B200 at 512^2 x 32 channels: one image per group means ~10 us kernels whose launch gaps and
+// ramp-up/tail cost more than the saved HBM reads (13.7 ms vs 9.2 ms per step over the 22 layers).  The whole batch
+// therefore goes in one group; the partial sums are to move into the producers' epilogues instead.
+static int bwd_images_per_chunk(int N, int64_t HW, int C, bool has_dz2) {
+  (void)HW;
   (void)C;
-  int64_t p = HW / 1024;
-  if (p < 1) p = 1;
-  if (p > 64) p = 64;
-  return static_cast<int>(p);
+  (void)has_dz2;
+  return N;
+}
+static int bwd_partials(int N, int64_t HW, int C, bool has_dz2) {
+  const PixelMap m = make_map(C);
+  const int ipc = bwd_images_per_chunk(N, HW, C, has_dz2);
+  const int64_t chunk = pixels_per_block(HW, ipc, m);
+  return static_cast<int>(ceil_div64(HW, chunk));
 }
 
-static InBwdArgs make_bwd_args(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch, const void* y,
-                               int64_t y_pitch, const float* a, const float* b, const float* mean, const float* rstd,
-                               const float* drop, float slope, int64_t HW, int C) {
-  InBwdArgs A;
-  A.dz = static_cast<const __nv_bfloat16*>(dz);
-  A.dzp = dz_pitch;
-  A.dz2 = static_cast<const __nv_bfloat16*>(dz2);
-  A.dz2p = dz2_pitch;
-  A.y = static_cast<const __nv_bfloat16*>(y);
-  A.yp = y_pitch;
-  A.a = a;
-  A.b = b;
-  A.mean = mean;
-  A.rstd = rstd;
-  A.drop = drop;
-  A.slope = slope;
-  A.HW = HW;
-  A.C = C;
-  return A;
+extern "C" int64_t b200unet_in_backward_workspace(int N, int64_t HW, int C) {
+  // worst case over has_dz2: partials [N][P][C][2] + coef [N][C][4] + per-image sums [N][C][2]
+  const int P0 = bwd_partials(N, HW, C, false), P1 = bwd_partials(N, HW, C, true);
+  const int P = P0 > P1 ? P0 : P1;
+  return (static_cast<int64_t>(N) * P * C * 2 + static_cast<int64_t>(N) * C * 6) * 4;
 }
 
-extern "C" int b200unet_in_bwd_reduce(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch,
-                                      const void* y, int64_t y_pitch, const float* a, const float* b,
-                                      const float* mean, const float* rstd, const float* drop_scale, float slope,
-                                      float* part, int N, int64_t HW, int C, void* stream) {
-  B200_CHECK_ARG(dz && y && a && b && mean && rstd && part, "in_bwd_reduce: null pointer");
-  int rc = check_nhwc("in_bwd_reduce", C, dz_pitch, dz2 ? dz2_pitch : 0, y_pitch);
+extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream) {
+  B200_CHECK_ARG(A && A->dz && A->y && A->a && A->b && A->mean && A->rstd && A->gamma && A->dy && A->dgamma &&
+                     A->dbeta && A->workspace,
+                 "in_backward: null pointer");
+  int rc = check_nhwc("in_backward", A->C, A->dz_pitch, A->dz2 ? A->dz2_pitch : 0, A->y_pitch);
   if (rc) return rc;
-  const int P = b200unet_in_bwd_partials(HW, C);
-  InBwdArgs A = make_bwd_args(dz, dz_pitch, dz2, dz2_pitch, y, y_pitch, a, b, mean, rstd, drop_scale, slope, HW, C);
-  const size_t smem = (5 * C + kNormThreads * 16) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    B200_CUDA(cudaFuncSetAttribute(in_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
+  B200_CHECK_ARG(A->dy_pitch % 8 == 0, "in_backward: dy pitch must be a multiple of 8");
+  const int N = A->N, C = A->C;
+  const int64_t HW = A->HW;
+  B200_CHECK_ARG(A->workspace_bytes >= b200unet_in_backward_workspace(N, HW, C), "in_backward: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool has2 = A->dz2 != nullptr;
+  const PixelMap m = make_map(C);
+  const int ipc = bwd_images_per_chunk(N, HW, C, has2);
+  const int64_t chunk = pixels_per_block(HW, ipc, m);
+  const int P = static_cast<int>(ceil_div64(HW, chunk));
+  float* part = A->workspace;
+  float* coef = part + static_cast<int64_t>(N) * P * C * 2;
+  float* imgsum = coef + static_cast<int64_t>(N) * C * 4;
+  InBwdK K;
+  K.dz = static_cast<const __nv_bfloat16*>(A->dz);
+  K.dzp = A->dz_pitch;
+  K.dz2 = static_cast<const __nv_bfloat16*>(A->dz2);
+  K.dz2p = A->dz2_pitch;
+  K.y = static_cast<const __nv_bfloat16*>(A->y);
+  K.yp = A->y_pitch;
+  K.a = A->a;
+  K.b = A->b;
+  K.mean = A->mean;
+  K.slope = A->slope;
+  K.HW = HW;
+  K.C = C;
+  K.c8n = m.c8n;
+  K.lanes = m.lanes;
+  K.chunk = chunk;
+  const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(float);
+  const double inv_hw = 1.0 / static_cast<double>(HW);
+  for (int n0 = 0; n0 < N; n0 += ipc) {
+    const int nn = (N - n0 < ipc) ? N - n0 : ipc;
+    K.n0 = n0;
+    in_bwd_reduce_kernel<<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+    B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
+    in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
+                                                                     imgsum, C, n0, inv_hw);
+    B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
+    in_bwd_apply_kernel<<<dim3(P, nn), m.threads, 0, st>>>(K, coef, static_cast<__nv_bfloat16*>(A->dy), A->dy_pitch);
+    B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
-  in_bwd_reduce_kernel<<<dim3(P, N), kNormThreads, smem, static_cast<cudaStream_t>(stream)>>>(A, part, P,
-                                                                                              ceil_div64(HW, P));
-  B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
-  return 0;
-}
-
-extern "C" int b200unet_in_bwd_finalize(const float* part, int P, const float* gamma, const float* rstd, float* dgamma,
-                                        float* dbeta, float* coef, int N, int C, int64_t HW, void* stream) {
-  B200_CHECK_ARG(part && gamma && rstd && dgamma && dbeta && coef, "in_bwd_finalize: null pointer");
-  in_bwd_finalize_kernel<<<ceil_div(C, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      part, P, gamma, rstd, dgamma, dbeta, coef, N, C, 1.0 / static_cast<double>(HW));
-  B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
-  return 0;
-}
-
-extern "C" int b200unet_in_bwd_apply(const void* dz, int64_t dz_pitch, const void* dz2, int64_t dz2_pitch,
-                                     const void* y, int64_t y_pitch, const float* a, const float* b, const float* mean,
-                                     const float* rstd, const float* drop_scale, const float* coef, float slope,
-                                     void* dy, int64_t dy_pitch, int N, int64_t HW, int C, void* stream) {
-  B200_CHECK_ARG(dz && y && a && b && mean && rstd && coef && dy, "in_bwd_apply: null pointer");
-  int rc = check_nhwc("in_bwd_apply", C, dz_pitch, dz2 ? dz2_pitch : 0, y_pitch);
-  if (rc) return rc;
-  B200_CHECK_ARG(dy_pitch % 8 == 0, "in_bwd_apply: dy pitch must be a multiple of 8");
-  InBwdArgs A = make_bwd_args(dz, dz_pitch, dz2, dz2_pitch, y, y_pitch, a, b, mean, rstd, drop_scale, slope, HW, C);
-  const int blocks = elementwise_blocks(HW * (C / 8), N);
-  in_bwd_apply_kernel<<<dim3(blocks, N), kNormThreads, 8 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      A, coef, static_cast<__nv_bfloat16*>(dy), dy_pitch);
-  B200_LAUNCH_CHECK("in_bwd_apply_kernel");
+  in_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+  B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
 }

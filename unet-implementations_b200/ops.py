@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvDgradArgs, ConvFpropArgs, ConvWgradArgs
+from ._lib import ConvDgradArgs, ConvFpropArgs, ConvWgradArgs, InBwdArgs
 
 BF16 = torch.bfloat16
 
@@ -165,18 +165,14 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
     Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C])."""
     n, h, w, c = y.shape
     hw = h * w
-    parts = _lib.call("b200unet_in_bwd_partials", hw, c)
-    part = torch.empty((n, parts, c, 2), dtype=torch.float32, device=y.device)
-    dz2p = pitch_of(dz2) if dz2 is not None else 0
-    _lib.call("b200unet_in_bwd_reduce", _p(dz), pitch_of(dz), _p(dz2), dz2p, _p(y), pitch_of(y), _p(a), _p(b),
-              _p(mean), _p(rstd), _p(drop_scale), float(slope), _p(part), n, hw, c, _stream())
+    nbytes = _lib.call("b200unet_in_backward_workspace", n, hw, c)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=y.device)
     dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
-    coef = torch.empty((n, c, 3), dtype=torch.float32, device=y.device)
-    _lib.call("b200unet_in_bwd_finalize", _p(part), parts, _p(_f32(gamma.detach())), _p(rstd), _p(dgb[0]), _p(dgb[1]),
-              _p(coef), n, c, hw, _stream())
     dy = torch.empty((n, h, w, c), dtype=BF16, device=y.device)
-    _lib.call("b200unet_in_bwd_apply", _p(dz), pitch_of(dz), _p(dz2), dz2p, _p(y), pitch_of(y), _p(a), _p(b), _p(mean),
-              _p(rstd), _p(drop_scale), _p(coef), float(slope), _p(dy), pitch_of(dy), n, hw, c, _stream())
+    args = InBwdArgs(_p(dz), pitch_of(dz), _p(dz2), pitch_of(dz2) if dz2 is not None else 0, _p(y), pitch_of(y), _p(a),
+                     _p(b), _p(mean), _p(rstd), _p(drop_scale), _p(_f32(gamma.detach())), float(slope), _p(dy),
+                     pitch_of(dy), _p(dgb[0]), _p(dgb[1]), _p(ws), nbytes, n, hw, c)
+    _lib.call("b200unet_in_backward", ctypes.byref(args), _stream())
     return dy, dgb[0], dgb[1]
 
 
