@@ -5,7 +5,14 @@
 
 namespace b200 {
 
-constexpr int kConvThreads = 192;  // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
+// Warp roles of the tensor-core conv kernels.  A cp.async.bulk.tensor issue blocks its thread for ~420 cycles (4-D
+// box) / ~200 cycles (2-D box) on B200 regardless of the box size (tools/micro/tma_rate.cu), so ONE producer thread
+// caps a CTA at one box per ~420 cycles (< 20 B/cycle/SM with 8 KB boxes): the loads are spread over four producer
+// warps (one elected lane each), which issue concurrently.
+constexpr int kProducerWarps = 4;                 // warps 0..3: TMA producers
+constexpr int kMmaWarp = 4;                       // warp 4: TMEM owner + single-thread MMA issuer
+constexpr int kEpiWarp0 = 5;                      // warps 5..8: epilogue (TMEM lane quarter = warp % 4)
+constexpr int kConvThreads = 32 * (kEpiWarp0 + 4);
 
 static inline int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int64_t pitch, int N, int H, int W, int C,
                         int hstep, int wstep, int hoff, int woff, int boxC, int boxW, int boxH) {
@@ -38,6 +45,11 @@ static inline int pick_bn(int n_total) {
   if (n_total % 64 == 0) return 64;
   if (n_total % 32 == 0) return 32;
   return 0;
+}
+// N tile of the fprop/dgrad kernel: additionally 96 (one tile instead of three 32-wide ones, 75 % MMA rate)
+static inline int pick_bn_gconv(int n_total, int bk) {
+  if (n_total == 96 && bk == 32) return 96;
+  return pick_bn(n_total);
 }
 static inline int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 0); }
 

@@ -1,0 +1,632 @@
+// Implicit-GEMM 3x3 convolutions on tcgen05 / TMEM, operands staged by TMA (sm_100a only): forward and data gradient.
+//
+// Replaces nn.Conv2d forward and the data-gradient half of aten::convolution_backward for the ConvBlock convs of the
+// reference (Our_UNet/models/unet.py:106-115).  Activations are NHWC bf16, accumulation fp32 in tensor memory.
+//
+//   D[128 pixels, BN] = sum over taps (kh,kw) and channel chunks c of
+//        A_tap[128 pixels, BK channels]  x  W[BN, tap*C + c*BK .. +BK]^T
+//   A 128-pixel tile is an 8 x 16 patch of one image of the output lattice.
+//
+// Operand staging ("patch loads").  A tap-shifted A tile is 8 whole image rows of 16 pixels, i.e. 128 contiguous
+// 128-byte (64-byte for BK = 32) rows in shared memory.  Taps that differ only in their ROW shift are therefore windows
+// of ONE (8 + r) x 16 patch at a 16-row (2048-byte: swizzle-aligned) offset: a stride-1 conv loads 3 patches of 10
+// rows per channel chunk (one per column shift, the column shift and the zero padding are TMA coordinates /
+// out-of-bounds fill) instead of 9 tiles -- 2.4x less L2->SM traffic and 3x fewer TMA instructions, which matters
+// because a 4-D cp.async.bulk.tensor costs its issuing thread ~420 cycles on B200 (tools/micro/tma_rate.cu).
+// Stride 2: fprop reads the four parity sub-lattices of the input (6 patch loads per chunk); dgrad writes the four
+// parity sub-lattices of dx through four launches (gather form: no scatter, no atomics).
+// Weights (B): K-major [BN x BK] tiles of the packed weight matrix; when the whole slab of a layer (taps x chunks)
+// fits in ~72 KB it is loaded ONCE per CTA and stays resident (all Cout <= 96 layers), otherwise it streams through
+// its own ring.
+//
+// Persistent CTAs (one per SM) with three pipelines: A ring and B ring (TMA <-> MMA) running across tiles, and two
+// TMEM accumulator buffers (MMA <-> epilogue) so that the epilogue of tile i overlaps the mainloop of tile i+1.
+// Warp roles (288 threads): warps 0..3 = TMA producers (one elected lane each, issuing concurrently; each owns a
+// fixed subset of ring slots so that it observes every phase of its barriers in order), warp 4 = TMEM allocator +
+// single-thread MMA issuer, warps 5..8 = epilogue: tcgen05.ld -> bf16 -> swizzled staging -> TMA store, plus the
+// per-(n,c) sum / sum-of-squares partials of the stored values that InstanceNorm needs (deterministic, no atomics).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "conv_common.cuh"
+#include <stdlib.h>
+
+namespace b200 {
+
+constexpr int kTH = 8, kTW = 16;  // output patch of a tile
+constexpr int kMaxLoads = 9;
+
+struct ALoad {
+  int dh, dw;       // patch origin relative to the tile origin (in the load's source lattice)
+  int rows;         // patch height in image rows (8 .. 10)
+  int ntaps;        // taps served by this patch
+  int rowoff[3];    // image-row offset of each tap's window inside the patch
+  int koff[3];      // K offset (elements) of each tap in the packed weight matrix
+};
+
+struct GConvParams {
+  int N, OH, OW, tiles_w, tiles_h;
+  int nloads, ntaps_total;
+  int s1;  // 1 when the loads are the stride-1 pattern: 3 patches, each serving row windows 0, 1, 2 in this order
+  ALoad loads[kMaxLoads];
+  int cin;   // channels per tap on the K side (multiple of BK)
+  int cout;  // total N of the GEMM
+  float* stats;
+  long long* debug;  // optional [gridDim.x][8] cycle counters (developer instrumentation; NULL in production)
+};
+
+struct GConvMaps {
+  CUtensorMap src[kMaxLoads];  // one per patch load (the box height is part of the descriptor)
+  CUtensorMap w;
+  CUtensorMap out;
+};
+
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+struct GConvCfg {
+  static constexpr int kRowBytes = BK * 2;
+  static constexpr int kASlotBytes = (kTH + 2) * kTW * kRowBytes;              // largest patch (10 rows)
+  static constexpr int kBTileBytes = ((BN * BK * 2 + 1023) / 1024) * 1024;     // one [BN x BK] weight tile
+  static constexpr int kBTileTx = BN * BK * 2;
+  static constexpr int kBResBytes = 72 * 1024;                                 // resident weight slab budget
+  static constexpr int kBBytes = B_RES ? kBResBytes : B_SLOTS * kBTileBytes;
+  static constexpr int kOC = (BN % 64 == 0) ? 64 : 32;                         // channels per TMA-store box
+  static constexpr int kStageBufBytes = 128 * kOC * 2;                         // one staging buffer (two are used)
+  static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBBytes + 2 * kStageBufBytes + 1024;
+  static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
+  static constexpr uint32_t kSbo = 8 * kRowBytes;
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                        : (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers
+  // producers: A loads go to warps [0, NA), B tiles (streaming) to warps [4 - NB, 4)
+  static constexpr int NA = B_RES ? ((A_SLOTS % 4 == 0) ? 4 : (A_SLOTS % 2 == 0) ? 2 : 1)
+                                  : ((A_SLOTS % 2 == 0) ? 2 : 1);
+  static constexpr int NB = B_RES ? 0 : ((B_SLOTS % 2 == 0) ? 2 : 1);
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+__global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_constant__ GConvMaps maps,
+                                                                 const __grid_constant__ GConvParams p) {
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
+  constexpr int kBBar = B_RES ? 1 : B_SLOTS;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
+  __shared__ __align__(8) uint64_t b_full[kBBar], b_empty[kBBar];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_holder;
+  __shared__ float red[4][(BN % 64 == 0) ? 64 : 32][2];  // per staging chunk
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + A_SLOTS * Cfg::kASlotBytes;
+  uint8_t* staging = smem_b + Cfg::kBBytes;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int n_tiles = p.cout / BN;
+  const int total_tiles = tiles_per_img * p.N * n_tiles;
+  const int chunks = p.cin / BK;
+  const int loads_per_tile = chunks * p.nloads;
+  const int btiles_per_tile = chunks * p.ntaps_total;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kBBar; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&tmem_base_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp < kProducerWarps) {
+    if (elect_one()) {
+      if (B_RES && warp == 0) {
+        // ---------------------------------------------------------- resident weights: the whole (taps x chunks) slab
+        // of the layer, loaded once per CTA (resident mode is dispatched only when cout == BN, i.e. n0 == 0)
+        tma_prefetch_desc(&maps.w);
+        mbar_expect_tx(&b_full[0], static_cast<uint32_t>(btiles_per_tile) * Cfg::kBTileTx);
+        int u = 0;
+        for (int c = 0; c < chunks; ++c)
+          for (int l = 0; l < p.nloads; ++l)
+            for (int t = 0; t < p.loads[l].ntaps; ++t, ++u)
+              tma_load_2d(smem_b + u * Cfg::kBTileBytes, &maps.w, &b_full[0], p.loads[l].koff[t] + c * BK, 0);
+      }
+      if (warp < Cfg::NA) {
+        // ------------------------------------------------------------ A producer `warp` of NA: patch loads
+        tma_prefetch_desc(&maps.src[0]);
+        long long dbg_wait = 0, dbg_issue = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const int m_tile = tile / n_tiles;
+          const int n_img = m_tile / tiles_per_img;
+          const int t_in = m_tile - n_img * tiles_per_img;
+          const int th = t_in / p.tiles_w;
+          const int h0 = th * kTH, w0 = (t_in - th * p.tiles_w) * kTW;
+          const long long g0 = static_cast<long long>(it) * loads_per_tile;  // global load index of this tile's first
+          int i = (warp - static_cast<int>(g0 % Cfg::NA) + Cfg::NA) % Cfg::NA;
+          for (; i < loads_per_tile; i += Cfg::NA) {
+            const long long g = g0 + i;
+            const int slot = static_cast<int>(g % A_SLOTS);
+            const uint32_t ph = static_cast<uint32_t>((g / A_SLOTS) & 1);
+            const int c = i / p.nloads;
+            const int l = i - c * p.nloads;
+            const ALoad& L = p.loads[l];
+            const long long t0 = p.debug ? clock64() : 0;
+            mbar_wait(&a_empty[slot], ph ^ 1);
+            const long long t1 = p.debug ? clock64() : 0;
+            mbar_expect_tx(&a_full[slot], L.rows * kTW * Cfg::kRowBytes);
+            tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src[l], &a_full[slot], c * BK, w0 + L.dw, h0 + L.dh, n_img);
+            if (p.debug) {
+              dbg_wait += t1 - t0;
+              dbg_issue += clock64() - t1;
+            }
+          }
+        }
+        if (p.debug && warp == 0) {
+          p.debug[blockIdx.x * 8 + 0] = dbg_wait;
+          p.debug[blockIdx.x * 8 + 1] = dbg_issue;
+        }
+      } else if (!B_RES && warp >= kProducerWarps - Cfg::NB) {
+        // ------------------------------------------------------------ B producer: one [BN x BK] tile per (tap, chunk)
+        const int me = warp - (kProducerWarps - Cfg::NB);
+        tma_prefetch_desc(&maps.w);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const int m_tile = tile / n_tiles;
+          const int n0 = (tile - m_tile * n_tiles) * BN;
+          const long long g0 = static_cast<long long>(it) * btiles_per_tile;
+          int u = 0;
+          for (int c = 0; c < chunks; ++c)
+            for (int l = 0; l < p.nloads; ++l)
+              for (int t = 0; t < p.loads[l].ntaps; ++t, ++u) {
+                const long long g = g0 + u;
+                if (static_cast<int>(g % Cfg::NB) != me) continue;
+                const int slot = static_cast<int>(g % B_SLOTS);
+                const uint32_t ph = static_cast<uint32_t>((g / B_SLOTS) & 1);
+                mbar_wait(&b_empty[slot], ph ^ 1);
+                mbar_expect_tx(&b_full[slot], Cfg::kBTileTx);
+                tma_load_2d(smem_b + slot * Cfg::kBTileBytes, &maps.w, &b_full[slot], p.loads[l].koff[t] + c * BK, n0);
+              }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      // ONE thread issues every MMA of the CTA: its scalar instruction stream is the critical path, so everything
+      // that can be is hoisted -- descriptors are 32-bit adds on precomputed halves, barrier addresses are
+      // precomputed, the stride-1 tap pattern (3 patches x 3 row windows) is fully unrolled.
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);
+      constexpr uint32_t kWin = (kTW * Cfg::kRowBytes) >> 4;       // one image row of the patch, in 16-byte units
+      constexpr uint32_t kASlot16 = Cfg::kASlotBytes >> 4, kBTile16 = Cfg::kBTileBytes >> 4;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b), 16);
+      const uint32_t a_full0 = smem_u32(&a_full[0]), a_empty0 = smem_u32(&a_empty[0]);
+      const uint32_t b_full0 = smem_u32(&b_full[0]), b_empty0 = smem_u32(&b_empty[0]);
+      if (B_RES) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      const bool s1 = p.s1 != 0;
+      uint32_t aslot = 0, aph = 0, bslot = 0, bph = 0;  // ring positions and phase parities (run across tiles)
+      long long dbg_te = 0, dbg_af = 0, dbg_total0 = clock64();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long long t0 = p.debug ? clock64() : 0;
+        mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // epilogue drained this buffer
+        if (p.debug) dbg_te += clock64() - t0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t acc = 0;
+        uint32_t b_res = b_lo0;  // next resident weight tile
+        for (int c = 0; c < chunks; ++c) {
+          const int nl = s1 ? 3 : p.nloads;
+#pragma unroll 3
+          for (int l = 0; l < nl; ++l) {
+            const long long t1 = p.debug ? clock64() : 0;
+            mbar_wait_u32(a_full0 + aslot * 8, aph);
+            if (p.debug) dbg_af += clock64() - t1;
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + aslot * kASlot16;
+            const int nt = s1 ? 3 : p.loads[l].ntaps;
+#pragma unroll 3
+            for (int t = 0; t < nt; ++t) {
+              uint32_t b_lo;
+              if (B_RES) {
+                b_lo = b_res;
+                b_res += kBTile16;
+              } else {
+                mbar_wait_u32(b_full0 + bslot * 8, bph);
+                tc_fence_after();
+                b_lo = b_lo0 + bslot * kBTile16;
+              }
+              const uint32_t at_lo = a_lo + (s1 ? static_cast<uint32_t>(t) : static_cast<uint32_t>(p.loads[l].rowoff[t])) * kWin;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16_lean(d_tmem, at_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
+                acc = 1;
+              }
+              if (!B_RES) {
+                umma_commit_u32(b_empty0 + bslot * 8);
+                if (++bslot == B_SLOTS) { bslot = 0; bph ^= 1; }
+              }
+            }
+            umma_commit_u32(a_empty0 + aslot * 8);
+            if (++aslot == A_SLOTS) { aslot = 0; aph ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+      if (p.debug) {
+        p.debug[blockIdx.x * 8 + 2] = dbg_te;
+        p.debug[blockIdx.x * 8 + 3] = dbg_af;
+        p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_total0;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 5..8)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int r_h = row / kTW;
+    const int r_w = row - r_h * kTW;
+    const int et = threadIdx.x - 32 * kEpiWarp0;  // 0..127
+    const bool do_stats = p.stats != nullptr;
+    constexpr int OC = Cfg::kOC;
+    int it = 0;
+    long long dbg_tf = 0, dbg_e0 = clock64();
+    uint32_t sbuf = 0;  // staging buffer toggle (runs across tiles)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / n_tiles;
+      const int n0 = (tile - m_tile * n_tiles) * BN;
+      const int n_img = m_tile / tiles_per_img;
+      const int t_in = m_tile - n_img * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int h0 = th * kTH, w0 = (t_in - th * p.tiles_w) * kTW;
+      const bool valid = (h0 + r_h < p.OH) && (w0 + r_w < p.OW);
+      const int buf = it & 1;
+      const long long t0 = clock64();
+      mbar_wait(&tmem_full_bar[buf], static_cast<uint32_t>((it >> 1) & 1));
+      dbg_tf += clock64() - t0;
+      tc_fence_after();
+#pragma unroll 1
+      for (int jb = 0; jb < BN / OC; ++jb, sbuf ^= 1) {
+        // the store issued two groups ago read this staging buffer; the last reader of `red` is two barriers back
+        if (et == 0) tma_store_wait_read_1();
+        named_bar_sync(1, 128);
+        uint8_t* stg = staging + sbuf * Cfg::kStageBufBytes;
+#pragma unroll 1
+        for (int c0 = jb * OC; c0 < (jb + 1) * OC; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c0, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          // staging store, swizzled like the TMA store box (conflict-free for these writes and for the TMA read)
+          if (OC == 64) {
+            const uint32_t base = smem_u32(stg) + row * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int cj = ((c0 & 63) >> 3) + i;
+              const uint32_t addr = base + (((cj ^ (row & 7)) & 7) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                           : "memory");
+            }
+          } else {
+            const uint32_t base = smem_u32(stg) + row * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t addr = base + (((i ^ ((row >> 1) & 3)) & 3) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                           : "memory");
+            }
+          }
+          if (do_stats) {
+            // statistics of the values as stored (bf16-rounded), fp32 sums; rows outside the image contribute nothing
+            float f[32], g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = valid ? bf16_round(__uint_as_float(v[j])) : 0.f;
+              f[j] = x;
+              g[j] = x * x;
+            }
+            const float s1 = warp_colsum32(f, lane);
+            const float s2 = warp_colsum32(g, lane);
+            red[q][c0 - jb * OC + lane][0] = s1;
+            red[q][c0 - jb * OC + lane][1] = s2;
+          }
+        }
+        if (jb == BN / OC - 1) {
+          // this warp's TMEM reads of the tile are complete: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&maps.out, stg, n0 + jb * OC, w0, h0, n_img);
+          tma_store_commit();
+        }
+        if (do_stats && et < OC) {
+          // `red` is rewritten only after the next named barrier 1, which this thread reaches after these reads
+          float* dst = p.stats + (static_cast<size_t>(n_img) * tiles_per_img + t_in) * p.cout * 2;
+          const float s1 = (red[0][et][0] + red[1][et][0]) + (red[2][et][0] + red[3][et][0]);
+          const float s2 = (red[0][et][1] + red[1][et][1]) + (red[2][et][1] + red[3][et][1]);
+          reinterpret_cast<float2*>(dst)[n0 + jb * OC + et] = make_float2(s1, s2);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+    if (p.debug && et == 0) {
+      p.debug[blockIdx.x * 8 + 5] = dbg_tf;
+      p.debug[blockIdx.x * 8 + 6] = clock64() - dbg_e0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- host side
+struct TapSpec {
+  int map;       // source lattice (parity class) index 0..3
+  int dh, dw;    // shift in that lattice
+  int koff;      // K offset of the tap in the packed weights
+};
+
+struct SrcLattice {
+  const __nv_bfloat16* base;
+  int64_t pitch;
+  int N, H, W, C, hstep, wstep, hoff, woff;
+};
+
+// Group taps that share (lattice, column shift) into patch loads and build one tensor map per load.
+static int build_loads(const TapSpec* taps, int ntaps, const SrcLattice* lat, int BK, GConvParams* p, GConvMaps* maps) {
+  p->nloads = 0;
+  p->ntaps_total = ntaps;
+  bool used[9] = {false};
+  for (int i = 0; i < ntaps; ++i) {
+    if (used[i]) continue;
+    int idx[3], n = 0;
+    for (int j = i; j < ntaps && n < 3; ++j)
+      if (!used[j] && taps[j].map == taps[i].map && taps[j].dw == taps[i].dw) idx[n++] = j;
+    int dh_min = taps[idx[0]].dh, dh_max = dh_min;
+    for (int k = 1; k < n; ++k) {
+      if (taps[idx[k]].dh < dh_min) dh_min = taps[idx[k]].dh;
+      if (taps[idx[k]].dh > dh_max) dh_max = taps[idx[k]].dh;
+    }
+    if (dh_max - dh_min > 2) return set_error(kErrInvalid, "gconv: tap row span %d too large", dh_max - dh_min);
+    ALoad& L = p->loads[p->nloads];
+    L.dh = dh_min;
+    L.dw = taps[i].dw;
+    L.rows = kTH + (dh_max - dh_min);
+    L.ntaps = n;
+    for (int k = 0; k < n; ++k) {
+      used[idx[k]] = true;
+      L.rowoff[k] = taps[idx[k]].dh - dh_min;
+      L.koff[k] = taps[idx[k]].koff;
+    }
+    const SrcLattice& S = lat[taps[i].map];
+    int rc = make_act_map(&maps->src[p->nloads], S.base, S.pitch, S.N, S.H, S.W, S.C, S.hstep, S.wstep, S.hoff, S.woff,
+                          BK, kTW, L.rows);
+    if (rc) return rc;
+    ++p->nloads;
+  }
+  p->s1 = (p->nloads == 3);
+  for (int l = 0; l < p->nloads && p->s1; ++l)
+    if (p->loads[l].ntaps != 3 || p->loads[l].rowoff[0] != 0 || p->loads[l].rowoff[1] != 1 || p->loads[l].rowoff[2] != 2)
+      p->s1 = 0;
+  return 0;
+}
+
+// Developer instrumentation: B200UNET_GCONV_DEBUG=1 makes every launch synchronise and print per-role wait cycles.
+static long long* debug_buffer() {
+  static long long* buf = nullptr;
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("B200UNET_GCONV_DEBUG");
+    state = (e && e[0] == '1') ? 1 : 0;
+    if (state) cudaMalloc(&buf, 148 * 8 * sizeof(long long));
+  }
+  return state ? buf : nullptr;
+}
+
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStream_t st) {
+  GConvParams p = p_in;
+  p.debug = debug_buffer();
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
+  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * p.N * (p.cout / BN);
+  const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+  if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("gconv_kernel");
+  if (p.debug) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.debug, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long tiles = total / grid;
+    fprintf(stderr,
+            "gconv<%d,%d,%d,%d,%d> cin %d cout %d loads %d taps %d tiles/CTA %lld | per tile: producer0 wait %lld issue %lld | "
+            "mma total %lld wait_tmem_empty %lld wait_a_full %lld | epi total %lld wait_tmem_full %lld\n",
+            BK, BN, A_SLOTS, B_SLOTS, (int)B_RES, p.cin, p.cout, p.nloads, p.ntaps_total, tiles, h[0] / tiles,
+            h[1] / tiles, h[4] / tiles, h[2] / tiles, h[3] / tiles, h[6] / tiles, h[5] / tiles);
+  }
+  return 0;
+}
+
+static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, int BN, cudaStream_t st) {
+  // resident weights: one N tile and the whole (taps x chunks) slab inside the 72 KB budget
+  const int btile = ((BN * BK * 2 + 1023) / 1024) * 1024;
+  const bool res = (p.cout == BN) && (BN <= 96) &&
+                   (static_cast<long long>(p.ntaps_total) * (p.cin / BK) * btile <= 72 * 1024);
+#define GC(bk, bn, as, bs, r) \
+  if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
+  GC(64, 256, 3, 4, false)
+  GC(64, 128, 4, 4, false)
+  GC(64, 64, 6, 4, false)
+  GC(64, 64, 4, 1, true)
+  GC(64, 32, 8, 4, false)
+  GC(64, 32, 4, 1, true)
+  GC(32, 256, 4, 4, false)
+  GC(32, 128, 8, 4, false)
+  GC(32, 96, 8, 4, false)
+  GC(32, 96, 8, 1, true)
+  GC(32, 64, 8, 4, false)
+  GC(32, 64, 8, 1, true)
+  GC(32, 32, 8, 4, false)
+  GC(32, 32, 8, 1, true)
+#undef GC
+  return set_error(kErrUnsupported, "no gconv instantiation for BK=%d BN=%d", BK, BN);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200unet_conv_fprop_partials(int OH, int OW) { return ceil_div(OW, kTW) * ceil_div(OH, kTH); }
+
+extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_fprop: stride %d unsupported", a->stride);
+  const int BK = pick_bk(a->Cin), BN = pick_bn_gconv(a->Cout, BK);
+  if (!BK || !BN)
+    return set_error(kErrUnsupported, "conv_fprop: Cin=%d Cout=%d outside the tensor-core envelope (multiples of 32)",
+                     a->Cin, a->Cout);
+  B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->y_pitch % 8 == 0, "conv_fprop: pitches must be multiples of 8 elements");
+  const int s = a->stride;
+  const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  GConvParams p{};
+  GConvMaps maps;
+  p.N = a->N;
+  p.OH = OH;
+  p.OW = OW;
+  p.tiles_w = ceil_div(OW, kTW);
+  p.tiles_h = ceil_div(OH, kTH);
+  p.cin = a->Cin;
+  p.cout = a->Cout;
+  p.stats = a->stats;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a->x);
+  TapSpec taps[9];
+  SrcLattice lat[4];
+  int rc;
+  if (s == 1) {
+    lat[0] = SrcLattice{x, a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0};
+    // order: column shift outermost so that the three row taps of a patch are adjacent
+    int n = 0;
+    for (int kw = 0; kw < 3; ++kw)
+      for (int kh = 0; kh < 3; ++kh) taps[n++] = TapSpec{0, kh - 1, kw - 1, (kh * 3 + kw) * a->Cin};
+  } else {
+    B200_CHECK_ARG(a->H >= 2 && a->W >= 2, "conv_fprop: stride-2 input must be at least 2x2");
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp)
+        lat[hp * 2 + wp] = SrcLattice{x, a->x_pitch, a->N, a->H, a->W, a->Cin, 2, 2, hp, wp};
+    // input row 2*oh + kh - 1:  kh=0 -> parity 1, index oh-1;  kh=1 -> parity 0, index oh;  kh=2 -> parity 1, index oh
+    const int par[3] = {1, 0, 1}, sh[3] = {-1, 0, 0};
+    int n = 0;
+    for (int kw = 0; kw < 3; ++kw)
+      for (int kh = 0; kh < 3; ++kh)
+        taps[n++] = TapSpec{par[kh] * 2 + par[kw], sh[kh], sh[kw], (kh * 3 + kw) * a->Cin};
+  }
+  if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
+  if ((rc = make_weight_map(&maps.w, a->w, a->Cout, 9 * a->Cin, BK, BN))) return rc;
+  const int OC = (BN % 64 == 0) ? 64 : 32;
+  if ((rc = make_act_map(&maps.out, static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->N, OH, OW, a->Cout, 1, 1, 0,
+                         0, OC, kTW, kTH)))
+    return rc;
+  return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_dgrad: stride %d unsupported", a->stride);
+  // GEMM: M = input pixels, N = Cin, K = taps * Cout
+  const int BK = pick_bk(a->Cout), BN = pick_bn_gconv(a->Cin, BK);
+  if (!BK || !BN)
+    return set_error(kErrUnsupported, "conv_dgrad: Cin=%d Cout=%d outside the tensor-core envelope", a->Cin, a->Cout);
+  B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad: pitches must be multiples of 8 elements");
+  const int s = a->stride;
+  const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);
+  const __nv_bfloat16* dx = static_cast<const __nv_bfloat16*>(a->dx);
+  const int OC = (BN % 64 == 0) ? 64 : 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  GConvMaps maps;
+  if ((rc = make_weight_map(&maps.w, a->wt, a->Cin, 9 * a->Cout, BK, BN))) return rc;
+  SrcLattice lat[1] = {SrcLattice{dy, a->dy_pitch, a->N, OH, OW, a->Cout, 1, 1, 0, 0}};
+  if (s == 1) {
+    GConvParams p{};
+    p.N = a->N;
+    p.OH = a->H;
+    p.OW = a->W;
+    p.tiles_w = ceil_div(a->W, kTW);
+    p.tiles_h = ceil_div(a->H, kTH);
+    p.cin = a->Cout;
+    p.cout = a->Cin;
+    p.stats = nullptr;
+    // dx[ih,iw] += dy[ih + 1 - kh, iw + 1 - kw] * W[kh,kw]
+    TapSpec taps[9];
+    int n = 0;
+    for (int kw = 0; kw < 3; ++kw)
+      for (int kh = 2; kh >= 0; --kh) taps[n++] = TapSpec{0, 1 - kh, 1 - kw, (kh * 3 + kw) * a->Cout};  // row offsets 0,1,2
+    if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
+    if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, kTW, kTH))) return rc;
+    return dispatch_gconv(maps, p, BK, BN, st);
+  }
+  // stride 2: one launch per parity class (ph,pw) of the input pixel; ih = 2a + ph receives
+  //   ph = 0: kh = 1 from oh = a;      ph = 1: kh = 0 from oh = a + 1 and kh = 2 from oh = a   (same along w)
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int Hs = (a->H - ph + 1) / 2, Ws = (a->W - pw + 1) / 2;
+      if (Hs <= 0 || Ws <= 0) continue;
+      GConvParams p{};
+      p.N = a->N;
+      p.OH = Hs;
+      p.OW = Ws;
+      p.tiles_w = ceil_div(Ws, kTW);
+      p.tiles_h = ceil_div(Hs, kTH);
+      p.cin = a->Cout;
+      p.cout = a->Cin;
+      p.stats = nullptr;
+      int khs[2], dhs[2], nkh, kws[2], dws[2], nkw;
+      if (ph == 0) { nkh = 1; khs[0] = 1; dhs[0] = 0; } else { nkh = 2; khs[0] = 0; dhs[0] = 1; khs[1] = 2; dhs[1] = 0; }
+      if (pw == 0) { nkw = 1; kws[0] = 1; dws[0] = 0; } else { nkw = 2; kws[0] = 0; dws[0] = 1; kws[1] = 2; dws[1] = 0; }
+      TapSpec taps[4];
+      int n = 0;
+      for (int j = 0; j < nkw; ++j)
+        for (int i = 0; i < nkh; ++i) taps[n++] = TapSpec{0, dhs[i], dws[j], (khs[i] * 3 + kws[j]) * a->Cout};
+      if ((rc = build_loads(taps, n, lat, BK, &p, &maps))) return rc;
+      if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, OC, kTW, kTH)))
+        return rc;
+      if ((rc = dispatch_gconv(maps, p, BK, BN, st))) return rc;
+    }
+  return 0;
+}

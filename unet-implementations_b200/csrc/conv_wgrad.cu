@@ -1,0 +1,341 @@
+// Weight gradient of the 3x3 convolutions on tcgen05 / TMEM for the general case (any stride, Cout a multiple of 32):
+//   D[128 = (tap, ci) rows, BN = co] += X_tap^T[rows, 64 pixels] . dY[64 pixels, BN]
+// both operands MN-major (channels contiguous in NHWC), K = pixels, split over CTAs, fp32 partials reduced
+// deterministically by wgrad_finalize_kernel into the OIHW gradient.  Stride-1 layers with Cout in {32, 64} take the
+// narrow-output kernel (conv_wgrad_narrow.cu).  Replaces the weight-gradient half of aten::convolution_backward for
+// nn.Conv2d (Our_UNet/models/unet.py:106-115).
+// Warp roles (288 threads): warps 0..3 = TMA producers, warp 4 = TMEM allocator + MMA issuer, warps 5..8 = epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "conv_common.cuh"
+
+namespace b200 {
+
+struct WTap {
+  int map, dh, dw;
+};
+
+struct WgradParams {
+  int N, OH, OW, blocks_w, blocks_h, TWk, THk;
+  int total_kb, kb_per_split;
+  WTap taps[9];
+  int cin, cout;
+  int units_per_tap, total_units;
+  int G;  // M-groups (of 128 rows) per CTA
+  float* partial;  // [S][9][cin][cout]
+};
+
+struct WgradMaps {
+  CUtensorMap src[4];
+  CUtensorMap dy;
+};
+
+constexpr int kWgStages = 3;
+
+// U  = channels per unit on the M side (64 -> 128B-swizzled blocks, 32 -> 64B-swizzled blocks)
+// BN = output-channel tile (N side); 32 uses one 64B-swizzled block, otherwise BN/64 128B-swizzled blocks
+template <int U, int BN>
+__global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_constant__ WgradMaps maps,
+                                                                 const __grid_constant__ WgradParams p) {
+  constexpr int UPG = 128 / U;                      // units per M-group
+  constexpr int kUnitBytes = 64 * U * 2;            // 64 pixels x U channels
+  constexpr int kGroupBytes = UPG * kUnitBytes;     // 16 KB
+  constexpr int kDyBlockCh = BN >= 64 ? 64 : BN;    // channels per dY block
+  constexpr int kDyBlocks = BN / kDyBlockCh;
+  constexpr int kDyBlockBytes = 64 * kDyBlockCh * 2;
+  constexpr int kDyBytes = kDyBlocks * kDyBlockBytes;
+  constexpr uint32_t kSwzA = (U == 64) ? kSwz128 : kSwz64;
+  constexpr uint32_t kSwzB = (kDyBlockCh == 64) ? kSwz128 : kSwz64;
+  constexpr uint32_t kRowA = U * 2, kRowB = kDyBlockCh * 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWgStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int G = p.G;
+  const int stage_bytes = kDyBytes + G * kGroupBytes;
+  const int split = blockIdx.x;
+  const int group0 = blockIdx.y * G;
+  const int n0 = blockIdx.z * BN;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  const int num_kb = kb_end - kb_begin;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(G * BN)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full_bar[s], kProducerWarps);  // every producer arrives with the bytes of the loads it issues
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&tmem_base_holder, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  // units of this CTA that exist (the last group of a layer may be partially filled)
+  int valid_units = p.total_units - group0 * UPG;
+  if (valid_units > G * UPG) valid_units = G * UPG;
+  if (valid_units < 0) valid_units = 0;
+
+  if (warp < kProducerWarps) {
+    if (elect_one()) {
+      // every producer walks all K-blocks and issues loads j = warp, warp+4, ... of each (dY blocks first, then units)
+      const int blocks_per_img = p.blocks_w * p.blocks_h;
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb_begin + i;
+        const int n_img = kb / blocks_per_img;
+        const int b_in = kb - n_img * blocks_per_img;
+        const int bh = b_in / p.blocks_w;
+        const int bw = b_in - bh * p.blocks_w;
+        const int h0 = bh * p.THk, w0 = bw * p.TWk;
+        const int s = i % kWgStages;
+        const uint32_t ph = (i / kWgStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint32_t my_bytes = 0;
+        for (int j = warp; j < kDyBlocks + valid_units; j += kProducerWarps)
+          my_bytes += (j < kDyBlocks) ? kDyBlockBytes : kUnitBytes;
+        mbar_expect_tx(&full_bar[s], my_bytes);
+        uint8_t* sb = smem + s * stage_bytes;
+        for (int j = warp; j < kDyBlocks + valid_units; j += kProducerWarps) {
+          if (j < kDyBlocks) {
+            tma_load_4d(sb + j * kDyBlockBytes, &maps.dy, &full_bar[s], n0 + j * kDyBlockCh, w0, h0, n_img);
+          } else {
+            const int u = j - kDyBlocks;
+            const int unit = group0 * UPG + u;
+            const int tap = unit / p.units_per_tap;
+            const int c0 = (unit - tap * p.units_per_tap) * U;
+            const WTap t = p.taps[tap];
+            tma_load_4d(sb + kDyBytes + u * kUnitBytes, &maps.src[t.map], &full_bar[s], c0, w0 + t.dw, h0 + t.dh,
+                        n_img);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      const int groups = (valid_units + UPG - 1) / UPG;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kWgStages;
+        const uint32_t ph = (i / kWgStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + s * stage_bytes);
+        for (int g = 0; g < groups; ++g) {
+          const uint32_t sa = sb + kDyBytes + g * kGroupBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // MN-major canonical layout: LBO = byte stride between channel blocks, SBO = 8 pixel rows
+            const uint64_t adesc = umma_smem_desc(sa + k * 16 * kRowA, kUnitBytes, 8 * kRowA, kSwzA);
+            const uint64_t bdesc = umma_smem_desc(sb + k * 16 * kRowB, kDyBlockBytes, 8 * kRowB, kSwzB);
+            umma_bf16(tmem_base + g * BN, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const int groups = (valid_units + UPG - 1) / UPG;
+    for (int g = 0; g < groups; ++g) {
+      const int u = g * UPG + row / U;
+      const int unit = group0 * UPG + u;
+      const bool uvalid = u < valid_units;
+      int tap = 0, ci = 0;
+      if (uvalid) {
+        tap = unit / p.units_per_tap;
+        ci = (unit - tap * p.units_per_tap) * U + (row % U);
+      }
+      float* dst = p.partial + ((static_cast<size_t>(split) * 9 + tap) * p.cin + ci) * p.cout + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        if (num_kb > 0) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        }
+        if (uvalid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dw[co][ci][tap] = sum_s partial[s][tap][ci][co]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int cin,
+                                      int cout) {
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % cout);
+  const int64_t r = i / cout;
+  const int ci = static_cast<int>(r % cin);
+  const int tap = static_cast<int>(r / cin);
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += partial[static_cast<int64_t>(s) * total + i];
+  dw[(static_cast<int64_t>(co) * cin + ci) * 9 + tap] = acc;
+}
+
+int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+  wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, dw, S, cin, cout);
+  B200_LAUNCH_CHECK("wgrad_finalize_kernel");
+  return 0;
+}
+
+struct WgradPlan {
+  int U, BN, G, S, gy, gz, total_kb, kb_per_split, TWk, THk, blocks_w, blocks_h, OH, OW;
+  int64_t smem_bytes, partial_floats;
+};
+
+static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int stride, WgradPlan* pl) {
+  pl->U = pick_bk(Cin);
+  pl->BN = pick_bn(Cout);
+  if (!pl->U || !pl->BN) return set_error(kErrUnsupported, "conv_wgrad: Cin=%d Cout=%d outside the envelope", Cin, Cout);
+  pl->OH = (H - 1) / stride + 1;
+  pl->OW = (W - 1) / stride + 1;
+  pl->TWk = 16;
+  pl->THk = 4;
+  pl->blocks_w = ceil_div(pl->OW, pl->TWk);
+  pl->blocks_h = ceil_div(pl->OH, pl->THk);
+  pl->total_kb = N * pl->blocks_w * pl->blocks_h;
+  const int upg = 128 / pl->U;
+  const int total_units = 9 * (Cin / pl->U);
+  const int groups_total = ceil_div(total_units, upg);
+  int G = 512 / pl->BN;
+  const int dy_bytes = 64 * pl->BN * 2;
+  const int gsm = (70 * 1024 - dy_bytes) / 16384;  // keep a stage under ~70 KB so three stages fit
+  if (G > gsm) G = gsm;
+  if (G > groups_total) G = groups_total;
+  if (G < 1) G = 1;
+  pl->G = G;
+  pl->gy = ceil_div(groups_total, G);
+  pl->gz = Cout / pl->BN;
+  const int base_ctas = pl->gy * pl->gz;
+  int S = ceil_div(num_sms(), base_ctas);
+  if (S > pl->total_kb) S = pl->total_kb;
+  if (S < 1) S = 1;
+  pl->kb_per_split = ceil_div(pl->total_kb, S);
+  pl->S = ceil_div(pl->total_kb, pl->kb_per_split);
+  pl->smem_bytes = static_cast<int64_t>(kWgStages) * (dy_bytes + G * 16384) + 1024;
+  pl->partial_floats = static_cast<int64_t>(pl->S) * 9 * Cin * Cout;
+  return 0;
+}
+
+template <int U, int BN>
+static int launch_wgrad(const WgradMaps& maps, const WgradParams& p, const WgradPlan& pl, cudaStream_t st) {
+  auto kern = wgrad_kernel<U, BN>;
+  static int attr_bytes = 0;
+  if (attr_bytes < pl.smem_bytes) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    attr_bytes = (int)pl.smem_bytes;
+  }
+  dim3 grid(pl.S, pl.gy, pl.gz);
+  kern<<<grid, kConvThreads, pl.smem_bytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("wgrad_kernel");
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200unet_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int stride) {
+  if (wgradn_supported(Cin, Cout, stride)) return wgradn_workspace_bytes(N, H, W, Cin, Cout);
+  WgradPlan pl;
+  if (plan_wgrad(N, H, W, Cin, Cout, stride, &pl)) return -1;
+  return pl.partial_floats * 4;
+}
+
+extern "C" int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->x && a->dy && a->dw && a->workspace, "conv_wgrad: null pointer");
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_wgrad: stride %d unsupported", a->stride);
+  B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_wgrad: pitches must be multiples of 8 elements");
+  if (wgradn_supported(a->Cin, a->Cout, a->stride)) return wgradn_launch(a, static_cast<cudaStream_t>(stream));
+  WgradPlan pl;
+  int rc;
+  if ((rc = plan_wgrad(a->N, a->H, a->W, a->Cin, a->Cout, a->stride, &pl))) return rc;
+  B200_CHECK_ARG(a->workspace_bytes >= pl.partial_floats * 4, "conv_wgrad: workspace too small (%lld < %lld)",
+                 (long long)a->workspace_bytes, (long long)(pl.partial_floats * 4));
+  WgradParams p{};
+  WgradMaps maps;
+  p.N = a->N;
+  p.OH = pl.OH;
+  p.OW = pl.OW;
+  p.blocks_w = pl.blocks_w;
+  p.blocks_h = pl.blocks_h;
+  p.TWk = pl.TWk;
+  p.THk = pl.THk;
+  p.total_kb = pl.total_kb;
+  p.kb_per_split = pl.kb_per_split;
+  p.cin = a->Cin;
+  p.cout = a->Cout;
+  p.units_per_tap = a->Cin / pl.U;
+  p.total_units = 9 * p.units_per_tap;
+  p.G = pl.G;
+  p.partial = a->workspace;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(a->x);
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);
+  if (a->stride == 1) {
+    if ((rc = make_act_map(&maps.src[0], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, pl.U, pl.TWk, pl.THk)))
+      return rc;
+    maps.src[1] = maps.src[2] = maps.src[3] = maps.src[0];
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = WTap{0, kh - 1, kw - 1};
+  } else {
+    B200_CHECK_ARG(a->H >= 2 && a->W >= 2, "conv_wgrad: stride-2 input must be at least 2x2");
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp)
+        if ((rc = make_act_map(&maps.src[hp * 2 + wp], x, a->x_pitch, a->N, a->H, a->W, a->Cin, 2, 2, hp, wp, pl.U,
+                               pl.TWk, pl.THk)))
+          return rc;
+    const int par[3] = {1, 0, 1}, sh[3] = {-1, 0, 0};
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.taps[kh * 3 + kw] = WTap{par[kh] * 2 + par[kw], sh[kh], sh[kw]};
+  }
+  const int dyc = pl.BN >= 64 ? 64 : pl.BN;
+  if ((rc = make_act_map(&maps.dy, dy, a->dy_pitch, a->N, pl.OH, pl.OW, a->Cout, 1, 1, 0, 0, dyc, pl.TWk, pl.THk)))
+    return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define WG(u, bn) \
+  if (pl.U == u && pl.BN == bn) rc = launch_wgrad<u, bn>(maps, p, pl, st); else
+  WG(64, 256) WG(64, 128) WG(64, 64) WG(64, 32) WG(32, 256) WG(32, 128) WG(32, 64) WG(32, 32)
+  rc = set_error(kErrUnsupported, "no wgrad instantiation for U=%d BN=%d", pl.U, pl.BN);
+#undef WG
+  if (rc) return rc;
+  return launch_wgrad_finalize(a->workspace, a->dw, pl.S, a->Cin, a->Cout, st);
+}

@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], kProducerWarps);  // every producer arrives with the bytes of the loads it issues
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&tmem_base_holder, tmem_cols);
     tmem_relinquish();
   }
@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < kProducerWarps) {
+    if (elect_one()) {
+      // every producer walks all pixel blocks and issues loads j = warp, warp+4, ... of each (3 dY tiles, CPB X patches)
       tma_prefetch_desc(&maps.x);
       tma_prefetch_desc(&maps.dy);
       const int blocks_per_img = p.blocks_w * p.blocks_h;
@@ -107,20 +108,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], stage_bytes);
+        uint32_t my_bytes = 0;
+        for (int j = warp; j < 3 + CPB; j += kProducerWarps) my_bytes += (j < 3) ? Cfg::kDyBytes : Cfg::kXBytes;
+        mbar_expect_tx(&full_bar[s], my_bytes);
         uint8_t* sb = smem + s * stage_bytes;
-        // B: dY shifted by kw - 1 pixels: B_kw[oh, w'] = dY[oh, w' - kw + 1]
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          tma_load_4d(sb + kw * Cfg::kDyBytes, &maps.dy, &full_bar[s], 0, w0 + 1 - kw, h0, n_img);
-        // A: X patch rows [h0 - 1, h0 + R + 2) of each channel chunk
-        for (int j = 0; j < CPB; ++j)
-          tma_load_4d(sb + 3 * Cfg::kDyBytes + j * Cfg::kXBytes, &maps.x, &full_bar[s], (chunk0 + j) * CH, w0, h0 - 1,
-                      n_img);
+        for (int j = warp; j < 3 + CPB; j += kProducerWarps) {
+          if (j < 3) {
+            // B: dY shifted by kw - 1 pixels: B_kw[oh, w'] = dY[oh, w' - kw + 1]   (kw = j)
+            tma_load_4d(sb + j * Cfg::kDyBytes, &maps.dy, &full_bar[s], 0, w0 + 1 - j, h0, n_img);
+          } else {
+            // A: X patch rows [h0 - 1, h0 + R + 2) of channel chunk j - 3
+            tma_load_4d(sb + 3 * Cfg::kDyBytes + (j - 3) * Cfg::kXBytes, &maps.x, &full_bar[s],
+                        (chunk0 + j - 3) * CH, w0, h0 - 1, n_img);
+          }
+        }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kNcols, 1, 1);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
