@@ -47,11 +47,12 @@ typedef struct {
   const void* w;      /* bf16 packed weights [Cout][3][3][Cin] (b200unet_pack_conv_weights) */
   void* y;            /* bf16 NHWC raw conv output [N,OH,OW,Cout], pitch y_pitch */
   int64_t y_pitch;
-  float* stats;       /* fp32 [N][P][Cout][2] partial sums of y and y*y over valid pixels, or NULL */
+  float* stats;       /* fp32 [N][P][Cout][2] partial sums of y and y*y over valid pixels (P from
+                         b200unet_conv_fprop_partials; zero-filled by the call), or NULL */
   int N, H, W, Cin, Cout, stride;
 } b200unet_conv_fprop_args;
-/* Number of stat partials per image (P) the fprop kernel writes for an output of OH x OW. */
-int b200unet_conv_fprop_partials(int OH, int OW);
+/* Number of stat partial slots per image (P) of the fprop kernel for N images of OH x OW x Cout outputs. */
+int b200unet_conv_fprop_partials(int N, int OH, int OW, int Cout);
 int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream);
 
 typedef struct {
@@ -79,6 +80,7 @@ int b200unet_conv_wgrad(const b200unet_conv_wgrad_args* a, void* stream);
 
 /* CUDA-core direct convolutions with the same argument structs: the slow, obviously-correct path used by the
  * tests to cross-check the tensor-core kernels on the device and for shapes outside their envelope. */
+int b200unet_conv_fprop_simt_partials(int OH, int OW); /* P of the stats buffer for the _simt fprop */
 int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream);
 int b200unet_conv_dgrad_simt(const b200unet_conv_dgrad_args* a, void* stream);
 int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void* stream);

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_sizing_calls_need_no_gpu():
     from unet_implementations_b200 import _lib
     assert _lib.call("b200unet_version") == 100
-    assert _lib.call("b200unet_conv_fprop_partials", 512, 512) == (512 // 16) * (512 // 8)
+    assert _lib.call("b200unet_conv_fprop_partials", 32, 512, 512, 32) >= 4
     assert _lib.call("b200unet_loss_workspace", 4, 512 * 512) > 0
 
 

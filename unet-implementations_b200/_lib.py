@@ -55,11 +55,12 @@ SIGNATURES = {
     "b200unet_last_error": (c_char_p, []),
     "b200unet_device_ok": (c_int, []),
     "b200unet_launch_count": (c_int64, []),
-    "b200unet_conv_fprop_partials": (c_int, [_I, _I]),
+    "b200unet_conv_fprop_partials": (c_int, [_I, _I, _I, _I]),
     "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
     "b200unet_conv_dgrad": (c_int, [POINTER(ConvDgradArgs), _P]),
     "b200unet_conv_wgrad_workspace": (c_int64, [_I, _I, _I, _I, _I, _I]),
     "b200unet_conv_wgrad": (c_int, [POINTER(ConvWgradArgs), _P]),
+    "b200unet_conv_fprop_simt_partials": (c_int, [_I, _I]),
     "b200unet_conv_fprop_simt": (c_int, [POINTER(ConvFpropArgs), _P]),
     "b200unet_conv_dgrad_simt": (c_int, [POINTER(ConvDgradArgs), _P]),
     "b200unet_conv_wgrad_simt": (c_int, [POINTER(ConvWgradArgs), _P]),
@@ -87,6 +88,7 @@ SIGNATURES = {
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
+    "b200unet_conv_fprop_simt_partials",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
     "b200unet_in_backward_workspace", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
 }

@@ -50,6 +50,8 @@ struct GConvParams {
   ALoad loads[kMaxLoads];
   int cin;   // channels per tap on the K side (multiple of BK)
   int cout;  // total N of the GEMM
+  int tiles_per_cta;
+  int stat_slots;  // P: partial-sum slots per image in `stats` ([N][P][cout][2])
   float* stats;
   long long* debug;  // optional [gridDim.x][8] cycle counters (developer instrumentation; NULL in production)
 };
@@ -92,7 +94,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
   __shared__ __align__(8) uint64_t b_full[kBBar], b_empty[kBBar];
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_holder;
-  __shared__ float red[4][(BN % 64 == 0) ? 64 : 32][2];  // per staging chunk
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,6 +107,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
   const int chunks = p.cin / BK;
   const int loads_per_tile = chunks * p.nloads;
   const int btiles_per_tile = chunks * p.ntaps_total;
+  // contiguous tile range of this CTA (tile = m_tile * n_tiles + n_tile): consecutive patches of one image, which
+  // keeps the halo rows in L2 and lets the epilogue accumulate the InstanceNorm partial sums across tiles
+  const int tile_lo = min(static_cast<int>(blockIdx.x) * p.tiles_per_cta, total_tiles);
+  const int tile_hi = min(tile_lo + p.tiles_per_cta, total_tiles);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_SLOTS; ++s) {
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         tma_prefetch_desc(&maps.src[0]);
         long long dbg_wait = 0, dbg_issue = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
           const int m_tile = tile / n_tiles;
           const int n_img = m_tile / tiles_per_img;
           const int t_in = m_tile - n_img * tiles_per_img;
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         const int me = warp - (kProducerWarps - Cfg::NB);
         tma_prefetch_desc(&maps.w);
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
           const int m_tile = tile / n_tiles;
           const int n0 = (tile - m_tile * n_tiles) * BN;
           const long long g0 = static_cast<long long>(it) * btiles_per_tile;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       uint32_t aslot = 0, aph = 0, bslot = 0, bph = 0;  // ring positions and phase parities (run across tiles)
       long long dbg_te = 0, dbg_af = 0, dbg_total0 = clock64();
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int buf = it & 1;
         const long long t0 = p.debug ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // epilogue drained this buffer
@@ -281,30 +286,68 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     // ------------------------------------------------------------------ epilogue (warps 5..8)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int r_h = row / kTW;
-    const int r_w = row - r_h * kTW;
     const int et = threadIdx.x - 32 * kEpiWarp0;  // 0..127
     const bool do_stats = p.stats != nullptr;
     constexpr int OC = Cfg::kOC;
+    // InstanceNorm partial sums: after a staging chunk is complete, warp q re-reads rows [32q, 32q+32) of it from
+    // shared memory with lane = channel pair (OC = 64) or (row parity, channel pair) (OC = 32) -- one conflict-free
+    // row per step, no shuffles -- and accumulates sum / sum of squares of the STORED bf16 values in registers across
+    // all tiles of the same image; the sums are flushed (one partial slot per (image, CTA, q)) when the image changes.
+    constexpr int kAccChunks = (OC == 64) ? 8 : 4;  // cout <= 512 (OC = 64) / cout <= 96 (OC = 32: BN in {32, 96})
+    float acc[kAccChunks][4];             // [chunk of the layer's channels][s1 c0, s2 c0, s1 c1, s2 c1]
+#pragma unroll
+    for (int i = 0; i < kAccChunks; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const int cout_chunks = p.cout / OC;
+    int acc_img = -1;
+    auto flush = [&](int img) {
+      // slot of this (CTA, q) among the CTAs that cover image `img`
+      const int first_tile = img * tiles_per_img * n_tiles;
+      const int b0 = first_tile / p.tiles_per_cta;
+      const int slot = (static_cast<int>(blockIdx.x) - b0) * 4 + q;
+      float* dst = p.stats + (static_cast<size_t>(img) * p.stat_slots + slot) * p.cout * 2;
+#pragma unroll
+      for (int i = 0; i < kAccChunks; ++i) {
+        if (i < cout_chunks) {
+          if (OC == 64) {
+            // lane = channel pair: channels 2*lane, 2*lane+1 of chunk i
+            *reinterpret_cast<float4*>(dst + (i * 64 + 2 * lane) * 2) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          } else {
+            // lanes l and l+16 hold the even / odd rows of the same channel pair: combine, lane < 16 writes
+            const float a0 = acc[i][0] + __shfl_down_sync(0xffffffffu, acc[i][0], 16);
+            const float a1 = acc[i][1] + __shfl_down_sync(0xffffffffu, acc[i][1], 16);
+            const float a2 = acc[i][2] + __shfl_down_sync(0xffffffffu, acc[i][2], 16);
+            const float a3 = acc[i][3] + __shfl_down_sync(0xffffffffu, acc[i][3], 16);
+            if (lane < 16) *reinterpret_cast<float4*>(dst + (i * 32 + 2 * lane) * 2) = make_float4(a0, a1, a2, a3);
+          }
+        }
+        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      }
+    };
     int it = 0;
     long long dbg_tf = 0, dbg_e0 = clock64();
     uint32_t sbuf = 0;  // staging buffer toggle (runs across tiles)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
       const int m_tile = tile / n_tiles;
-      const int n0 = (tile - m_tile * n_tiles) * BN;
+      const int nt_idx = tile - m_tile * n_tiles;
+      const int n0 = nt_idx * BN;
       const int n_img = m_tile / tiles_per_img;
       const int t_in = m_tile - n_img * tiles_per_img;
       const int th = t_in / p.tiles_w;
       const int h0 = th * kTH, w0 = (t_in - th * p.tiles_w) * kTW;
-      const bool valid = (h0 + r_h < p.OH) && (w0 + r_w < p.OW);
+      if (do_stats && n_img != acc_img) {
+        if (acc_img >= 0) flush(acc_img);
+        acc_img = n_img;
+      }
+      // rows of this warp's quarter that lie inside the image (rows below / right of it hold TMA zero-fill garbage
+      // of the accumulator and must not enter the statistics)
       const int buf = it & 1;
-      const long long t0 = clock64();
+      const long long t0 = p.debug ? clock64() : 0;
       mbar_wait(&tmem_full_bar[buf], static_cast<uint32_t>((it >> 1) & 1));
-      dbg_tf += clock64() - t0;
+      if (p.debug) dbg_tf += clock64() - t0;
       tc_fence_after();
 #pragma unroll 1
       for (int jb = 0; jb < BN / OC; ++jb, sbuf ^= 1) {
-        // the store issued two groups ago read this staging buffer; the last reader of `red` is two barriers back
+        // the store issued two groups ago read this staging buffer
         if (et == 0) tma_store_wait_read_1();
         named_bar_sync(1, 128);
         uint8_t* stg = staging + sbuf * Cfg::kStageBufBytes;
@@ -337,20 +380,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
                            : "memory");
             }
           }
-          if (do_stats) {
-            // statistics of the values as stored (bf16-rounded), fp32 sums; rows outside the image contribute nothing
-            float f[32], g[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = valid ? bf16_round(__uint_as_float(v[j])) : 0.f;
-              f[j] = x;
-              g[j] = x * x;
-            }
-            const float s1 = warp_colsum32(f, lane);
-            const float s2 = warp_colsum32(g, lane);
-            red[q][c0 - jb * OC + lane][0] = s1;
-            red[q][c0 - jb * OC + lane][1] = s2;
-          }
         }
         if (jb == BN / OC - 1) {
           // this warp's TMEM reads of the tile are complete: hand the accumulator buffer back to the MMA warp
@@ -364,15 +393,54 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
           tma_store_4d(&maps.out, stg, n0 + jb * OC, w0, h0, n_img);
           tma_store_commit();
         }
-        if (do_stats && et < OC) {
-          // `red` is rewritten only after the next named barrier 1, which this thread reaches after these reads
-          float* dst = p.stats + (static_cast<size_t>(n_img) * tiles_per_img + t_in) * p.cout * 2;
-          const float s1 = (red[0][et][0] + red[1][et][0]) + (red[2][et][0] + red[3][et][0]);
-          const float s2 = (red[0][et][1] + red[1][et][1]) + (red[2][et][1] + red[3][et][1]);
-          reinterpret_cast<float2*>(dst)[n0 + jb * OC + et] = make_float2(s1, s2);
+        if (do_stats) {
+          // rows of this warp's quarter: 32 (OC = 64: one per step) or 2 x 16 (OC = 32: lanes >= 16 take odd rows)
+          constexpr int kSteps = (OC == 64) ? 32 : 16;
+          const uint32_t cp = (OC == 64) ? static_cast<uint32_t>(lane) : (static_cast<uint32_t>(lane) & 15);
+          const uint32_t par = (OC == 64) ? 0u : (static_cast<uint32_t>(lane) >> 4);
+          const uint32_t cw = cp >> 2, wi = (cp & 3) << 2;
+          const uint8_t* sbase = stg;
+          const bool full = (h0 + kTH <= p.OH) && (w0 + kTW <= p.OW);
+          float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f, t1a = 0.f, t2a = 0.f, t1b = 0.f, t2b = 0.f;
+#pragma unroll
+          for (int i0 = 0; i0 < kSteps; i0 += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // issue the loads of 8 rows first, then consume
+              const int r = q * 32 + ((OC == 64) ? (i0 + i) : (2 * (i0 + i) + static_cast<int>(par)));
+              const uint32_t off = (OC == 64) ? (r * 128 + (((cw ^ (r & 7)) & 7) << 4) + wi)
+                                              : (r * 64 + (((cw ^ ((r >> 1) & 3)) & 3) << 4) + wi);
+              w[i] = *reinterpret_cast<const uint32_t*>(sbase + off);
+              if (!full && !((h0 + (r >> 4) < p.OH) && (w0 + (r & 15) < p.OW))) w[i] = 0;  // outside the image
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
+              const float y0 = __uint_as_float(w[i + 1] << 16), y1 = __uint_as_float(w[i + 1] & 0xffff0000u);
+              s1a += x0;
+              s2a = fmaf(x0, x0, s2a);
+              s1b += x1;
+              s2b = fmaf(x1, x1, s2b);
+              t1a += y0;
+              t2a = fmaf(y0, y0, t2a);
+              t1b += y1;
+              t2b = fmaf(y1, y1, t2b);
+            }
+          }
+          // static indexing of the accumulator array (a dynamic index would push it to local memory)
+          const int ci = nt_idx * (BN / OC) + jb;
+#pragma unroll
+          for (int i = 0; i < kAccChunks; ++i)
+            if (i == ci) {
+              acc[i][0] += s1a + t1a;
+              acc[i][1] += s2a + t2a;
+              acc[i][2] += s1b + t1b;
+              acc[i][3] += s2b + t2b;
+            }
         }
       }
     }
+    if (do_stats && acc_img >= 0) flush(acc_img);
     if (et == 0) tma_store_wait_all();
     if (p.debug && et == 0) {
       p.debug[blockIdx.x * 8 + 5] = dbg_tf;
@@ -440,6 +508,23 @@ static int build_loads(const TapSpec* taps, int ntaps, const SrcLattice* lat, in
   return 0;
 }
 
+struct GConvGrid {
+  int grid, tiles_per_cta, stat_slots;
+};
+// Persistent grid: contiguous tile ranges of equal length; P = partial-sum slots per image = 4 (lane quarters) x the
+// largest number of CTAs whose range can intersect one image.
+static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN) {
+  GConvGrid g;
+  const long long per_img = static_cast<long long>(ceil_div(OW, kTW)) * ceil_div(OH, kTH) * (cout / BN);
+  const long long total = per_img * N;
+  const int sms = num_sms();
+  g.tiles_per_cta = static_cast<int>(ceil_div64(total, sms));
+  if (g.tiles_per_cta < 1) g.tiles_per_cta = 1;
+  g.grid = static_cast<int>(ceil_div64(total, g.tiles_per_cta));
+  g.stat_slots = 4 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);
+  return g;
+}
+
 // Developer instrumentation: B200UNET_GCONV_DEBUG=1 makes every launch synchronise and print per-role wait cycles.
 static long long* debug_buffer() {
   static long long* buf = nullptr;
@@ -464,7 +549,11 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
     attr_set = true;
   }
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * p.N * (p.cout / BN);
-  const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+  GConvGrid gg = gconv_grid(p.N, p.OH, p.OW, p.cout, BN);
+  const int grid = gg.grid;
+  p.tiles_per_cta = gg.tiles_per_cta;
+  p.stat_slots = gg.stat_slots;
+  if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * gg.stat_slots * p.cout * 2 * sizeof(float), st));
   if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("gconv_kernel");
@@ -511,7 +600,11 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
 
 using namespace b200;
 
-extern "C" int b200unet_conv_fprop_partials(int OH, int OW) { return ceil_div(OW, kTW) * ceil_div(OH, kTH); }
+extern "C" int b200unet_conv_fprop_partials(int N, int OH, int OW, int Cout) {
+  const int BN = pick_bn_gconv(Cout, 64);
+  if (!BN) return -1;
+  return gconv_grid(N, OH, OW, Cout, BN).stat_slots;
+}
 
 extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream) {
   B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop: null pointer");

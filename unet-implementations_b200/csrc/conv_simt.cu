@@ -287,6 +287,11 @@ extern "C" int b200unet_pack_conv_weights(const float* w_oihw, void* w_fprop, vo
   return 0;
 }
 
+extern "C" int b200unet_conv_fprop_simt_partials(int OH, int OW) {
+  int64_t p = (static_cast<int64_t>(OH) * OW) / 1024;
+  return static_cast<int>(p < 1 ? 1 : (p > 64 ? 64 : p));
+}
+
 extern "C" int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream) {
   B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop_simt: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_fprop_simt: stride %d unsupported", a->stride);
@@ -298,7 +303,7 @@ extern "C" int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void*
       static_cast<__nv_bfloat16*>(a->y), a->y_pitch, a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
   B200_LAUNCH_CHECK("conv_fprop_simt_kernel");
   if (a->stats) {
-    const int P = b200unet_conv_fprop_partials(OH, OW);
+    const int P = b200unet_conv_fprop_simt_partials(OH, OW);
     const int64_t HW = static_cast<int64_t>(OH) * OW;
     stats_partial_kernel<<<dim3(P, a->N), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->stats, P,
                                                         HW, a->Cout, ceil_div64(HW, P));

@@ -76,7 +76,12 @@ def conv_fprop(x, w_fprop, stride=1, out=None, want_stats=True, simt=False):
     assert tuple(y.shape) == (n, oh, ow, cout)
     stats = None
     if want_stats:
-        parts = _lib.call("b200unet_conv_fprop_partials", oh, ow)
+        if simt:
+            parts = _lib.call("b200unet_conv_fprop_simt_partials", oh, ow)
+        else:
+            parts = _lib.call("b200unet_conv_fprop_partials", n, oh, ow, cout)
+            if parts < 0:
+                raise RuntimeError(f"conv_fprop: Cout={cout} outside the tensor-core envelope")
         stats = torch.empty((n, parts, cout, 2), dtype=torch.float32, device=x.device)
     a = ConvFpropArgs(_p(x), pitch_of(x), _p(w_fprop), _p(y), pitch_of(y), _p(stats), n, h, w, cin, cout, stride)
     _lib.call("b200unet_conv_fprop_simt" if simt else "b200unet_conv_fprop", ctypes.byref(a), _stream())
