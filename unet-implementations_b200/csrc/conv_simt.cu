@@ -135,8 +135,12 @@ __global__ void conv_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, int6
 }
 
 // ------------------------------------------------------------------------------------------ stem (Cin=3 -> 32)
+// K = 27 is too small for a UMMA tile and the fp32 NCHW image would need a layout pass first, so the stem runs on the
+// CUDA cores -- with the packed FFMA2 (two fp32 FMAs per instruction, sm_100) and two pixels per thread so that every
+// shared-memory weight fetch feeds four FMAs.  HBM: reads the image once, writes 64 B per pixel.
 constexpr int kStemCo = 32;
-constexpr int kStemThreads = 256;
+constexpr int kStemThreads = 128;
+constexpr int kStemPx = 2;  // adjacent pixels (along w) per thread
 
 __global__ void __launch_bounds__(kStemThreads) stem_fprop_kernel(const float* __restrict__ img,
                                                                    const float* __restrict__ w_oihw,
@@ -144,56 +148,81 @@ __global__ void __launch_bounds__(kStemThreads) stem_fprop_kernel(const float* _
                                                                    float* __restrict__ stats, int P, int H, int W) {
   __shared__ __align__(16) float wsm[27][kStemCo];  // [ci*9 + kh*3 + kw][co]
   __shared__ float red[kStemThreads / 32][kStemCo][2];
-  const int n = blockIdx.y;
+  const int n = blockIdx.z;
+  const int h = blockIdx.y;
   const int64_t HW = static_cast<int64_t>(H) * W;
   for (int i = threadIdx.x; i < 27 * kStemCo; i += kStemThreads) {
     const int co = i % kStemCo, k = i / kStemCo;
     wsm[k][co] = w_oihw[co * 27 + k];
   }
   __syncthreads();
-  const int64_t px = static_cast<int64_t>(blockIdx.x) * kStemThreads + threadIdx.x;
-  const bool valid = px < HW;
-  float acc[kStemCo];
+  const int w0 = (blockIdx.x * kStemThreads + threadIdx.x) * kStemPx;
+  float2 acc[kStemPx][kStemCo / 2];
 #pragma unroll
-  for (int c = 0; c < kStemCo; ++c) acc[c] = 0.f;
-  if (valid) {
-    const int h = static_cast<int>(px / W), w = static_cast<int>(px % W);
+  for (int q = 0; q < kStemPx; ++q)
+#pragma unroll
+    for (int c = 0; c < kStemCo / 2; ++c) acc[q][c] = make_float2(0.f, 0.f);
+  if (w0 < W) {
     const float* base = img + static_cast<int64_t>(n) * 3 * HW;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = h + kh - 1;
+        const bool hin = ih >= 0 && ih < H;
+        const float* rowp = base + ci * HW + static_cast<int64_t>(ih) * W;
+        // the kStemPx + 2 input columns this thread needs
+        float v[kStemPx + 2];
+#pragma unroll
+        for (int j = 0; j < kStemPx + 2; ++j) {
+          const int iw = w0 + j - 1;
+          v[j] = (hin && iw >= 0 && iw < W) ? __ldg(rowp + iw) : 0.f;
+        }
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int iw = w + kw - 1;
-          float v = 0.f;
-          if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(base + ci * HW + static_cast<int64_t>(ih) * W + iw);
           const float4* wr = reinterpret_cast<const float4*>(wsm[ci * 9 + kh * 3 + kw]);
 #pragma unroll
           for (int c4 = 0; c4 < kStemCo / 4; ++c4) {
             const float4 ww = wr[c4];
-            acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
-            acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
-            acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+            const float2 wa = make_float2(ww.x, ww.y), wb = make_float2(ww.z, ww.w);
+#pragma unroll
+            for (int q = 0; q < kStemPx; ++q) {
+              const float2 vv = make_float2(v[q + kw], v[q + kw]);
+              acc[q][2 * c4] = __ffma2_rn(vv, wa, acc[q][2 * c4]);
+              acc[q][2 * c4 + 1] = __ffma2_rn(vv, wb, acc[q][2 * c4 + 1]);
+            }
           }
         }
       }
-    uint4* dst = reinterpret_cast<uint4*>(y + (static_cast<int64_t>(n) * HW + px) * yp);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      dst[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
-                          pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
+    for (int q = 0; q < kStemPx; ++q) {
+      if (w0 + q < W) {
+        uint4* dst = reinterpret_cast<uint4*>(y + (static_cast<int64_t>(n) * HW + static_cast<int64_t>(h) * W + w0 + q) * yp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_bf16x2(acc[q][4 * j].x, acc[q][4 * j].y), pack_bf16x2(acc[q][4 * j + 1].x, acc[q][4 * j + 1].y),
+                              pack_bf16x2(acc[q][4 * j + 2].x, acc[q][4 * j + 2].y),
+                              pack_bf16x2(acc[q][4 * j + 3].x, acc[q][4 * j + 3].y));
+      }
+    }
   }
   if (stats) {
+    // sums of the values as stored (bf16-rounded) over this block's pixels: per-lane over its pixels, then across lanes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float f[32], g[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const float v = valid ? bf16_round(acc[c]) : 0.f;
-      f[c] = v;
-      g[c] = v * v;
+    for (int c = 0; c < 32; ++c) f[c] = g[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < kStemPx; ++q) {
+      const bool valid = (w0 + q) < W;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float a0 = valid ? bf16_round(acc[q][c].x) : 0.f, a1 = valid ? bf16_round(acc[q][c].y) : 0.f;
+        f[2 * c] += a0;
+        g[2 * c] = fmaf(a0, a0, g[2 * c]);
+        f[2 * c + 1] += a1;
+        g[2 * c + 1] = fmaf(a1, a1, g[2 * c + 1]);
+      }
     }
     red[warp][lane][0] = warp_colsum32(f, lane);
     red[warp][lane][1] = warp_colsum32(g, lane);
@@ -203,26 +232,29 @@ __global__ void __launch_bounds__(kStemThreads) stem_fprop_kernel(const float* _
       float s = 0.f;
 #pragma unroll
       for (int wv = 0; wv < kStemThreads / 32; ++wv) s += red[wv][c][k];
-      stats[((static_cast<int64_t>(n) * P + blockIdx.x) * kStemCo + c) * 2 + k] = s;
+      const int p = blockIdx.y * gridDim.x + blockIdx.x;
+      stats[((static_cast<int64_t>(n) * P + p) * kStemCo + c) * 2 + k] = s;
     }
   }
 }
 
-// dW[co][ci][kh][kw] = sum dy[n,h,w,co] * img[n,ci,h+kh-1,w+kw-1].  lane = co; each block walks row segments of
-// kSegW pixels with the 3-row fp32 input patch staged in shared memory (broadcast reads), 27 accumulators per lane.
+// dW[co][ci][kh][kw] = sum dy[n,h,w,co] * img[n,ci,h+kh-1,w+kw-1].  A warp takes 2 pixels per step: lane = (pixel
+// sub-index, channel pair); the 3-row fp32 input patch of a row segment is staged in shared memory; 27 float2
+// accumulators per lane updated with packed FFMA2 (one instruction = both channels of the pair).
 constexpr int kSegW = 256;
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img,
-                                                          const __nv_bfloat16* __restrict__ dy, int64_t dyp,
-                                                          float* __restrict__ partial, int N, int H, int W) {
-  __shared__ float patch[3][3][kSegW + 2];
+__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restrict__ img,
+                                                             const __nv_bfloat16* __restrict__ dy, int64_t dyp,
+                                                             float* __restrict__ partial, int N, int H, int W) {
+  __shared__ float patch[3][3][kSegW + 4];
   __shared__ float red[8][kStemCo][27];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ps = lane >> 4, cp = lane & 15;  // pixel sub-index 0..1, channels 2*cp, 2*cp+1
   const int segs_w = (W + kSegW - 1) / kSegW;
   const int64_t total_segs = static_cast<int64_t>(N) * H * segs_w;
   const int64_t HW = static_cast<int64_t>(H) * W;
-  float acc[27];
+  float2 acc[27];
 #pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 27; ++k) acc[k] = make_float2(0.f, 0.f);
   for (int64_t seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
     const int sw = static_cast<int>(seg % segs_w);
     const int64_t r = seg / segs_w;
@@ -241,18 +273,38 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     }
     __syncthreads();
     const int wend = min(kSegW, W - w0);
-    for (int j = warp; j < wend; j += 8) {
-      const float d = __bfloat162float(dy[(static_cast<int64_t>(n) * HW + static_cast<int64_t>(h) * W + w0 + j) * dyp + lane]);
+    const __nv_bfloat16* drow = dy + (static_cast<int64_t>(n) * HW + static_cast<int64_t>(h) * W + w0) * dyp + 2 * cp;
+#pragma unroll 2
+    for (int j0 = warp * 2; j0 < wend; j0 += 16) {
+      const int j = j0 + ps;
+      float2 d = make_float2(0.f, 0.f);
+      if (j < wend) {
+        const uint32_t raw = *reinterpret_cast<const uint32_t*>(drow + static_cast<int64_t>(j) * dyp);
+        d = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+      }
+      const int jj = j < wend ? j : 0;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) acc[ci * 9 + kh * 3 + kw] = fmaf(d, patch[ci][kh][j + kw], acc[ci * 9 + kh * 3 + kw]);
+        for (int kh = 0; kh < 3; ++kh) {
+          const float p0 = patch[ci][kh][jj], p1 = patch[ci][kh][jj + 1], p2 = patch[ci][kh][jj + 2];
+          const int k = ci * 9 + kh * 3;
+          acc[k] = __ffma2_rn(d, make_float2(p0, p0), acc[k]);
+          acc[k + 1] = __ffma2_rn(d, make_float2(p1, p1), acc[k + 1]);
+          acc[k + 2] = __ffma2_rn(d, make_float2(p2, p2), acc[k + 2]);
+        }
     }
   }
+  // combine the two pixel sub-groups (lanes cp and cp+16), then the warps
 #pragma unroll
-  for (int k = 0; k < 27; ++k) red[warp][lane][k] = acc[k];
+  for (int k = 0; k < 27; ++k) {
+    const float vx = acc[k].x + __shfl_xor_sync(0xffffffffu, acc[k].x, 16);
+    const float vy = acc[k].y + __shfl_xor_sync(0xffffffffu, acc[k].y, 16);
+    if (ps == 0) {
+      red[warp][2 * cp][k] = vx;
+      red[warp][2 * cp + 1][k] = vy;
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < kStemCo * 27; i += 256) {
     const int co = i / 27, k = i % 27;
@@ -336,16 +388,17 @@ extern "C" int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void*
   return 0;
 }
 
-extern "C" int b200unet_stem_partials(int H, int W) {
-  return static_cast<int>(ceil_div64(static_cast<int64_t>(H) * W, kStemThreads));
-}
+static int stem_blocks_w(int W) { return ceil_div(W, kStemThreads * kStemPx); }
+
+extern "C" int b200unet_stem_partials(int H, int W) { return H * stem_blocks_w(W); }
 
 extern "C" int b200unet_stem_fprop(const float* img_nchw, const float* w_oihw, void* y, int64_t y_pitch, float* stats,
                                    int N, int H, int W, void* stream) {
   B200_CHECK_ARG(img_nchw && w_oihw && y, "stem_fprop: null pointer");
   B200_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= kStemCo, "stem_fprop: bad output pitch");
   const int P = b200unet_stem_partials(H, W);
-  stem_fprop_kernel<<<dim3(P, N), kStemThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200_CHECK_ARG(H <= 65535 && N <= 65535, "stem_fprop: H and N must fit the grid");
+  stem_fprop_kernel<<<dim3(stem_blocks_w(W), H, N), kStemThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       img_nchw, w_oihw, static_cast<__nv_bfloat16*>(y), y_pitch, stats, P, H, W);
   B200_LAUNCH_CHECK("stem_fprop_kernel");
   return 0;
