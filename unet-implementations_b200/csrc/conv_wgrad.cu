@@ -126,25 +126,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_con
     }
   } else if (warp == kMmaWarp) {
     if (elect_one()) {
+      // lean issue loop (see ptx.cuh): 32-bit descriptor halves, the K advance is an add on the low word
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t a_hi = umma_desc_hi(8 * kRowA, kSwzA), b_hi = umma_desc_hi(8 * kRowB, kSwzB);
+      constexpr uint32_t kStepA = (16 * kRowA) >> 4, kStepB = (16 * kRowB) >> 4;  // 16 pixels of K, in 16-byte units
       const int groups = (valid_units + UPG - 1) / UPG;
+      const uint32_t lo0 = umma_desc_lo(smem_u32(smem), 0);
+      constexpr uint32_t a_lbo = ((kUnitBytes >> 4) & 0x3FFFu) << 16, b_lbo = ((kDyBlockBytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+      uint32_t s = 0, ph = 0, acc = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % kWgStages;
-        const uint32_t ph = (i / kWgStages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t sb = smem_u32(smem + s * stage_bytes);
-        for (int g = 0; g < groups; ++g) {
-          const uint32_t sa = sb + kDyBytes + g * kGroupBytes;
+        const uint32_t b_lo = lo0 + s * stage16 + b_lbo;
+        uint32_t a_lo = lo0 + s * stage16 + (kDyBytes >> 4) + a_lbo;
+        for (int g = 0; g < groups; ++g, a_lo += (kGroupBytes >> 4)) {
+          // MN-major canonical layout: LBO = byte stride between channel blocks, SBO = 8 pixel rows
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // MN-major canonical layout: LBO = byte stride between channel blocks, SBO = 8 pixel rows
-            const uint64_t adesc = umma_smem_desc(sa + k * 16 * kRowA, kUnitBytes, 8 * kRowA, kSwzA);
-            const uint64_t bdesc = umma_smem_desc(sb + k * 16 * kRowB, kDyBlockBytes, 8 * kRowB, kSwzB);
-            umma_bf16(tmem_base + g * BN, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lean(tmem_base + g * BN, a_lo + k * kStepA, a_hi, b_lo + k * kStepB, b_hi, idesc, acc | k);
         }
+        acc = 1;
         umma_commit(&empty_bar[s]);
+        if (++s == kWgStages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);
     }

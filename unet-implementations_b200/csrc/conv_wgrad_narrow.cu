@@ -126,29 +126,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
     }
   } else if (warp == kMmaWarp) {
     if (elect_one()) {
+      // lean issue loop (see ptx.cuh): 32-bit descriptor halves, image-row advance = an add on the low word
       constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kNcols, 1, 1);
+      constexpr uint32_t a_hi = umma_desc_hi(8 * Cfg::kRowA, Cfg::kSwzA), b_hi = umma_desc_hi(8 * Cfg::kRowB, Cfg::kSwzB);
+      constexpr uint32_t kRowStepA = (16 * Cfg::kRowA) >> 4, kRowStepB = (16 * Cfg::kRowB) >> 4;  // one image row
+      // A: leading-dimension stride = one image row (kh slots);  B: leading-dimension stride = one shifted dY tile
+      constexpr uint32_t a_lbo = (((16 * Cfg::kRowA) >> 4) & 0x3FFFu) << 16, b_lbo = ((Cfg::kDyBytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t lo0 = umma_desc_lo(smem_u32(smem), 0);
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+      uint32_t s = 0, ph = 0, acc = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t sb = smem_u32(smem + s * stage_bytes);
-        const uint32_t sx = sb + 3 * Cfg::kDyBytes;
-#pragma unroll 1
+        const uint32_t b0 = lo0 + s * stage16 + b_lbo;
+        const uint32_t x0 = lo0 + s * stage16 + ((3 * Cfg::kDyBytes) >> 4) + a_lbo;
+#pragma unroll 2
         for (int r = 0; r < kWnR; ++r) {
-          // B: 16 pixels of image row r, three (kw) blocks Cfg::kDyBytes apart; SBO = 8 pixel rows
-          const uint64_t bdesc = umma_smem_desc(sb + r * 16 * Cfg::kRowB, Cfg::kDyBytes, 8 * Cfg::kRowB, Cfg::kSwzB);
-          for (int j = 0; j < CPB; ++j) {
+          const uint32_t b_lo = b0 + r * kRowStepB;
+          uint32_t a_lo = x0 + r * kRowStepA;
+          for (int j = 0; j < CPB; ++j, a_lo += (Cfg::kXBytes >> 4)) {
 #pragma unroll
-            for (int g = 0; g < Cfg::kGroups; ++g) {
-              // A: kh slot t of this group = patch row r + g*kSlots + t  ->  leading-dimension stride = one image row
-              const uint64_t adesc = umma_smem_desc(sx + j * Cfg::kXBytes + (r + g * Cfg::kSlots) * 16 * Cfg::kRowA,
-                                                    16 * Cfg::kRowA, 8 * Cfg::kRowA, Cfg::kSwzA);
-              umma_bf16(tmem_base + (j * Cfg::kGroups + g) * Cfg::kNcols, adesc, bdesc, idesc, (i | r) != 0 ? 1u : 0u);
-            }
+            for (int g = 0; g < Cfg::kGroups; ++g)
+              umma_bf16_lean(tmem_base + (j * Cfg::kGroups + g) * Cfg::kNcols, a_lo + g * Cfg::kSlots * kRowStepA, a_hi,
+                             b_lo, b_hi, idesc, acc | r);
           }
         }
+        acc = 1;
         umma_commit(&empty_bar[s]);
+        if (++s == static_cast<uint32_t>(STAGES)) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);
     }
