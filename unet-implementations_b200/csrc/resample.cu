@@ -22,81 +22,103 @@ __device__ __forceinline__ void unpack8r(const uint4& u, float (&f)[8]) {
   }
 }
 
-// one thread = 8 channels of one OUTPUT pixel
-__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
-                                                              __nv_bfloat16* __restrict__ out, int64_t op, int N, int H,
-                                                              int W, int C) {
-  const int c8n = C >> 3;
-  const int OH = 2 * H, OW = 2 * W;
-  const int64_t total = static_cast<int64_t>(N) * OH * OW * c8n;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c0 = static_cast<int>(i % c8n) << 3;
-  int64_t r = i / c8n;
-  const int ow = static_cast<int>(r % OW);
-  r /= OW;
-  const int oh = static_cast<int>(r % OH);
-  const int n = static_cast<int>(r / OH);
-  // source rows/cols and weights
-  const int ih = oh >> 1, iw = ow >> 1;
-  const int h_near = ih, h_far = (oh & 1) ? min(ih + 1, H - 1) : max(ih - 1, 0);
-  const int w_near = iw, w_far = (ow & 1) ? min(iw + 1, W - 1) : max(iw - 1, 0);
-  const __nv_bfloat16* b = x + static_cast<int64_t>(n) * H * W * xp + c0;
-  float nn[8], nf[8], fn[8], ff[8];
-  unpack8r(*reinterpret_cast<const uint4*>(b + (static_cast<int64_t>(h_near) * W + w_near) * xp), nn);
-  unpack8r(*reinterpret_cast<const uint4*>(b + (static_cast<int64_t>(h_near) * W + w_far) * xp), nf);
-  unpack8r(*reinterpret_cast<const uint4*>(b + (static_cast<int64_t>(h_far) * W + w_near) * xp), fn);
-  unpack8r(*reinterpret_cast<const uint4*>(b + (static_cast<int64_t>(h_far) * W + w_far) * xp), ff);
-  float o[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // same association as ATen's upsample_bilinear2d: interpolate along w, then along h
-    const float top = 0.75f * nn[j] + 0.25f * nf[j];
-    const float bot = 0.75f * fn[j] + 0.25f * ff[j];
-    o[j] = 0.75f * top + 0.25f * bot;
-  }
-  *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * op + c0) =
-      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+__device__ __forceinline__ uint4 pack8r(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
-// one thread = 8 channels of one INPUT pixel; gathers its 4x4 output neighbourhood
+// Forward: one thread = 8 channels of one INPUT pixel -> its 2x2 output block.  The 3x3 input neighbourhood comes
+// through L1 (each input element is shared by 9 threads of the same / adjacent warps); interpolation along w first,
+// then along h (the association of ATen's upsample_bilinear2d).  grid (ceil(W*C/8 / 256), H, N): no integer division
+// by runtime values.
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
+                                                              __nv_bfloat16* __restrict__ out, int64_t op, int H, int W,
+                                                              int c8n, int c8shift) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int iw = t >> c8shift;  // c8n is a power of two on this path
+  if (iw >= W) return;
+  const int c0 = (t & (c8n - 1)) << 3;
+  const int ih = blockIdx.y, n = blockIdx.z;
+  const int hm = ih > 0 ? ih - 1 : 0, hp = ih < H - 1 ? ih + 1 : H - 1;
+  const int wm = iw > 0 ? iw - 1 : 0, wp = iw < W - 1 ? iw + 1 : W - 1;
+  const __nv_bfloat16* b = x + static_cast<int64_t>(n) * H * W * xp + c0;
+  const int rows[3] = {hm, ih, hp};
+  float L[3][8], R[3][8];  // per source row: the two output columns 2iw, 2iw+1
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const __nv_bfloat16* rp = b + static_cast<int64_t>(rows[r]) * W * xp;
+    float a[8], c[8], d[8];
+    unpack8r(ldg16(rp + static_cast<int64_t>(wm) * xp), a);
+    unpack8r(ldg16(rp + static_cast<int64_t>(iw) * xp), c);
+    unpack8r(ldg16(rp + static_cast<int64_t>(wp) * xp), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      L[r][j] = 0.75f * c[j] + 0.25f * a[j];
+      R[r][j] = 0.75f * c[j] + 0.25f * d[j];
+    }
+  }
+  const int OW = 2 * W;
+  __nv_bfloat16* o = out + (static_cast<int64_t>(n) * 2 * H + 2 * ih) * OW * op + static_cast<int64_t>(2 * iw) * op + c0;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.75f * L[1][j] + 0.25f * L[0][j];
+  *reinterpret_cast<uint4*>(o) = pack8r(v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.75f * R[1][j] + 0.25f * R[0][j];
+  *reinterpret_cast<uint4*>(o + op) = pack8r(v);
+  o += static_cast<int64_t>(OW) * op;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.75f * L[1][j] + 0.25f * L[2][j];
+  *reinterpret_cast<uint4*>(o) = pack8r(v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.75f * R[1][j] + 0.25f * R[2][j];
+  *reinterpret_cast<uint4*>(o + op) = pack8r(v);
+}
+
+// Backward (gather): one thread = 8 channels of one INPUT pixel; separable: for each of the 4 output rows
+// 2ih-1 .. 2ih+2 (clamped) combine the 4 output columns 2iw-1 .. 2iw+2 (clamped) with (.25,.75,.75,.25), then the rows
+// with the same weights.  A clamped index is where the reference's edge-replicated tap landed, so its weight stays.
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int64_t dp,
-                                                              __nv_bfloat16* __restrict__ dx, int64_t xp, int N, int H,
-                                                              int W, int C) {
-  const int c8n = C >> 3;
+                                                              __nv_bfloat16* __restrict__ dx, int64_t xp, int H, int W,
+                                                              int c8n, int c8shift) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int iw = t >> c8shift;
+  if (iw >= W) return;
+  const int c0 = (t & (c8n - 1)) << 3;
+  const int ih = blockIdx.y, n = blockIdx.z;
   const int OH = 2 * H, OW = 2 * W;
-  const int64_t total = static_cast<int64_t>(N) * H * W * c8n;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c0 = static_cast<int>(i % c8n) << 3;
-  int64_t r = i / c8n;
-  const int iw = static_cast<int>(r % W);
-  r /= W;
-  const int ih = static_cast<int>(r % H);
-  const int n = static_cast<int>(r / H);
+  const __nv_bfloat16* b = dout + static_cast<int64_t>(n) * OH * OW * dp + c0;
+  int cols[4], rws[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int ow = 2 * iw - 1 + a, oh = 2 * ih - 1 + a;
+    cols[a] = ow < 0 ? 0 : (ow >= OW ? OW - 1 : ow);
+    rws[a] = oh < 0 ? 0 : (oh >= OH ? OH - 1 : oh);
+  }
   const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const __nv_bfloat16* b = dout + static_cast<int64_t>(n) * OH * OW * dp + c0;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    int oh = 2 * ih - 1 + a;
-    oh = oh < 0 ? 0 : (oh >= OH ? OH - 1 : oh);
+    const __nv_bfloat16* rp = b + static_cast<int64_t>(rws[a]) * OW * dp;
+    uint4 raw[4];
 #pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      int ow = 2 * iw - 1 + bb;
-      ow = ow < 0 ? 0 : (ow >= OW ? OW - 1 : ow);
-      float d[8];
-      unpack8r(*reinterpret_cast<const uint4*>(b + (static_cast<int64_t>(oh) * OW + ow) * dp), d);
-      const float wgt = wt[a] * wt[bb];
+    for (int bb = 0; bb < 4; ++bb) raw[bb] = ldg16(rp + static_cast<int64_t>(cols[bb]) * dp);
+    float d0[8], d1[8], d2[8], d3[8];
+    unpack8r(raw[0], d0);
+    unpack8r(raw[1], d1);
+    unpack8r(raw[2], d2);
+    unpack8r(raw[3], d3);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, d[j], acc[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float hsum = 0.25f * (d0[j] + d3[j]) + 0.75f * (d1[j] + d2[j]);
+      acc[j] = fmaf(wt[a], hsum, acc[j]);
     }
   }
-  *reinterpret_cast<uint4*>(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0) =
-      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                 pack_bf16x2(acc[6], acc[7]));
+  *reinterpret_cast<uint4*>(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0) = pack8r(acc);
 }
 
 // ------------------------------------------------------------------------------------------------ layout
@@ -143,13 +165,21 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int64
 
 using namespace b200;
 
+static int ilog2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
+}
+
 extern "C" int b200unet_upsample2x_fwd(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H,
                                        int W, int C, void* stream) {
   B200_CHECK_ARG(x && out, "upsample2x_fwd: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0, "upsample2x_fwd: C and pitches must be multiples of 8");
-  const int64_t total = static_cast<int64_t>(N) * 4 * H * W * (C / 8);
-  upsample2x_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(out), out_pitch, N, H, W, C);
+  const int c8n = C / 8, sh = ilog2_exact(c8n);
+  B200_CHECK_ARG(sh >= 0, "upsample2x_fwd: C/8 = %d must be a power of two", c8n);
+  B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_fwd: H and N must fit the grid");
+  upsample2x_fwd_kernel<<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(out), out_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_fwd_kernel");
   return 0;
 }
@@ -158,9 +188,11 @@ extern "C" int b200unet_upsample2x_bwd(const void* dout, int64_t dout_pitch, voi
                                        int W, int C, void* stream) {
   B200_CHECK_ARG(dout && dx, "upsample2x_bwd: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && dout_pitch % 8 == 0 && dx_pitch % 8 == 0, "upsample2x_bwd: C and pitches must be multiples of 8");
-  const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
-  upsample2x_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dout), dout_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, N, H, W, C);
+  const int c8n = C / 8, sh = ilog2_exact(c8n);
+  B200_CHECK_ARG(sh >= 0, "upsample2x_bwd: C/8 = %d must be a power of two", c8n);
+  B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_bwd: H and N must fit the grid");
+  upsample2x_bwd_kernel<<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), dout_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_bwd_kernel");
   return 0;
 }
