@@ -9,6 +9,7 @@
 // in shared memory once per block.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -54,8 +55,20 @@ static PixelMap make_map(int C) {
   return m;
 }
 // pixels per block so that the whole launch is ~8 blocks per SM, rounded to a multiple of 4 sweeps
-static int64_t pixels_per_block(int64_t HW, int N, const PixelMap& m) {
-  int64_t per_img = ceil_div64(static_cast<int64_t>(num_sms()) * 8, N);
+static int blocks_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B200UNET_NORM_BPS");  // developer knob
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 8;
+  }
+  return v;
+}
+// bps = blocks per SM over the whole launch.  Measured on B200 (tools/norm_bench.py): the streaming apply kernels want
+// many small blocks (32/SM: 6.1 TB/s vs 5.5 at 8/SM); the reduce kernel wants fewer (8/SM) because every block adds a
+// partial that the finalize kernel has to sum.
+static int64_t pixels_per_block(int64_t HW, int N, const PixelMap& m, int bps) {
+  int64_t per_img = ceil_div64(static_cast<int64_t>(num_sms()) * bps, N);
   if (per_img < 1) per_img = 1;
   int64_t chunk = ceil_div64(HW, per_img);
   const int64_t q = static_cast<int64_t>(m.lanes) * 4;
@@ -189,17 +202,18 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, f
   const __nv_bfloat16* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
   const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
   const int lanes = K.lanes;
-  for (int64_t px = lo + lane; px < hi; px += 2 * lanes) {
-    uint4 vy[2], vd[2], vd2[2];
+  constexpr int U = 4;  // pixels in flight per thread: 8-12 independent 16-byte loads cover the HBM latency
+  for (int64_t px = lo + lane; px < hi; px += U * lanes) {
+    uint4 vy[U], vd[U], vd2[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
         vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
         vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
         if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (px + u * lanes >= hi) break;
       float yv[8], d[8];
       unpack8(vy[u], yv);
@@ -321,17 +335,18 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_apply_kernel(InBwdK K, co
   const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
   __nv_bfloat16* ob = dy + static_cast<int64_t>(n) * K.HW * dyp + c0;
   const int lanes = K.lanes;
-  for (int64_t px = lo + lane; px < hi; px += 2 * lanes) {
-    uint4 vy[2], vd[2], vd2[2];
+  constexpr int U = 4;
+  for (int64_t px = lo + lane; px < hi; px += U * lanes) {
+    uint4 vy[U], vd[U], vd2[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
         vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
         vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
         if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (px + u * lanes >= hi) break;
       float yv[8], d[8], o[8];
       unpack8(vy[u], yv);
@@ -380,7 +395,7 @@ extern "C" int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a,
   int rc = check_nhwc("in_apply", C, y_pitch, z_pitch, 0);
   if (rc) return rc;
   const PixelMap m = make_map(C);
-  const int64_t chunk = pixels_per_block(HW, N, m);
+  const int64_t chunk = pixels_per_block(HW, N, m, 4 * blocks_per_sm());
   in_apply_kernel<<<dim3((unsigned)ceil_div64(HW, chunk), N), m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), y_pitch, a, b, slope, static_cast<__nv_bfloat16*>(z), z_pitch, HW, C, m.c8n,
       m.lanes, chunk);
@@ -401,7 +416,7 @@ static int bwd_images_per_chunk(int N, int64_t HW, int C, bool has_dz2) {
 static int bwd_partials(int N, int64_t HW, int C, bool has_dz2) {
   const PixelMap m = make_map(C);
   const int ipc = bwd_images_per_chunk(N, HW, C, has_dz2);
-  const int64_t chunk = pixels_per_block(HW, ipc, m);
+  const int64_t chunk = pixels_per_block(HW, ipc, m, blocks_per_sm());
   return static_cast<int>(ceil_div64(HW, chunk));
 }
 
@@ -426,7 +441,9 @@ extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream)
   const bool has2 = A->dz2 != nullptr;
   const PixelMap m = make_map(C);
   const int ipc = bwd_images_per_chunk(N, HW, C, has2);
-  const int64_t chunk = pixels_per_block(HW, ipc, m);
+  const int64_t chunk = pixels_per_block(HW, ipc, m, blocks_per_sm());
+  // the backward apply re-loads ~56 per-channel parameters per thread at block start: it keeps the coarser grid
+  const int64_t chunk_apply = chunk;
   const int P = static_cast<int>(ceil_div64(HW, chunk));
   float* part = A->workspace;
   float* coef = part + static_cast<int64_t>(N) * P * C * 2;
@@ -457,7 +474,10 @@ extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream)
     in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
                                                                      imgsum, C, n0, inv_hw);
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
-    in_bwd_apply_kernel<<<dim3(P, nn), m.threads, 0, st>>>(K, coef, static_cast<__nv_bfloat16*>(A->dy), A->dy_pitch);
+    K.chunk = chunk_apply;
+    in_bwd_apply_kernel<<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+        K, coef, static_cast<__nv_bfloat16*>(A->dy), A->dy_pitch);
+    K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
   in_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
