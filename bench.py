@@ -268,11 +268,36 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with host buffers: every step copies ITS batch (image + int64 mask) from
+    # pinned host memory and reads its loss back to the host.  The copies run on a side stream one step ahead of the
+    # compute stream (what a pinned-memory DataLoader with non_blocking copies does), so they overlap the previous
+    # step's kernels; each of the K timed steps still issues and waits for its own H2D copy and D2H read.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(image_d), torch.empty_like(mask_d)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the step that last used this slot has finished with it
+            bufs[slot][0].copy_(image_h, non_blocking=True)
+            bufs[slot][1].copy_(mask_h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    for sl in range(2):
+        consumed[sl].record()
+
     def e2e_step():
-        img = image_h.to(dev, non_blocking=True)
-        msk = mask_h.to(dev, non_blocking=True)
-        loss = step(img, msk)
+        i = state["i"]
+        slot = i & 1
+        if i == 0:
+            prefetch(0)
+        prefetch(slot ^ 1)  # next step's batch, overlapping this step's compute
+        torch.cuda.current_stream().wait_event(ready[slot])
+        loss = step(bufs[slot][0], bufs[slot][1])
+        consumed[slot].record()
+        state["i"] = i + 1
         return loss.item()
 
     if args.no_e2e:

@@ -28,6 +28,8 @@ CONV_CASES = [
     (1, 8, 8, 512, 512, 1), (1, 8, 8, 512, 512, 2), (1, 8, 8, 1024, 512, 1), (1, 8, 8, 768, 256, 1),
     (1, 8, 16, 384, 128, 1), (1, 16, 16, 192, 64, 1), (2, 16, 32, 96, 32, 1),
     (2, 13, 21, 64, 64, 1), (2, 13, 21, 64, 96, 2), (1, 5, 7, 32, 32, 1), (3, 2, 2, 64, 64, 2),
+    # wide images: the narrow-output kernels (column taps stacked on N, 30-of-32 column tiles, ragged edges)
+    (1, 12, 70, 32, 32, 1), (1, 9, 64, 96, 32, 1), (2, 8, 96, 64, 64, 1), (1, 6, 121, 64, 32, 1), (1, 7, 90, 32, 64, 1),
 ]
 
 

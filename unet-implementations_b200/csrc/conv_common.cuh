@@ -57,6 +57,16 @@ static inline int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 :
 // fp32 split-K partials [S][9][cin][cout] -> OIHW gradient (conv_tc.cu)
 int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st);
 
+// Narrow-output forward / data gradient with the column taps stacked on N (conv_narrow.cu): stride 1, N-side
+// channels in {32, 64}, weights resident in shared memory, image at least 64 pixels wide.
+bool nconv_supported(int k_channels, int n_channels, int stride, int W);
+int nconv_stat_slots(int N, int H, int W);
+int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
+                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st);
+// Partial-sum slots per image of the fprop statistics buffer [N][P][Cout][2]: one value for both fprop kernels
+// (conv_fprop_dgrad.cu), so that the caller can size the buffer without knowing which kernel will run.
+int conv_stat_slots(int N, int OH, int OW, int Cout);
+
 // Narrow-output weight gradient (conv_wgrad_narrow.cu): stride 1, Cout in {32, 64}, Cin a multiple of 32.
 bool wgradn_supported(int Cin, int Cout, int stride);
 int64_t wgradn_workspace_bytes(int N, int H, int W, int Cin, int Cout);

@@ -525,6 +525,14 @@ static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN) {
   return g;
 }
 
+int conv_stat_slots(int N, int OH, int OW, int Cout) {
+  const int BN = pick_bn_gconv(Cout, 64);
+  if (!BN) return -1;
+  const int a = gconv_grid(N, OH, OW, Cout, BN).stat_slots;
+  const int b = (Cout == 32 || Cout == 64) ? nconv_stat_slots(N, OH, OW) : 0;
+  return a > b ? a : b;
+}
+
 // Developer instrumentation: B200UNET_GCONV_DEBUG=1 makes every launch synchronise and print per-role wait cycles.
 static long long* debug_buffer() {
   static long long* buf = nullptr;
@@ -552,8 +560,8 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
   GConvGrid gg = gconv_grid(p.N, p.OH, p.OW, p.cout, BN);
   const int grid = gg.grid;
   p.tiles_per_cta = gg.tiles_per_cta;
-  p.stat_slots = gg.stat_slots;
-  if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * gg.stat_slots * p.cout * 2 * sizeof(float), st));
+  p.stat_slots = conv_stat_slots(p.N, p.OH, p.OW, p.cout);  // P of the caller's buffer (>= gg.stat_slots)
+  if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * p.cout * 2 * sizeof(float), st));
   if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("gconv_kernel");
@@ -600,11 +608,7 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
 
 using namespace b200;
 
-extern "C" int b200unet_conv_fprop_partials(int N, int OH, int OW, int Cout) {
-  const int BN = pick_bn_gconv(Cout, 64);
-  if (!BN) return -1;
-  return gconv_grid(N, OH, OW, Cout, BN).stat_slots;
-}
+extern "C" int b200unet_conv_fprop_partials(int N, int OH, int OW, int Cout) { return conv_stat_slots(N, OH, OW, Cout); }
 
 extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stream) {
   B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop: null pointer");
@@ -614,6 +618,9 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
     return set_error(kErrUnsupported, "conv_fprop: Cin=%d Cout=%d outside the tensor-core envelope (multiples of 32)",
                      a->Cin, a->Cout);
   B200_CHECK_ARG(a->x_pitch % 8 == 0 && a->y_pitch % 8 == 0, "conv_fprop: pitches must be multiples of 8 elements");
+  if (nconv_supported(a->Cin, a->Cout, a->stride, a->W))
+    return nconv_launch(a->x, a->x_pitch, a->w, a->y, a->y_pitch, a->stats, a->N, a->H, a->W, a->Cin, a->Cout, 0,
+                        conv_stat_slots(a->N, a->H, a->W, a->Cout), static_cast<cudaStream_t>(stream));
   const int s = a->stride;
   const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   GConvParams p{};
@@ -665,6 +672,9 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
   if (!BK || !BN)
     return set_error(kErrUnsupported, "conv_dgrad: Cin=%d Cout=%d outside the tensor-core envelope", a->Cin, a->Cout);
   B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad: pitches must be multiples of 8 elements");
+  if (nconv_supported(a->Cout, a->Cin, a->stride, a->W))
+    return nconv_launch(a->dy, a->dy_pitch, a->wt, a->dx, a->dx_pitch, nullptr, a->N, a->H, a->W, a->Cout, a->Cin, 1, 0,
+                        static_cast<cudaStream_t>(stream));
   const int s = a->stride;
   const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);

@@ -1,0 +1,402 @@
+// 3x3 / stride-1 convolutions with a NARROW output (N = Cout for fprop, N = Cin for dgrad, N in {32, 64}) on
+// tcgen05 / TMEM: the 512^2 and 256^2 levels of the UNet.  Same role as conv_fprop_dgrad.cu (nn.Conv2d forward and the
+// data-gradient half of aten::convolution_backward, Our_UNet/models/unet.py:106-115); dispatched from there.
+//
+// Why a second kernel.  On B200 a tcgen05.mma with M = 128 costs max(~45, N/2) cycles (tools/micro/umma_rate.cu): the
+// A operand (128 x 16 bf16 = 4 KB) is re-read from shared memory for every MMA, so N = 32 runs at 36 % and N = 64 at
+// 67 % of the tensor pipe, and the single issuing thread spends one MMA + one barrier round trip per tap.  Here the
+// three COLUMN taps (kw) are stacked on N instead:
+//     E[pixel, (co, kw)] = sum_{kh, ci} X[h + kh - 1, w', ci] * W[co, ci, kh, kw]          (N = 3 * Cout = 96 / 192)
+//     out[h, w, co]      = E[(h, w-1), (co, 0)] + E[(h, w), (co, 1)] + E[(h, w+1), (co, 2)]
+//   * one A patch of 6 image rows x 32 pixels per channel chunk serves all 9 taps (the kh shift is a 32-row window
+//     offset inside the patch, swizzle-aligned), 3x fewer MMAs, each 3x wider;
+//   * a tile is 4 image rows x 32 pixels = one warp per row, so the +-1 pixel shift of the epilogue is a warp
+//     shuffle; lanes 0 and 31 are halo: a tile produces 4 x 30 outputs and tiles step by 30 columns (94 % of M);
+//   * the weights need no second packing: a 4-D tensor map over the packed [Cout][3][3][Cin] matrix delivers the
+//     [(co, kw) x BK] tile of one kh directly; the whole slab stays resident in shared memory.
+// Persistent CTAs, 4 TMA producer warps, one lean MMA-issuing thread, two TMEM accumulator buffers, epilogue warps
+// that also produce the InstanceNorm partial sums (see conv_fprop_dgrad.cu for the shared conventions).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "conv_common.cuh"
+
+namespace b200 {
+
+constexpr int kNcTH = 4, kNcTW = 32, kNcValidW = 30;  // tile rows / columns (lanes) / valid output columns
+constexpr int kNcPatchRows = kNcTH + 2;
+
+struct NConvParams {
+  int N, H, W, tiles_w, tiles_h;
+  int cin;   // K-side channels (multiple of BK)
+  int rev;   // 0 fprop: window kh pairs with weight row kh, E_kw at column 3*co + kw; 1 dgrad: both reversed
+  int tiles_per_cta;
+  int stat_slots;
+  float* stats;
+};
+
+struct NConvMaps {
+  CUtensorMap src;  // box (BK, 32, 6, 1)
+  CUtensorMap w;    // 4-D (K-side channel, kw, kh, N-side channel), box (BK, 3, 1, CO)
+  CUtensorMap out;  // box (CO, 30, 4, 1)
+};
+
+template <int BK, int CO, int A_SLOTS>
+struct NConvCfg {
+  static constexpr int kRowBytes = BK * 2;
+  static constexpr int kASlotBytes = kNcPatchRows * kNcTW * kRowBytes;  // 24 KB (BK = 64) / 12 KB
+  static constexpr int kWin16 = (kNcTW * kRowBytes) >> 4;               // one image row of the patch, 16-byte units
+  static constexpr int kNeff = 3 * CO;
+  static constexpr int kBTileBytes = kNeff * kRowBytes;                 // [(co, kw) x BK] of one kh: 6 / 24 KB
+  static constexpr int kBResBytes = 80 * 1024;
+  static constexpr int kStageBufBytes = ((kNcTH * kNcValidW * CO * 2 + 1023) / 1024) * 1024;
+  static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBResBytes + 2 * kStageBufBytes + 1024;
+  static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
+  static constexpr uint32_t kSbo = 8 * kRowBytes;
+  static constexpr uint32_t kTmemCols = (2 * kNeff <= 256) ? 256 : 512;
+  static_assert(kBTileBytes % 1024 == 0, "weight tiles must keep the swizzle alignment");
+  static_assert(A_SLOTS % kProducerWarps == 0, "each producer owns a fixed subset of slots");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int BK, int CO, int A_SLOTS>
+__global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
+                                                                 const __grid_constant__ NConvParams p) {
+  using Cfg = NConvCfg<BK, CO, A_SLOTS>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
+  __shared__ __align__(8) uint64_t b_full;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + A_SLOTS * Cfg::kASlotBytes;
+  uint8_t* staging = smem_b + Cfg::kBResBytes;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int total_tiles = tiles_per_img * p.N;
+  const int chunks = p.cin / BK;
+  const int tile_lo = min(static_cast<int>(blockIdx.x) * p.tiles_per_cta, total_tiles);
+  const int tile_hi = min(tile_lo + p.tiles_per_cta, total_tiles);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(&b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(&tmem_base_holder, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp < kProducerWarps) {
+    if (elect_one()) {
+      if (warp == 0) {
+        // resident weights: tile (c, kh) = [(n, kw) x BK] of weight row kh and K chunk c
+        tma_prefetch_desc(&maps.w);
+        mbar_expect_tx(&b_full, static_cast<uint32_t>(chunks) * 3 * Cfg::kBTileBytes);
+        for (int c = 0; c < chunks; ++c)
+          for (int kh = 0; kh < 3; ++kh)
+            tma_load_4d(smem_b + (c * 3 + kh) * Cfg::kBTileBytes, &maps.w, &b_full, c * BK, 0, kh, 0);
+      }
+      tma_prefetch_desc(&maps.src);
+      int it = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+        const int n_img = tile / tiles_per_img;
+        const int t_in = tile - n_img * tiles_per_img;
+        const int th = t_in / p.tiles_w;
+        const int h0 = th * kNcTH, w0 = (t_in - th * p.tiles_w) * kNcValidW;
+        const long long g0 = static_cast<long long>(it) * chunks;
+        int c = (warp - static_cast<int>(g0 % kProducerWarps) + kProducerWarps) % kProducerWarps;
+        for (; c < chunks; c += kProducerWarps) {
+          const long long g = g0 + c;
+          const int slot = static_cast<int>(g % A_SLOTS);
+          const uint32_t ph = static_cast<uint32_t>((g / A_SLOTS) & 1);
+          mbar_wait(&a_empty[slot], ph ^ 1);
+          mbar_expect_tx(&a_full[slot], Cfg::kASlotBytes);
+          tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src, &a_full[slot], c * BK, w0 - 1, h0 - 1, n_img);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kNeff, 0, 0);
+      constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);
+      constexpr uint32_t kASlot16 = Cfg::kASlotBytes >> 4, kBTile16 = Cfg::kBTileBytes >> 4;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b), 16);
+      const uint32_t a_full0 = smem_u32(&a_full[0]), a_empty0 = smem_u32(&a_empty[0]);
+      mbar_wait(&b_full, 0);
+      tc_fence_after();
+      uint32_t aslot = 0, aph = 0;
+      int it = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * Cfg::kNeff;
+        uint32_t acc = 0;
+        uint32_t b_c = b_lo0;
+        for (int c = 0; c < chunks; ++c, b_c += 3 * kBTile16) {
+          mbar_wait_u32(a_full0 + aslot * 8, aph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + aslot * kASlot16;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            // window kh of the patch pairs with weight row kh (fprop) or 2 - kh (dgrad)
+            const uint32_t b_lo = b_c + (p.rev ? (2 - kh) : kh) * kBTile16;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_lean(d_tmem, a_lo + kh * Cfg::kWin16 + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit_u32(a_empty0 + aslot * 8);
+          if (++aslot == A_SLOTS) { aslot = 0; aph ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 5..8): warp q = tile row q
+    const int q = warp & 3;
+    const int et = threadIdx.x - 32 * kEpiWarp0;
+    const bool do_stats = p.stats != nullptr;
+    const bool col_ok = lane >= 1 && lane <= kNcValidW;
+    const int srow = q * kNcValidW + lane - 1;  // staging row of this thread's output pixel
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};       // [s1 c0, s2 c0, s1 c1, s2 c1] of this lane's channel pair
+    int acc_img = -1;
+    auto flush = [&](int img) {
+      const int first_tile = img * tiles_per_img;
+      const int b0 = first_tile / p.tiles_per_cta;
+      const int slot = (static_cast<int>(blockIdx.x) - b0) * 4 + q;
+      float* dst = p.stats + (static_cast<size_t>(img) * p.stat_slots + slot) * CO * 2;
+      if (CO == 64) {
+        *reinterpret_cast<float4*>(dst + (2 * lane) * 2) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+        const float a0 = acc[0] + __shfl_down_sync(0xffffffffu, acc[0], 16);
+        const float a1 = acc[1] + __shfl_down_sync(0xffffffffu, acc[1], 16);
+        const float a2 = acc[2] + __shfl_down_sync(0xffffffffu, acc[2], 16);
+        const float a3 = acc[3] + __shfl_down_sync(0xffffffffu, acc[3], 16);
+        if (lane < 16) *reinterpret_cast<float4*>(dst + (2 * lane) * 2) = make_float4(a0, a1, a2, a3);
+      }
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    };
+    int it = 0;
+    uint32_t sbuf = 0;
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it, sbuf ^= 1) {
+      const int n_img = tile / tiles_per_img;
+      const int t_in = tile - n_img * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int h0 = th * kNcTH, w0 = (t_in - th * p.tiles_w) * kNcValidW;
+      if (do_stats && n_img != acc_img) {
+        if (acc_img >= 0) flush(acc_img);
+        acc_img = n_img;
+      }
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], static_cast<uint32_t>((it >> 1) & 1));
+      tc_fence_after();
+      if (et == 0) tma_store_wait_read_1();  // the store issued two tiles ago read this staging buffer
+      named_bar_sync(1, 128);
+      uint8_t* stg = staging + sbuf * Cfg::kStageBufBytes;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kNeff;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CO; c0 += 32) {
+        // 32 output channels = 96 accumulator columns (co, kw) starting at 3 * c0
+        uint32_t v[96];
+        tmem_ld_32x32(t_addr + 3 * c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(t_addr + 3 * c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_32x32(t_addr + 3 * c0 + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * j + e;
+            // left neighbour's column tap (kw = 0 in fprop order) and right neighbour's (kw = 2)
+            const float from_left = __shfl_up_sync(0xffffffffu, __uint_as_float(p.rev ? v[3 * c + 2] : v[3 * c]), 1);
+            const float from_right = __shfl_down_sync(0xffffffffu, __uint_as_float(p.rev ? v[3 * c] : v[3 * c + 2]), 1);
+            o[e] = __uint_as_float(v[3 * c + 1]) + from_left + from_right;
+          }
+          pk[j] = pack_bf16x2(o[0], o[1]);
+        }
+        if (col_ok) {
+          if (CO == 64) {
+            const uint32_t base = smem_u32(stg) + srow * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int cj = (c0 >> 3) + i;
+              const uint32_t addr = base + (((cj ^ (srow & 7)) & 7) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                           : "memory");
+            }
+          } else {
+            const uint32_t base = smem_u32(stg) + srow * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t addr = base + (((i ^ ((srow >> 1) & 3)) & 3) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                           : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (et == 0) {
+        tma_store_4d(&maps.out, stg, 0, w0, h0, n_img);
+        tma_store_commit();
+      }
+      if (do_stats) {
+        // warp q sums staging rows [30q, 30q + 30) (its own image row): lane = channel pair (CO = 64) or
+        // (row parity, channel pair) (CO = 32); only pixels inside the image count
+        constexpr int kSteps = (CO == 64) ? kNcValidW : kNcValidW / 2;
+        const uint32_t cp = (CO == 64) ? static_cast<uint32_t>(lane) : (static_cast<uint32_t>(lane) & 15);
+        const uint32_t par = (CO == 64) ? 0u : (static_cast<uint32_t>(lane) >> 4);
+        const uint32_t cw = cp >> 2, wi = (cp & 3) << 2;
+        const bool row_in = (h0 + q) < p.H;
+        float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+        for (int i0 = 0; i0 < kSteps; i0 += 5) {
+          uint32_t w[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const int col = (CO == 64) ? (i0 + i) : (2 * (i0 + i) + static_cast<int>(par));
+            const int r = q * kNcValidW + col;
+            const uint32_t off = (CO == 64) ? (r * 128 + (((cw ^ (r & 7)) & 7) << 4) + wi)
+                                            : (r * 64 + (((cw ^ ((r >> 1) & 3)) & 3) << 4) + wi);
+            w[i] = *reinterpret_cast<const uint32_t*>(stg + off);
+            if (!row_in || w0 + col >= p.W) w[i] = 0;
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
+            s1a += x0;
+            s2a = fmaf(x0, x0, s2a);
+            s1b += x1;
+            s2b = fmaf(x1, x1, s2b);
+          }
+        }
+        acc[0] += s1a;
+        acc[1] += s2a;
+        acc[2] += s1b;
+        acc[3] += s2b;
+      }
+    }
+    if (do_stats && acc_img >= 0) flush(acc_img);
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- host side
+struct NConvGrid {
+  int grid, tiles_per_cta, stat_slots, tiles_w, tiles_h;
+};
+
+static NConvGrid nconv_grid(int N, int H, int W) {
+  NConvGrid g;
+  g.tiles_w = ceil_div(W, kNcValidW);
+  g.tiles_h = ceil_div(H, kNcTH);
+  const long long per_img = static_cast<long long>(g.tiles_w) * g.tiles_h;
+  const long long total = per_img * N;
+  g.tiles_per_cta = static_cast<int>(ceil_div64(total, num_sms()));
+  if (g.tiles_per_cta < 1) g.tiles_per_cta = 1;
+  g.grid = static_cast<int>(ceil_div64(total, g.tiles_per_cta));
+  g.stat_slots = 4 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);
+  return g;
+}
+
+bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
+  if (stride != 1 || (n_channels != 32 && n_channels != 64) || k_channels % 32 != 0 || k_channels <= 0) return false;
+  if (W < 64) return false;  // the 30-of-32 column tiling only pays on wide images
+  const int BK = (k_channels % 64 == 0) ? 64 : 32;
+  return static_cast<long long>(k_channels / BK) * 3 * (3 * n_channels * BK * 2) <= 80 * 1024;  // resident weights
+}
+
+int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
+
+template <int BK, int CO, int A_SLOTS>
+static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& g, cudaStream_t st) {
+  // p.stat_slots = P of the caller's buffer (>= this kernel's own slot count); unused slots stay zero
+  using Cfg = NConvCfg<BK, CO, A_SLOTS>;
+  auto kern = nconv_kernel<BK, CO, A_SLOTS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if (p.stats)
+    B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
+  kern<<<g.grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  B200_LAUNCH_CHECK("nconv_kernel");
+  return 0;
+}
+
+// src: [N,H,W,K-side channels] (x for fprop, dy for dgrad); wpack: [N-side channels][3][3][K-side channels];
+// out: [N,H,W,n_channels] (y / dx); rev = 0 fprop, 1 dgrad
+int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
+                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st) {
+  const int BK = (k_channels % 64 == 0) ? 64 : 32;
+  const NConvGrid g = nconv_grid(N, H, W);
+  NConvParams p{};
+  NConvMaps maps;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_w = g.tiles_w;
+  p.tiles_h = g.tiles_h;
+  p.cin = k_channels;
+  p.rev = rev;
+  p.tiles_per_cta = g.tiles_per_cta;
+  p.stat_slots = stat_slots > g.stat_slots ? stat_slots : g.stat_slots;
+  p.stats = stats;
+  int rc;
+  if ((rc = make_act_map(&maps.src, static_cast<const __nv_bfloat16*>(src), src_pitch, N, H, W, k_channels, 1, 1, 0, 0, BK,
+                         kNcTW, kNcPatchRows)))
+    return rc;
+  if ((rc = make_act_map(&maps.out, static_cast<const __nv_bfloat16*>(out), out_pitch, N, H, W, n_channels, 1, 1, 0, 0,
+                         n_channels, kNcValidW, kNcTH)))
+    return rc;
+  {
+    // weights as a 4-D tensor (K-side channel, kw, kh, N-side channel) over the packed [n][kh][kw][k] matrix
+    const uint64_t kc = static_cast<uint64_t>(k_channels);
+    uint64_t dims[4] = {kc, 3, 3, static_cast<uint64_t>(n_channels)};
+    uint64_t strides[3] = {kc * 2, 3 * kc * 2, 9 * kc * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(BK), 3, 1, static_cast<uint32_t>(n_channels)};
+    if ((rc = make_tmap_bf16(&maps.w, wpack, 4, dims, strides, box,
+                             BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
+      return rc;
+  }
+  if (BK == 64 && n_channels == 64) return launch_nconv<64, 64, 4>(maps, p, g, st);
+  if (BK == 64 && n_channels == 32) return launch_nconv<64, 32, 4>(maps, p, g, st);
+  if (BK == 32 && n_channels == 64) return launch_nconv<32, 64, 8>(maps, p, g, st);
+  return launch_nconv<32, 32, 8>(maps, p, g, st);
+}
+
+}  // namespace b200
