@@ -10,9 +10,9 @@
 #include "conv_common.cuh"
 using namespace b200;
 
-constexpr int MAXS = 8, MAXP = 4;
+constexpr int MAXS = 8, MAXP = 8;
 
-__global__ void __launch_bounds__(256, 1) tma_kernel(const __grid_constant__ CUtensorMap map, int box_bytes, int G,
+__global__ void __launch_bounds__(512, 1) tma_kernel(const __grid_constant__ CUtensorMap map, int box_bytes, int G,
                                                       int stages, int P, int iters, int tiles_w, int tiles_h, int boxH,
                                                       int nimg, long long* cycles, long long* issue_cycles, int rank2) {
   extern __shared__ uint8_t smem_raw[];
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256, 1) tma_kernel(const __grid_constant__ CUt
     }
     cycles[blockIdx.x * MAXP + p] = clock64() - t0;
     issue_cycles[blockIdx.x * MAXP + p] = iss;
-  } else if (warp >= 4 && warp < 4 + P && lane == 0) {
-    const int p = warp - 4;
+  } else if (warp >= 8 && warp < 8 + P && lane == 0) {
+    const int p = warp - 8;
     for (int i = 0; i < iters; ++i) {
       const int s = i % stages;
       mbar_wait(&full_bar[p][s], (i / stages) & 1);
@@ -71,8 +71,9 @@ int main() {
     size_t bytes = (size_t)N * H * W * C * 2;
     cudaMalloc(&buf, bytes);
     cudaMemset(buf, 0, bytes);
+    for (int nimg : {32, 1})
     for (int rank2 : {0, 1})
-      for (int boxH : {2, 4, 8, 16}) {
+      for (int boxH : {4, 8, 16}) {
         CUtensorMap map;
         const int box_bytes = C * 2 * 16 * boxH;
         if (rank2) {
@@ -81,8 +82,8 @@ int main() {
           uint32_t box[2] = {(uint32_t)C, (uint32_t)(16 * boxH)};
           if (make_tmap_bf16(&map, buf, 2, dims, strides, box, C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) { printf("map2 failed: %s\n", b200unet_last_error()); return 1; }
         } else if (make_act_map(&map, buf, C, N, H, W, C, 1, 1, 0, 0, C, 16, boxH)) { printf("map failed: %s\n", b200unet_last_error()); return 1; }
-        for (int P : {1, 4})
-          for (int G : {1, 4}) {
+        for (int P : {1, 4, 8})
+          for (int G : {1, 2}) {
             const int stages = 4;
             const int smem = P * stages * G * box_bytes + 1024;
             if (smem > 220 * 1024) continue;
@@ -93,7 +94,7 @@ int main() {
             float ms = 0;
             for (int rep = 0; rep < 2; ++rep) {
               cudaEventRecord(e0);
-              tma_kernel<<<148, 256, smem>>>(map, box_bytes, G, stages, P, iters, tiles_w, tiles_h, boxH, 32, d, d2, rank2);
+              tma_kernel<<<148, 512, smem>>>(map, box_bytes, G, stages, P, iters, tiles_w, tiles_h, boxH, nimg, d, d2, rank2);
               cudaEventRecord(e1);
               if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
               cudaEventElapsedTime(&ms, e0, e1);
@@ -104,8 +105,8 @@ int main() {
             long long mx = 0, is = 0;
             for (int i = 0; i < 148; ++i) for (int p = 0; p < P; ++p) { if (h[i * MAXP + p] > mx) mx = h[i * MAXP + p]; if (h2[i * MAXP + p] > is) is = h2[i * MAXP + p]; }
             const double boxes = (double)iters * G * P;
-            printf("C=%2d rank%d box %3d rows (%5d B) P=%d G=%d: %7.1f cycles/box/SM  issue %6.1f cycles/box  %6.1f B/cycle/SM  chip %6.2f TB/s\n",
-                   C, rank2 ? 2 : 4, 16 * boxH, box_bytes, P, G, (double)mx / (iters * G * P), (double)is / (iters * G),
+            printf("imgs=%2d C=%2d rank%d box %3d rows (%5d B) P=%d G=%d: %7.1f cycles/box/SM  issue %6.1f cycles/box  %6.1f B/cycle/SM  chip %6.2f TB/s\n",
+                   nimg, C, rank2 ? 2 : 4, 16 * boxH, box_bytes, P, G, (double)mx / (iters * G * P), (double)is / (iters * G),
                    boxes * box_bytes / (double)mx, 148.0 * boxes * box_bytes / (ms * 1e-3) / 1e12);
           }
       }

@@ -47,8 +47,11 @@ static inline int pick_bn(int n_total) {
   return 0;
 }
 // N tile of the fprop/dgrad kernel: additionally 96 (one tile instead of three 32-wide ones, 75 % MMA rate)
+// and 192 (N = 192 / 384: the data gradients of the decoder convs that read a concat buffer -- one or two full-rate
+// tiles instead of three 64- or 128-wide passes over the same A operand)
 static inline int pick_bn_gconv(int n_total, int bk) {
   if (n_total == 96 && bk == 32) return 96;
+  if ((n_total == 192 || n_total == 384) && bk == 64) return 192;
   return pick_bn(n_total);
 }
 static inline int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 0); }

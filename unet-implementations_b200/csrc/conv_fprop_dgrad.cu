@@ -526,11 +526,17 @@ static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN) {
 }
 
 int conv_stat_slots(int N, int OH, int OW, int Cout) {
-  const int BN = pick_bn_gconv(Cout, 64);
-  if (!BN) return -1;
-  const int a = gconv_grid(N, OH, OW, Cout, BN).stat_slots;
-  const int b = (Cout == 32 || Cout == 64) ? nconv_stat_slots(N, OH, OW) : 0;
-  return a > b ? a : b;
+  // the largest slot count over the kernels / N tiles that may run for this Cout (the choice depends on Cin)
+  const int BN64 = pick_bn_gconv(Cout, 64), BN32 = pick_bn_gconv(Cout, 32);
+  if (!BN64 || !BN32) return -1;
+  int slots = gconv_grid(N, OH, OW, Cout, BN64).stat_slots;
+  const int s32 = gconv_grid(N, OH, OW, Cout, BN32).stat_slots;
+  if (s32 > slots) slots = s32;
+  if (Cout == 32 || Cout == 64) {
+    const int sn = nconv_stat_slots(N, OH, OW);
+    if (sn > slots) slots = sn;
+  }
+  return slots;
 }
 
 // Developer instrumentation: B200UNET_GCONV_DEBUG=1 makes every launch synchronise and print per-role wait cycles.
@@ -587,6 +593,7 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
 #define GC(bk, bn, as, bs, r) \
   if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
   GC(64, 256, 3, 4, false)
+  GC(64, 192, 4, 4, false)
   GC(64, 128, 4, 4, false)
   GC(64, 64, 6, 4, false)
   GC(64, 64, 4, 1, true)

@@ -14,8 +14,11 @@
 //     shuffle; lanes 0 and 31 are halo: a tile produces 4 x 30 outputs and tiles step by 30 columns (94 % of M);
 //   * the weights need no second packing: a 4-D tensor map over the packed [Cout][3][3][Cin] matrix delivers the
 //     [(co, kw) x BK] tile of one kh directly; the whole slab stays resident in shared memory.
-// Persistent CTAs, 4 TMA producer warps, one lean MMA-issuing thread, two TMEM accumulator buffers, epilogue warps
-// that also produce the InstanceNorm partial sums (see conv_fprop_dgrad.cu for the shared conventions).
+// Persistent CTAs (384 threads): warps 0..1 = TMA producers, warp 2 = TMEM owner + lean MMA-issuing thread, warps
+// 4..7 and 8..11 = TWO epilogue groups.  The epilogue (tcgen05.ld, 2 shuffles per channel, pack, staging, statistics)
+// is ~800 instructions per tile and warp with one warp per scheduler, i.e. several times the 6..12 MMAs of a tile
+// (ncu: tensor pipe 12 % busy with a single group), so consecutive tiles alternate between the groups: group g owns
+// TMEM accumulator buffer g, staging buffer g and its own named barriers / bulk-store groups.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "conv_common.cuh"
@@ -24,12 +27,12 @@ namespace b200 {
 
 constexpr int kNcTH = 4, kNcTW = 32, kNcValidW = 30;  // tile rows / columns (lanes) / valid output columns
 constexpr int kNcPatchRows = kNcTH + 2;
+constexpr int kNcProducers = 2, kNcMmaWarp = 2, kNcEpiWarp0 = 4, kNcThreads = 32 * 12;
 
 struct NConvParams {
   int N, H, W, tiles_w, tiles_h;
   int cin;   // K-side channels (multiple of BK)
-  int rev;   // 0 fprop: window kh pairs with weight row kh, E_kw at column 3*co + kw; 1 dgrad: both reversed
-  int tiles_per_cta;
+    int tiles_per_cta;
   int stat_slots;
   float* stats;
 };
@@ -54,12 +57,14 @@ struct NConvCfg {
   static constexpr uint32_t kSbo = 8 * kRowBytes;
   static constexpr uint32_t kTmemCols = (2 * kNeff <= 256) ? 256 : 512;
   static_assert(kBTileBytes % 1024 == 0, "weight tiles must keep the swizzle alignment");
-  static_assert(A_SLOTS % kProducerWarps == 0, "each producer owns a fixed subset of slots");
+  static_assert(A_SLOTS % kNcProducers == 0, "each producer owns a fixed subset of slots");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BK, int CO, int A_SLOTS>
-__global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
+// REV = false (fprop): patch window kh pairs with weight row kh, column tap kw of channel co at accumulator column
+// 3*co + kw.  REV = true (dgrad): both reversed (window kh pairs with weight row 2 - kh, the taps swap sides).
+template <int BK, int CO, int A_SLOTS, bool REV>
+__global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
                                                                  const __grid_constant__ NConvParams p) {
   using Cfg = NConvCfg<BK, CO, A_SLOTS>;
   extern __shared__ uint8_t smem_raw[];
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kNcMmaWarp) {
     tmem_alloc(&tmem_base_holder, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp < kProducerWarps) {
+  if (warp < kNcProducers) {
     if (elect_one()) {
       if (warp == 0) {
         // resident weights: tile (c, kh) = [(n, kw) x BK] of weight row kh and K chunk c
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
         const int th = t_in / p.tiles_w;
         const int h0 = th * kNcTH, w0 = (t_in - th * p.tiles_w) * kNcValidW;
         const long long g0 = static_cast<long long>(it) * chunks;
-        int c = (warp - static_cast<int>(g0 % kProducerWarps) + kProducerWarps) % kProducerWarps;
-        for (; c < chunks; c += kProducerWarps) {
+        int c = (warp - static_cast<int>(g0 % kNcProducers) + kNcProducers) % kNcProducers;
+        for (; c < chunks; c += kNcProducers) {
           const long long g = g0 + c;
           const int slot = static_cast<int>(g % A_SLOTS);
           const uint32_t ph = static_cast<uint32_t>((g / A_SLOTS) & 1);
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kNcMmaWarp) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, Cfg::kNeff, 0, 0);
       constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             // window kh of the patch pairs with weight row kh (fprop) or 2 - kh (dgrad)
-            const uint32_t b_lo = b_c + (p.rev ? (2 - kh) : kh) * kBTile16;
+            const uint32_t b_lo = b_c + (REV ? (2 - kh) : kh) * kBTile16;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               umma_bf16_lean(d_tmem, a_lo + kh * Cfg::kWin16 + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
@@ -169,19 +174,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
         umma_commit(&tmem_full_bar[buf]);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 5..8): warp q = tile row q
+  } else if (warp >= kNcEpiWarp0) {
+    // ------------------------------------------------ epilogue group g (warps 4..7 / 8..11): tiles it = g, g+2, ...;
+    // warp q of the group = TMEM lane quarter q = tile row q
+    const int g = (warp - kNcEpiWarp0) >> 2;
     const int q = warp & 3;
-    const int et = threadIdx.x - 32 * kEpiWarp0;
+    const int et = threadIdx.x - 32 * (kNcEpiWarp0 + 4 * g);  // 0..127 inside the group
+    const int bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
     const bool do_stats = p.stats != nullptr;
     const bool col_ok = lane >= 1 && lane <= kNcValidW;
     const int srow = q * kNcValidW + lane - 1;  // staging row of this thread's output pixel
+    uint8_t* stg = staging + g * Cfg::kStageBufBytes;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * Cfg::kNeff;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};       // [s1 c0, s2 c0, s1 c1, s2 c1] of this lane's channel pair
     int acc_img = -1;
     auto flush = [&](int img) {
       const int first_tile = img * tiles_per_img;
       const int b0 = first_tile / p.tiles_per_cta;
-      const int slot = (static_cast<int>(blockIdx.x) - b0) * 4 + q;
+      const int slot = ((static_cast<int>(blockIdx.x) - b0) * 2 + g) * 4 + q;
       float* dst = p.stats + (static_cast<size_t>(img) * p.stat_slots + slot) * CO * 2;
       if (CO == 64) {
         *reinterpret_cast<float4*>(dst + (2 * lane) * 2) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -194,24 +204,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
       }
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     };
-    int it = 0;
-    uint32_t sbuf = 0;
-    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it, sbuf ^= 1) {
-      const int n_img = tile / tiles_per_img;
-      const int t_in = tile - n_img * tiles_per_img;
-      const int th = t_in / p.tiles_w;
-      const int h0 = th * kNcTH, w0 = (t_in - th * p.tiles_w) * kNcValidW;
+    // tile coordinates advance incrementally (two tiles per step): no divisions in the loop
+    int tile = tile_lo + g;
+    int n_img = tile / tiles_per_img;
+    int th = (tile - n_img * tiles_per_img) / p.tiles_w;
+    int tw = tile - n_img * tiles_per_img - th * p.tiles_w;
+    uint32_t ph = 0;  // parity of this group's accumulator barrier
+    for (; tile < tile_hi; tile += 2, ph ^= 1) {
+      const int h0 = th * kNcTH, w0 = tw * kNcValidW;
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
       }
-      const int buf = it & 1;
-      mbar_wait(&tmem_full_bar[buf], static_cast<uint32_t>((it >> 1) & 1));
+      mbar_wait(&tmem_full_bar[g], ph);
       tc_fence_after();
-      if (et == 0) tma_store_wait_read_1();  // the store issued two tiles ago read this staging buffer
-      named_bar_sync(1, 128);
-      uint8_t* stg = staging + sbuf * Cfg::kStageBufBytes;
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kNeff;
+      if (et == 0) tma_store_wait_read_all();  // this group's previous store has read the staging buffer
+      named_bar_sync(bar_a, 128);
 #pragma unroll 1
       for (int c0 = 0; c0 < CO; c0 += 32) {
         // 32 output channels = 96 accumulator columns (co, kw) starting at 3 * c0
@@ -220,6 +228,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
         tmem_ld_32x32(t_addr + 3 * c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_32x32(t_addr + 3 * c0 + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
         tmem_ld_wait();
+        if (c0 + 32 >= CO) {
+          // all TMEM reads of this warp are done: hand the accumulator back before the arithmetic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -227,9 +241,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = 2 * j + e;
-            // left neighbour's column tap (kw = 0 in fprop order) and right neighbour's (kw = 2)
-            const float from_left = __shfl_up_sync(0xffffffffu, __uint_as_float(p.rev ? v[3 * c + 2] : v[3 * c]), 1);
-            const float from_right = __shfl_down_sync(0xffffffffu, __uint_as_float(p.rev ? v[3 * c] : v[3 * c + 2]), 1);
+            // the left neighbour's tap for this pixel is its kw = 0 column (fprop order), the right neighbour's kw = 2
+            const float from_left = __shfl_up_sync(0xffffffffu, __uint_as_float(REV ? v[3 * c + 2] : v[3 * c]), 1);
+            const float from_right = __shfl_down_sync(0xffffffffu, __uint_as_float(REV ? v[3 * c] : v[3 * c + 2]), 1);
             o[e] = __uint_as_float(v[3 * c + 1]) + from_left + from_right;
           }
           pk[j] = pack_bf16x2(o[0], o[1]);
@@ -257,11 +271,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       fence_proxy_async_smem();
-      named_bar_sync(2, 128);
+      named_bar_sync(bar_b, 128);
       if (et == 0) {
         tma_store_4d(&maps.out, stg, 0, w0, h0, n_img);
         tma_store_commit();
@@ -301,6 +312,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
         acc[2] += s1b;
         acc[3] += s2b;
       }
+      // next tile of this group
+      tw += 2;
+      while (tw >= p.tiles_w) {
+        tw -= p.tiles_w;
+        if (++th == p.tiles_h) {
+          th = 0;
+          ++n_img;
+        }
+      }
     }
     if (do_stats && acc_img >= 0) flush(acc_img);
     if (et == 0) tma_store_wait_all();
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) nconv_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kNcMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -328,7 +348,7 @@ static NConvGrid nconv_grid(int N, int H, int W) {
   g.tiles_per_cta = static_cast<int>(ceil_div64(total, num_sms()));
   if (g.tiles_per_cta < 1) g.tiles_per_cta = 1;
   g.grid = static_cast<int>(ceil_div64(total, g.tiles_per_cta));
-  g.stat_slots = 4 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);
+  g.stat_slots = 8 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);  // (CTA, group, lane quarter)
   return g;
 }
 
@@ -341,11 +361,11 @@ bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
 
 int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
 
-template <int BK, int CO, int A_SLOTS>
+template <int BK, int CO, int A_SLOTS, bool REV>
 static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& g, cudaStream_t st) {
   // p.stat_slots = P of the caller's buffer (>= this kernel's own slot count); unused slots stay zero
   using Cfg = NConvCfg<BK, CO, A_SLOTS>;
-  auto kern = nconv_kernel<BK, CO, A_SLOTS>;
+  auto kern = nconv_kernel<BK, CO, A_SLOTS, REV>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -353,7 +373,7 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
   }
   if (p.stats)
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
-  kern<<<g.grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  kern<<<g.grid, kNcThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("nconv_kernel");
   return 0;
 }
@@ -372,7 +392,6 @@ int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* ou
   p.tiles_w = g.tiles_w;
   p.tiles_h = g.tiles_h;
   p.cin = k_channels;
-  p.rev = rev;
   p.tiles_per_cta = g.tiles_per_cta;
   p.stat_slots = stat_slots > g.stat_slots ? stat_slots : g.stat_slots;
   p.stats = stats;
@@ -393,10 +412,12 @@ int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* ou
                              BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
   }
-  if (BK == 64 && n_channels == 64) return launch_nconv<64, 64, 4>(maps, p, g, st);
-  if (BK == 64 && n_channels == 32) return launch_nconv<64, 32, 4>(maps, p, g, st);
-  if (BK == 32 && n_channels == 64) return launch_nconv<32, 64, 8>(maps, p, g, st);
-  return launch_nconv<32, 32, 8>(maps, p, g, st);
+#define NC(bk, co, as) \
+  if (BK == bk && n_channels == co) \
+    return rev ? launch_nconv<bk, co, as, true>(maps, p, g, st) : launch_nconv<bk, co, as, false>(maps, p, g, st);
+  NC(64, 64, 4) NC(64, 32, 4) NC(32, 64, 8) NC(32, 32, 8)
+#undef NC
+  return set_error(kErrUnsupported, "no nconv instantiation for BK=%d N=%d", BK, n_channels);
 }
 
 }  // namespace b200

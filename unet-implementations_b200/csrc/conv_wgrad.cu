@@ -250,7 +250,9 @@ static int plan_wgrad(int N, int H, int W, int Cin, int Cout, int stride, WgradP
   pl->gy = ceil_div(groups_total, G);
   pl->gz = Cout / pl->BN;
   const int base_ctas = pl->gy * pl->gz;
-  int S = ceil_div(num_sms(), base_ctas);
+  // split K so that the whole grid is ONE wave (<= one CTA per SM): rounding the split count up instead
+  // (ceil(148 / base)) left a second, almost empty wave on nearly every layer of the model (e.g. 27 x 6 = 162 CTAs)
+  int S = num_sms() / base_ctas;
   if (S > pl->total_kb) S = pl->total_kb;
   if (S < 1) S = 1;
   pl->kb_per_split = ceil_div(pl->total_kb, S);
