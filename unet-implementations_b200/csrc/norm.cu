@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const __nv_bfloa
                                                                  const float* __restrict__ b, float slope,
                                                                  __nv_bfloat16* __restrict__ z, int64_t zp, int64_t HW,
                                                                  int C, int c8n, int lanes, int64_t chunk) {
-  const int n = blockIdx.y;
+  // images in REVERSE launch order: the producing conv wrote image N-1 last, so the first blocks find their input in
+  // L2; this kernel then leaves image 0 in L2 for the next conv, which starts there
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int c0 = (threadIdx.x % c8n) << 3;
   const int lane = threadIdx.x / c8n;
   float ra[8], rb[8];
@@ -184,7 +186,9 @@ struct InBwdK {
 // T1 = sum dz*m, T2 = sum dz*m*(y - mean) over the block's pixels, m = lrelu'(a*y+b).   grid (P, images)
 __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, float* __restrict__ part, int P) {
   extern __shared__ float red[];  // [lanes][c8n][16]
-  const int n = K.n0 + blockIdx.y;
+  // reverse image order (the producer of dz wrote the last image last: L2 hits); the apply pass then runs forward
+  // and finds the images this pass read last still in L2
+  const int n = K.n0 + (gridDim.y - 1 - blockIdx.y);
   const int c8 = threadIdx.x % K.c8n;
   const int c0 = c8 << 3;
   const int lane = threadIdx.x / K.c8n;
@@ -311,21 +315,26 @@ __global__ void in_bwd_param_kernel(const float* __restrict__ imgsum, float* __r
 }
 
 // grid (blocks_per_image, images)
-__global__ void __launch_bounds__(kNormThreads) in_bwd_apply_kernel(InBwdK K, const float* __restrict__ coef,
-                                                                     __nv_bfloat16* __restrict__ dy, int64_t dyp) {
+__global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK K, const float* __restrict__ coef,
+                                                                        __nv_bfloat16* __restrict__ dy, int64_t dyp) {
   const int n = K.n0 + blockIdx.y;
   const int c0 = (threadIdx.x % K.c8n) << 3;
   const int lane = threadIdx.x / K.c8n;
-  float ra[8], rb[8], rm[8], k1[8], k2[8], k3[8];
+  // dy = k1*gm - k2*(y - mean) - k3 = k1*gm - k2*y + k3',  k3' = k2*mean - k3: 40 parameter registers per thread, so
+  // that two 256-thread blocks fit an SM (the first version held 56 + 48 in-flight and ran at 12 % occupancy)
+  float ra[8], rb[8], k1[8], k2[8], k3[8];
   ld8f(K.a + n * K.C + c0, ra);
   ld8f(K.b + n * K.C + c0, rb);
-  ld8f(K.mean + n * K.C + c0, rm);
+  {
+    float rm[8];
+    ld8f(K.mean + n * K.C + c0, rm);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 k = reinterpret_cast<const float4*>(coef)[n * K.C + c0 + j];
-    k1[j] = k.x;
-    k2[j] = k.y;
-    k3[j] = k.z;
+    for (int j = 0; j < 8; ++j) {
+      const float4 k = reinterpret_cast<const float4*>(coef)[n * K.C + c0 + j];
+      k1[j] = k.x;
+      k2[j] = k.y;
+      k3[j] = fmaf(k.y, rm[j], -k.z);
+    }
   }
   const int64_t lo = blockIdx.x * K.chunk;
   int64_t hi = lo + K.chunk;
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_apply_kernel(InBwdK K, co
       for (int j = 0; j < 8; ++j) {
         const float pre = fmaf(ra[j], yv[j], rb[j]);
         const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
-        o[j] = fmaf(k1[j], gm, -fmaf(k2[j], yv[j] - rm[j], k3[j]));
+        o[j] = fmaf(k1[j], gm, fmaf(-k2[j], yv[j], k3[j]));
       }
       *reinterpret_cast<uint4*>(ob + (px + u * lanes) * dyp) = pack8(o);
     }
