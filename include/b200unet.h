@@ -186,6 +186,32 @@ int b200unet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int64_t dst_pitc
 int b200unet_nhwc_bf16_to_nchw_f32(const void* src, int64_t src_pitch, float* dst, int N, int C, int64_t HW,
                                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 verification mode (`UNet(...).precision = "fp32"`): the same operators with fp32 NHWC activations, fp32
+ * packed weights and fp32 arithmetic -- north_star's "1e-4 in fp32 mode".  Argument structs, layouts and
+ * semantics are those of the bf16 entry points above with every `bf16` read as `fp32`; the norm / resample /
+ * head kernels are the SAME templates instantiated for fp32 storage, the convolutions are the direct CUDA-core
+ * kernels (the tensor-core path is bf16-only).  Not a fallback: selected explicitly by the caller, CUDA only.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_pack_conv_weights_f32(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin, void* stream);
+int b200unet_conv_fprop_f32(const b200unet_conv_fprop_args* a, void* stream); /* stats: P = b200unet_conv_fprop_simt_partials */
+int b200unet_conv_dgrad_f32(const b200unet_conv_dgrad_args* a, void* stream);
+int b200unet_conv_wgrad_f32(const b200unet_conv_wgrad_args* a, void* stream); /* no workspace needed */
+int b200unet_in_apply_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
+                          int64_t z_pitch, int N, int64_t HW, int C, void* stream);
+int b200unet_in_backward_f32(const b200unet_in_bwd_args* a, void* stream);
+int b200unet_upsample2x_fwd_f32(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H, int W,
+                                int C, void* stream);
+int b200unet_upsample2x_bwd_f32(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H,
+                                int W, int C, void* stream);
+int b200unet_head_fwd_f32(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw,
+                          int N, int64_t HW, int C, int K, void* stream);
+int b200unet_head_bwd_f32(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
+                          int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
+                          int64_t HW, int C, int K, void* stream);
+int b200unet_nchw_f32_to_nhwc_f32(const float* src, void* dst, int64_t dst_pitch, int N, int C, int64_t HW,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

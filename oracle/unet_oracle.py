@@ -237,17 +237,27 @@ def synthetic_batch(batch: int, size: int = 512, seed: int = 0, variant: str = "
 
 def training_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, target: torch.Tensor, cfg: UNetConfig = UNetConfig(),
                   masks: Optional[List[torch.Tensor]] = None, training: bool = True, loss_kwargs: Optional[dict] = None,
-                  bf16_storage: bool = False):
+                  bf16_storage: bool = False, dtype: torch.dtype = torch.float32):
     """One reference training step on CPU fp32 (train.py:654-663: forward, SimpleLoss, backward) through the
     restatement above, differentiated by torch autograd.  Returns dict(logits, loss, ce, dice, grads).
     `bf16_storage=True` keeps the arithmetic but rounds to bf16 exactly where the CUDA path stores bf16 (conv
     operands, raw conv outputs, activations, upsampled tensors and their gradients): the matched-precision oracle
-    that separates kernel error from the cost of bf16 storage.  The default is the reference's fp32."""
+    that separates kernel error from the cost of bf16 storage.  The default is the reference's fp32.
+    `dtype=torch.float64` runs the same ops in double: the "exact" answer that tells how much of a difference between
+    two fp32 runs is the conditioning of the problem (at random init this network amplifies rounding noise ~1e5 x:
+    the reference's own fp32 gradients sit up to 1e-2 from the fp64 ones, tests/test_gpu_fp32_mode.py)."""
     leaves = {}
     for k, v in sd.items():
-        leaves[k] = v.detach().clone().float().requires_grad_(True)
-    logits = unet_forward(leaves, x.float(), cfg, masks, training, bf16_storage)
-    total, ce, dice = simple_loss(logits, target, parts=True, **(loss_kwargs or {}))
+        leaves[k] = v.detach().clone().to(dtype).requires_grad_(True)
+    if masks is not None:
+        masks = [m.to(dtype) for m in masks]
+    logits = unet_forward(leaves, x.to(dtype), cfg, masks, training, bf16_storage)
+    kw = dict(loss_kwargs or {})
+    if dtype != torch.float32 and kw.get("dynamic", True) and kw.get("weights") is None:
+        # the reference computes the class weights in fp32 from integer counts (losses.py:44-60); keep that and only
+        # lift them to the working precision
+        kw.update(weights=class_weights(target, kw.get("ignore_index", 255)).to(dtype), dynamic=False)
+    total, ce, dice = simple_loss(logits, target, parts=True, **kw)
     total.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     return dict(logits=logits.detach(), loss=total.detach(), ce=ce.detach(), dice=dice.detach(), grads=grads)

@@ -83,6 +83,18 @@ SIGNATURES = {
     "b200unet_loss_bwd": (c_int, [_P, _P, _P, _P, _F, _F, _I, _P, _I, _L, _P]),
     "b200unet_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
     "b200unet_nhwc_bf16_to_nchw_f32": (c_int, [_P, _L, _P, _I, _I, _L, _P]),
+    # fp32 verification mode: same signatures as the bf16 entry points
+    "b200unet_pack_conv_weights_f32": (c_int, [_P, _P, _P, _I, _I, _P]),
+    "b200unet_conv_fprop_f32": (c_int, [POINTER(ConvFpropArgs), _P]),
+    "b200unet_conv_dgrad_f32": (c_int, [POINTER(ConvDgradArgs), _P]),
+    "b200unet_conv_wgrad_f32": (c_int, [POINTER(ConvWgradArgs), _P]),
+    "b200unet_in_apply_f32": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
+    "b200unet_in_backward_f32": (c_int, [POINTER(InBwdArgs), _P]),
+    "b200unet_upsample2x_fwd_f32": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_upsample2x_bwd_f32": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_head_fwd_f32": (c_int, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
+    "b200unet_head_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
+    "b200unet_nchw_f32_to_nhwc_f32": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
 }
 
 # entry points that return a value rather than a status code

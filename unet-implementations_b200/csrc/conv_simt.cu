@@ -4,12 +4,14 @@
 // Reference call sites: nn.Conv2d in ConvBlock, Our_UNet/models/unet.py:106-115.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "vec8.cuh"
 
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------ weight packing
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin) {
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout,
+                                    int Cin) {
   const int64_t total = static_cast<int64_t>(Cout) * Cin * 9;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -19,35 +21,37 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   const int tap = static_cast<int>(r % 9);
   const int co = static_cast<int>(r / 9);
   const float v = w[(static_cast<int64_t>(co) * Cin + ci) * 9 + tap];
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  const T b = from_f32<T>(v);
   wf[i] = b;
   if (wd) wd[(static_cast<int64_t>(ci) * 9 + tap) * Cout + co] = b;
 }
 
 // ------------------------------------------------------------------------------------------ generic stats
 // partial (sum, sumsq) of a bf16 NHWC tensor: block (p, n) covers pixels [p*chunk, (p+1)*chunk) of image n
-__global__ void stats_partial_kernel(const __nv_bfloat16* __restrict__ y, int64_t pitch, float* __restrict__ stats,
+template <typename T>
+__global__ void stats_partial_kernel(const T* __restrict__ y, int64_t pitch, float* __restrict__ stats,
                                      int P, int64_t HW, int C, int64_t chunk) {
   const int p = blockIdx.x, n = blockIdx.y;
   const int64_t lo = p * chunk;
   int64_t hi = lo + chunk;
   if (hi > HW) hi = HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
+    typename AccT<T>::type s1 = 0, s2 = 0;
     for (int64_t px = lo; px < hi; ++px) {
-      const float v = __bfloat162float(y[(n * HW + px) * pitch + c]);
+      const typename AccT<T>::type v = to_f32(y[(n * HW + px) * pitch + c]);
       s1 += v;
       s2 += v * v;
     }
     float* d = stats + ((static_cast<int64_t>(n) * P + p) * C + c) * 2;
-    d[0] = s1;
-    d[1] = s2;
+    d[0] = static_cast<float>(s1);
+    d[1] = static_cast<float>(s2);
   }
 }
 
 // ------------------------------------------------------------------------------------------ direct convs
-__global__ void conv_fprop_simt_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
-                                       const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, int64_t yp,
+template <typename T>
+__global__ void conv_fprop_simt_kernel(const T* __restrict__ x, int64_t xp, const T* __restrict__ w,
+                                       T* __restrict__ y, int64_t yp,
                                        int N, int H, int W, int Cin, int Cout, int s, int OH, int OW) {
   const int64_t total = static_cast<int64_t>(N) * OH * OW * Cout;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -58,24 +62,26 @@ __global__ void conv_fprop_simt_kernel(const __nv_bfloat16* __restrict__ x, int6
   r /= OW;
   const int oh = static_cast<int>(r % OH);
   const int n = static_cast<int>(r / OH);
-  float acc = 0.f;
+  using Acc = typename AccT<T>::type;
+  Acc acc = 0;
   for (int kh = 0; kh < 3; ++kh) {
     const int ih = oh * s + kh - 1;
     if (ih < 0 || ih >= H) continue;
     for (int kw = 0; kw < 3; ++kw) {
       const int iw = ow * s + kw - 1;
       if (iw < 0 || iw >= W) continue;
-      const __nv_bfloat16* xr = x + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp;
-      const __nv_bfloat16* wr = w + (static_cast<int64_t>(co) * 9 + kh * 3 + kw) * Cin;
-      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(__bfloat162float(xr[ci]), __bfloat162float(wr[ci]), acc);
+      const T* xr = x + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp;
+      const T* wr = w + (static_cast<int64_t>(co) * 9 + kh * 3 + kw) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc += static_cast<Acc>(to_f32(xr[ci])) * static_cast<Acc>(to_f32(wr[ci]));
     }
   }
-  y[((static_cast<int64_t>(n) * OH + oh) * OW + ow) * yp + co] = __float2bfloat16_rn(acc);
+  y[((static_cast<int64_t>(n) * OH + oh) * OW + ow) * yp + co] = from_f32<T>(static_cast<float>(acc));
 }
 
-__global__ void conv_dgrad_simt_kernel(const __nv_bfloat16* __restrict__ dy, int64_t dyp,
-                                       const __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ dx,
-                                       int64_t dxp, int N, int H, int W, int Cin, int Cout, int s, int OH, int OW) {
+template <typename T>
+__global__ void conv_dgrad_simt_kernel(const T* __restrict__ dy, int64_t dyp, const T* __restrict__ wt,
+                                       T* __restrict__ dx, int64_t dxp, int N, int H, int W, int Cin, int Cout, int s,
+                                       int OH, int OW) {
   const int64_t total = static_cast<int64_t>(N) * H * W * Cin;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -85,7 +91,8 @@ __global__ void conv_dgrad_simt_kernel(const __nv_bfloat16* __restrict__ dy, int
   r /= W;
   const int ih = static_cast<int>(r % H);
   const int n = static_cast<int>(r / H);
-  float acc = 0.f;
+  using Acc = typename AccT<T>::type;
+  Acc acc = 0;
   for (int kh = 0; kh < 3; ++kh) {
     const int th = ih + 1 - kh;
     if (th < 0 || th % s != 0) continue;
@@ -96,17 +103,18 @@ __global__ void conv_dgrad_simt_kernel(const __nv_bfloat16* __restrict__ dy, int
       if (tw < 0 || tw % s != 0) continue;
       const int ow = tw / s;
       if (ow >= OW) continue;
-      const __nv_bfloat16* dr = dy + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * dyp;
-      const __nv_bfloat16* wr = wt + (static_cast<int64_t>(ci) * 9 + kh * 3 + kw) * Cout;
-      for (int co = 0; co < Cout; ++co) acc = fmaf(__bfloat162float(dr[co]), __bfloat162float(wr[co]), acc);
+      const T* dr = dy + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * dyp;
+      const T* wr = wt + (static_cast<int64_t>(ci) * 9 + kh * 3 + kw) * Cout;
+      for (int co = 0; co < Cout; ++co) acc += static_cast<Acc>(to_f32(dr[co])) * static_cast<Acc>(to_f32(wr[co]));
     }
   }
-  dx[((static_cast<int64_t>(n) * H + ih) * W + iw) * dxp + ci] = __float2bfloat16_rn(acc);
+  dx[((static_cast<int64_t>(n) * H + ih) * W + iw) * dxp + ci] = from_f32<T>(static_cast<float>(acc));
 }
 
-__global__ void conv_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
-                                       const __nv_bfloat16* __restrict__ dy, int64_t dyp, float* __restrict__ dw, int N,
-                                       int H, int W, int Cin, int Cout, int s, int OH, int OW) {
+template <typename T>
+__global__ void conv_wgrad_simt_kernel(const T* __restrict__ x, int64_t xp, const T* __restrict__ dy, int64_t dyp,
+                                       float* __restrict__ dw, int N, int H, int W, int Cin, int Cout, int s, int OH,
+                                       int OW) {
   // one warp per (co, ci, tap); lanes stride over pixels, shuffle-reduce
   const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,7 +125,8 @@ __global__ void conv_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, int6
   const int ci = static_cast<int>(r % Cin);
   const int co = static_cast<int>(r / Cin);
   const int kh = tap / 3, kw = tap % 3;
-  float acc = 0.f;
+  using Acc = typename AccT<T>::type;
+  Acc acc = 0;
   const int64_t npx = static_cast<int64_t>(N) * OH * OW;
   for (int64_t px = lane; px < npx; px += 32) {
     const int ow = static_cast<int>(px % OW);
@@ -126,12 +135,12 @@ __global__ void conv_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, int6
     const int n = static_cast<int>(q / OH);
     const int ih = oh * s + kh - 1, iw = ow * s + kw - 1;
     if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-    acc = fmaf(__bfloat162float(dy[px * dyp + co]),
-               __bfloat162float(x[((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + ci]), acc);
+    acc += static_cast<Acc>(to_f32(dy[px * dyp + co])) *
+           static_cast<Acc>(to_f32(x[((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + ci]));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) dw[gw] = acc;  // gw == (co*Cin + ci)*9 + tap, the OIHW offset
+  if (lane == 0) dw[gw] = static_cast<float>(acc);  // gw == (co*Cin + ci)*9 + tap, the OIHW offset
 }
 
 // ------------------------------------------------------------------------------------------ stem (Cin=3 -> 32)
@@ -329,14 +338,22 @@ static int stem_wgrad_blocks() { return num_sms() * 4; }
 
 using namespace b200;
 
-extern "C" int b200unet_pack_conv_weights(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin,
-                                          void* stream) {
+template <typename T>
+static int pack_weights_impl(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin, void* stream) {
   B200_CHECK_ARG(w_oihw && w_fprop, "pack_conv_weights: null pointer");
   const int64_t total = static_cast<int64_t>(Cout) * Cin * 9;
-  pack_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), Cout, Cin);
+  pack_weights_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, static_cast<T*>(w_fprop), static_cast<T*>(w_dgrad), Cout, Cin);
   B200_LAUNCH_CHECK("pack_weights_kernel");
   return 0;
+}
+extern "C" int b200unet_pack_conv_weights(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin,
+                                          void* stream) {
+  return pack_weights_impl<__nv_bfloat16>(w_oihw, w_fprop, w_dgrad, Cout, Cin, stream);
+}
+extern "C" int b200unet_pack_conv_weights_f32(const float* w_oihw, void* w_fprop, void* w_dgrad, int Cout, int Cin,
+                                              void* stream) {
+  return pack_weights_impl<float>(w_oihw, w_fprop, w_dgrad, Cout, Cin, stream);
 }
 
 extern "C" int b200unet_conv_fprop_simt_partials(int OH, int OW) {
@@ -344,48 +361,69 @@ extern "C" int b200unet_conv_fprop_simt_partials(int OH, int OW) {
   return static_cast<int>(p < 1 ? 1 : (p > 64 ? 64 : p));
 }
 
-extern "C" int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream) {
+template <typename T>
+static int conv_fprop_simt_impl(const b200unet_conv_fprop_args* a, void* stream) {
   B200_CHECK_ARG(a && a->x && a->w && a->y, "conv_fprop_simt: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_fprop_simt: stride %d unsupported", a->stride);
   const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = static_cast<int64_t>(a->N) * OH * OW * a->Cout;
-  conv_fprop_simt_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, static_cast<const __nv_bfloat16*>(a->w),
-      static_cast<__nv_bfloat16*>(a->y), a->y_pitch, a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  conv_fprop_simt_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+      static_cast<const T*>(a->x), a->x_pitch, static_cast<const T*>(a->w), static_cast<T*>(a->y), a->y_pitch, a->N, a->H,
+      a->W, a->Cin, a->Cout, s, OH, OW);
   B200_LAUNCH_CHECK("conv_fprop_simt_kernel");
   if (a->stats) {
     const int P = b200unet_conv_fprop_simt_partials(OH, OW);
     const int64_t HW = static_cast<int64_t>(OH) * OW;
-    stats_partial_kernel<<<dim3(P, a->N), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->stats, P,
-                                                        HW, a->Cout, ceil_div64(HW, P));
+    stats_partial_kernel<T><<<dim3(P, a->N), 128, 0, st>>>(static_cast<const T*>(a->y), a->y_pitch, a->stats, P, HW,
+                                                           a->Cout, ceil_div64(HW, P));
     B200_LAUNCH_CHECK("stats_partial_kernel");
   }
   return 0;
 }
+extern "C" int b200unet_conv_fprop_simt(const b200unet_conv_fprop_args* a, void* stream) {
+  return conv_fprop_simt_impl<__nv_bfloat16>(a, stream);
+}
+extern "C" int b200unet_conv_fprop_f32(const b200unet_conv_fprop_args* a, void* stream) {
+  return conv_fprop_simt_impl<float>(a, stream);
+}
 
-extern "C" int b200unet_conv_dgrad_simt(const b200unet_conv_dgrad_args* a, void* stream) {
+template <typename T>
+static int conv_dgrad_simt_impl(const b200unet_conv_dgrad_args* a, void* stream) {
   B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad_simt: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_dgrad_simt: stride %d unsupported", a->stride);
   const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   const int64_t total = static_cast<int64_t>(a->N) * a->H * a->W * a->Cin;
-  conv_dgrad_simt_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, static_cast<const __nv_bfloat16*>(a->wt),
-      static_cast<__nv_bfloat16*>(a->dx), a->dx_pitch, a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  conv_dgrad_simt_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(a->dy), a->dy_pitch, static_cast<const T*>(a->wt), static_cast<T*>(a->dx), a->dx_pitch, a->N,
+      a->H, a->W, a->Cin, a->Cout, s, OH, OW);
   B200_LAUNCH_CHECK("conv_dgrad_simt_kernel");
   return 0;
 }
+extern "C" int b200unet_conv_dgrad_simt(const b200unet_conv_dgrad_args* a, void* stream) {
+  return conv_dgrad_simt_impl<__nv_bfloat16>(a, stream);
+}
+extern "C" int b200unet_conv_dgrad_f32(const b200unet_conv_dgrad_args* a, void* stream) {
+  return conv_dgrad_simt_impl<float>(a, stream);
+}
 
-extern "C" int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void* stream) {
+template <typename T>
+static int conv_wgrad_simt_impl(const b200unet_conv_wgrad_args* a, void* stream) {
   B200_CHECK_ARG(a && a->x && a->dy && a->dw, "conv_wgrad_simt: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_wgrad_simt: stride %d unsupported", a->stride);
   const int s = a->stride, OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   const int64_t warps = static_cast<int64_t>(a->Cout) * a->Cin * 9;
-  conv_wgrad_simt_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, a->dw,
-      a->N, a->H, a->W, a->Cin, a->Cout, s, OH, OW);
+  conv_wgrad_simt_kernel<T><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(a->x), a->x_pitch, static_cast<const T*>(a->dy), a->dy_pitch, a->dw, a->N, a->H, a->W, a->Cin,
+      a->Cout, s, OH, OW);
   B200_LAUNCH_CHECK("conv_wgrad_simt_kernel");
   return 0;
+}
+extern "C" int b200unet_conv_wgrad_simt(const b200unet_conv_wgrad_args* a, void* stream) {
+  return conv_wgrad_simt_impl<__nv_bfloat16>(a, stream);
+}
+extern "C" int b200unet_conv_wgrad_f32(const b200unet_conv_wgrad_args* a, void* stream) {
+  return conv_wgrad_simt_impl<float>(a, stream);
 }
 
 static int stem_blocks_w(int W) { return ceil_div(W, kStemThreads * kStemPx); }

@@ -9,6 +9,7 @@
 // host syncs at losses.py:53 become a device-side clamp).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "vec8.cuh"
 
 namespace b200 {
 
@@ -184,8 +185,8 @@ constexpr int kHeadMaxC = 64;
 constexpr int kHeadMaxK = 4;
 
 // one thread per pixel: logits[k] = b[k] + sum_c W[k][c] * z[c]
-template <int C, int K>
-__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ z, int64_t zp,
+template <typename T, int C, int K>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, int64_t zp,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ logits, int64_t HW) {
   __shared__ float ws[K][C];
@@ -196,33 +197,28 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
   const int n = blockIdx.y;
   const int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (px >= HW) return;
-  const uint4* src = reinterpret_cast<const uint4*>(z + (static_cast<int64_t>(n) * HW + px) * zp);
+  const T* src = z + (static_cast<int64_t>(n) * HW + px) * zp;
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = bs[k];
 #pragma unroll
   for (int j = 0; j < C / 8; ++j) {
-    const uint4 u = src[j];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float zf[8];
+    Vec8<T>::ldg(src + 8 * j).unpack(zf);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = __bfloat1622float2(h[i]);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        acc[k] = fmaf(ws[k][8 * j + 2 * i], t.x, acc[k]);
-        acc[k] = fmaf(ws[k][8 * j + 2 * i + 1], t.y, acc[k]);
-      }
-    }
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(ws[k][8 * j + i], zf[i], acc[k]);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) logits[(static_cast<int64_t>(n) * K + k) * HW + px] = acc[k];
 }
 
 // grid-stride over pixels; thread accumulates dW[K][C] and db[K] privately, block-reduces, writes one partial row.
-template <int C, int K>
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ z,
+template <typename T, int C, int K>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ z,
                                                         int64_t zp, const float* __restrict__ w,
-                                                        __nv_bfloat16* __restrict__ dz, int64_t dzp,
+                                                        T* __restrict__ dz, int64_t dzp,
                                                         float* __restrict__ partial, int N, int64_t HW) {
   __shared__ float ws[K][C];
   __shared__ float red[8][K * C + K];
@@ -247,19 +243,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       d[k] = dl[(static_cast<int64_t>(n) * K + k) * HW + px];
       ab[k] += d[k];
     }
-    const uint4* src = reinterpret_cast<const uint4*>(z + g * zp);
-    uint4* dst = reinterpret_cast<uint4*>(dz + g * dzp);
+    const T* src = z + g * zp;
+    T* dst = dz + g * dzp;
 #pragma unroll
     for (int j = 0; j < C / 8; ++j) {
-      const uint4 u = src[j];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
       float zf[8], o[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 t = __bfloat1622float2(h[i]);
-        zf[2 * i] = t.x;
-        zf[2 * i + 1] = t.y;
-      }
+      Vec8<T>::ldg(src + 8 * j).unpack(zf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float s = 0.f;
@@ -270,8 +259,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         }
         o[i] = s;
       }
-      dst[j] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                          pack_bf16x2(o[6], o[7]));
+      Vec8<T>::st(dst + 8 * j, o);
     }
   }
   // block reduction: shuffle tree per value, then across the 8 warps in order
@@ -350,16 +338,25 @@ extern "C" int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target
   return 0;
 }
 
-extern "C" int b200unet_head_fwd(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw,
-                                 int N, int64_t HW, int C, int K, void* stream) {
+template <typename T>
+static int head_fwd_impl(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw, int N,
+                         int64_t HW, int C, int K, void* stream) {
   B200_CHECK_ARG(z && w && bias && logits_nchw, "head_fwd: null pointer");
   B200_CHECK_ARG(z_pitch % 8 == 0, "head_fwd: pitch must be a multiple of 8");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_fwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
   dim3 grid((unsigned)ceil_div64(HW, 256), N);
-  head_fwd_kernel<32, 3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(z), z_pitch, w, bias, logits_nchw, HW);
+  head_fwd_kernel<T, 32, 3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(z), z_pitch, w,
+                                                                                  bias, logits_nchw, HW);
   B200_LAUNCH_CHECK("head_fwd_kernel");
   return 0;
+}
+extern "C" int b200unet_head_fwd(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw,
+                                 int N, int64_t HW, int C, int K, void* stream) {
+  return head_fwd_impl<__nv_bfloat16>(z, z_pitch, w, bias, logits_nchw, N, HW, C, K, stream);
+}
+extern "C" int b200unet_head_fwd_f32(const void* z, int64_t z_pitch, const float* w, const float* bias,
+                                     float* logits_nchw, int N, int64_t HW, int C, int K, void* stream) {
+  return head_fwd_impl<float>(z, z_pitch, w, bias, logits_nchw, N, HW, C, K, stream);
 }
 
 extern "C" int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K) {
@@ -367,19 +364,33 @@ extern "C" int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K) 
   return static_cast<int64_t>(head_bwd_blocks()) * (K * C + K) * 4;
 }
 
-extern "C" int b200unet_head_bwd(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
-                                 int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes,
-                                 int N, int64_t HW, int C, int K, void* stream) {
+template <typename T>
+static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
+                         int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
+                         int64_t HW, int C, int K, void* stream) {
   B200_CHECK_ARG(dlogits_nchw && z && w && dz && dw && db && workspace, "head_bwd: null pointer");
   B200_CHECK_ARG(z_pitch % 8 == 0 && dz_pitch % 8 == 0, "head_bwd: pitches must be multiples of 8");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_bwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
   const int blocks = head_bwd_blocks();
   B200_CHECK_ARG(workspace_bytes >= b200unet_head_bwd_workspace(N, HW, C, K), "head_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  head_bwd_kernel<32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const __nv_bfloat16*>(z), z_pitch, w,
-                                                 static_cast<__nv_bfloat16*>(dz), dz_pitch, workspace, N, HW);
+  head_bwd_kernel<T, 32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
+                                                    static_cast<T*>(dz), dz_pitch, workspace, N, HW);
   B200_LAUNCH_CHECK("head_bwd_kernel");
   head_bwd_finalize_kernel<<<1, 128, 0, st>>>(workspace, blocks, K * C, K, dw, db);
   B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
   return 0;
+}
+
+extern "C" int b200unet_head_bwd(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
+                                 int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes,
+                                 int N, int64_t HW, int C, int K, void* stream) {
+  return head_bwd_impl<__nv_bfloat16>(dlogits_nchw, z, z_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N,
+                                      HW, C, K, stream);
+}
+extern "C" int b200unet_head_bwd_f32(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w,
+                                     void* dz, int64_t dz_pitch, float* dw, float* db, float* workspace,
+                                     int64_t workspace_bytes, int N, int64_t HW, int C, int K, void* stream) {
+  return head_bwd_impl<float>(dlogits_nchw, z, z_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N, HW, C,
+                              K, stream);
 }

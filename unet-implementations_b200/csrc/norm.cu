@@ -9,33 +9,12 @@
 // in shared memory once per block.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "vec8.cuh"
 #include <stdlib.h>
 
 namespace b200 {
 
 constexpr int kNormThreads = 256;
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                    pack_bf16x2(f[6], f[7]));
-}
-__device__ __forceinline__ uint4 ld_stream(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-
 
 // ---------------------------------------------------------------------------------------------- thread mapping
 // A block owns a contiguous pixel range of one image.  Thread t owns the FIXED channel octet c0 = 8*(t % c8n) for
@@ -129,10 +108,11 @@ __global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restric
 }
 
 // grid (blocks_per_image, N)
-__global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const __nv_bfloat16* __restrict__ y, int64_t yp,
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const T* __restrict__ y, int64_t yp,
                                                                  const float* __restrict__ a,
                                                                  const float* __restrict__ b, float slope,
-                                                                 __nv_bfloat16* __restrict__ z, int64_t zp, int64_t HW,
+                                                                 T* __restrict__ z, int64_t zp, int64_t HW,
                                                                  int C, int c8n, int lanes, int64_t chunk) {
   // images in REVERSE launch order: the producing conv wrote image N-1 last, so the first blocks find their input in
   // L2; this kernel then leaves image 0 in L2 for the next conv, which starts there
@@ -145,35 +125,36 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const __nv_bfloa
   const int64_t lo = blockIdx.x * chunk;
   int64_t hi = lo + chunk;
   if (hi > HW) hi = HW;
-  const __nv_bfloat16* yb = y + static_cast<int64_t>(n) * HW * yp + c0;
-  __nv_bfloat16* zb = z + static_cast<int64_t>(n) * HW * zp + c0;
+  const T* yb = y + static_cast<int64_t>(n) * HW * yp + c0;
+  T* zb = z + static_cast<int64_t>(n) * HW * zp + c0;
   for (int64_t px = lo + lane; px < hi; px += 4 * lanes) {
-    uint4 v[4];
+    Vec8<T> v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (px + u * lanes < hi) v[u] = ld_stream(yb + (px + u * lanes) * yp);
+      if (px + u * lanes < hi) v[u] = Vec8<T>::ld_stream(yb + (px + u * lanes) * yp);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (px + u * lanes >= hi) break;
       float f[8];
-      unpack8(v[u], f);
+      v[u].unpack(f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(ra[j], f[j], rb[j]);
         f[j] = t > 0.f ? t : t * slope;
       }
-      *reinterpret_cast<uint4*>(zb + (px + u * lanes) * zp) = pack8(f);
+      Vec8<T>::st(zb + (px + u * lanes) * zp, f);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
+template <typename T>
 struct InBwdK {
-  const __nv_bfloat16* dz;
+  const T* dz;
   int64_t dzp;
-  const __nv_bfloat16* dz2;
+  const T* dz2;
   int64_t dz2p;
-  const __nv_bfloat16* y;
+  const T* y;
   int64_t yp;
   const float *a, *b, *mean;
   float slope;
@@ -184,8 +165,11 @@ struct InBwdK {
 };
 
 // T1 = sum dz*m, T2 = sum dz*m*(y - mean) over the block's pixels, m = lrelu'(a*y+b).   grid (P, images)
-__global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, float* __restrict__ part, int P) {
-  extern __shared__ float red[];  // [lanes][c8n][16]
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK<T> K, float* __restrict__ part, int P) {
+  using Acc = typename AccT<T>::type;
+  extern __shared__ __align__(8) unsigned char red_raw[];
+  Acc* red = reinterpret_cast<Acc*>(red_raw);  // [lanes][c8n][16]
   // reverse image order (the producer of dz wrote the last image last: L2 hits); the apply pass then runs forward
   // and finds the images this pass read last still in L2
   const int n = K.n0 + (gridDim.y - 1 - blockIdx.y);
@@ -196,35 +180,35 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, f
   ld8f(K.a + n * K.C + c0, ra);
   ld8f(K.b + n * K.C + c0, rb);
   ld8f(K.mean + n * K.C + c0, rm);
-  float t1[8], t2[8];
+  Acc t1[8], t2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0;
   const int64_t lo = blockIdx.x * K.chunk;
   int64_t hi = lo + K.chunk;
   if (hi > K.HW) hi = K.HW;
-  const __nv_bfloat16* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
-  const __nv_bfloat16* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
-  const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  const T* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
+  const T* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
+  const T* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
   const int lanes = K.lanes;
   constexpr int U = 4;  // pixels in flight per thread: 8-12 independent 16-byte loads cover the HBM latency
   for (int64_t px = lo + lane; px < hi; px += U * lanes) {
-    uint4 vy[U], vd[U], vd2[U];
+    Vec8<T> vy[U], vd[U], vd2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
-        vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
-        vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
-        if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
+        vy[u] = Vec8<T>::ld_stream(yb + (px + u * lanes) * K.yp);
+        vd[u] = Vec8<T>::ld_stream(db + (px + u * lanes) * K.dzp);
+        if (d2b) vd2[u] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (px + u * lanes >= hi) break;
       float yv[8], d[8];
-      unpack8(vy[u], yv);
-      unpack8(vd[u], d);
+      vy[u].unpack(yv);
+      vd[u].unpack(d);
       if (d2b) {
         float d2[8];
-        unpack8(vd2[u], d2);
+        vd2[u].unpack(d2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] += d2[j];
       }
@@ -233,11 +217,11 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, f
         const float pre = fmaf(ra[j], yv[j], rb[j]);
         const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
         t1[j] += gm;
-        t2[j] = fmaf(gm, yv[j] - rm[j], t2[j]);
+        t2[j] += static_cast<Acc>(gm) * static_cast<Acc>(yv[j] - rm[j]);
       }
     }
   }
-  float* mine = red + static_cast<size_t>(threadIdx.x) * 16;
+  Acc* mine = red + static_cast<size_t>(threadIdx.x) * 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mine[j] = t1[j];
@@ -248,9 +232,9 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK K, f
   for (int t = threadIdx.x; t < K.C * 2; t += blockDim.x) {
     const int c = t >> 1, k = t & 1;
     const int cc8 = c >> 3, j = c & 7;
-    float s = 0.f;
+    Acc s = 0;
     for (int l = 0; l < lanes; ++l) s += red[(l * K.c8n + cc8) * 16 + k * 8 + j];
-    part[((static_cast<int64_t>(n) * P + blockIdx.x) * K.C + c) * 2 + k] = s;
+    part[((static_cast<int64_t>(n) * P + blockIdx.x) * K.C + c) * 2 + k] = static_cast<float>(s);
   }
 }
 
@@ -315,8 +299,9 @@ __global__ void in_bwd_param_kernel(const float* __restrict__ imgsum, float* __r
 }
 
 // grid (blocks_per_image, images)
-__global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK K, const float* __restrict__ coef,
-                                                                        __nv_bfloat16* __restrict__ dy, int64_t dyp) {
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T> K, const float* __restrict__ coef,
+                                                                        T* __restrict__ dy, int64_t dyp) {
   const int n = K.n0 + blockIdx.y;
   const int c0 = (threadIdx.x % K.c8n) << 3;
   const int lane = threadIdx.x / K.c8n;
@@ -339,30 +324,30 @@ __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK K,
   const int64_t lo = blockIdx.x * K.chunk;
   int64_t hi = lo + K.chunk;
   if (hi > K.HW) hi = K.HW;
-  const __nv_bfloat16* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
-  const __nv_bfloat16* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
-  const __nv_bfloat16* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
-  __nv_bfloat16* ob = dy + static_cast<int64_t>(n) * K.HW * dyp + c0;
+  const T* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
+  const T* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
+  const T* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  T* ob = dy + static_cast<int64_t>(n) * K.HW * dyp + c0;
   const int lanes = K.lanes;
   constexpr int U = 4;
   for (int64_t px = lo + lane; px < hi; px += U * lanes) {
-    uint4 vy[U], vd[U], vd2[U];
+    Vec8<T> vy[U], vd[U], vd2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
-        vy[u] = ld_stream(yb + (px + u * lanes) * K.yp);
-        vd[u] = ld_stream(db + (px + u * lanes) * K.dzp);
-        if (d2b) vd2[u] = ld_stream(d2b + (px + u * lanes) * K.dz2p);
+        vy[u] = Vec8<T>::ld_stream(yb + (px + u * lanes) * K.yp);
+        vd[u] = Vec8<T>::ld_stream(db + (px + u * lanes) * K.dzp);
+        if (d2b) vd2[u] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (px + u * lanes >= hi) break;
       float yv[8], d[8], o[8];
-      unpack8(vy[u], yv);
-      unpack8(vd[u], d);
+      vy[u].unpack(yv);
+      vd[u].unpack(d);
       if (d2b) {
         float d2[8];
-        unpack8(vd2[u], d2);
+        vd2[u].unpack(d2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] += d2[j];
       }
@@ -372,7 +357,7 @@ __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK K,
         const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
         o[j] = fmaf(k1[j], gm, fmaf(-k2[j], yv[j], k3[j]));
       }
-      *reinterpret_cast<uint4*>(ob + (px + u * lanes) * dyp) = pack8(o);
+      Vec8<T>::st(ob + (px + u * lanes) * dyp, o);
     }
   }
 }
@@ -398,18 +383,27 @@ extern "C" int b200unet_in_finalize(const float* stats, int P, const float* gamm
   return 0;
 }
 
-extern "C" int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
-                                 int64_t z_pitch, int N, int64_t HW, int C, void* stream) {
+template <typename T>
+static int in_apply_impl(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
+                         int64_t z_pitch, int N, int64_t HW, int C, void* stream) {
   B200_CHECK_ARG(y && a && b && z, "in_apply: null pointer");
   int rc = check_nhwc("in_apply", C, y_pitch, z_pitch, 0);
   if (rc) return rc;
   const PixelMap m = make_map(C);
   const int64_t chunk = pixels_per_block(HW, N, m, 4 * blocks_per_sm());
-  in_apply_kernel<<<dim3((unsigned)ceil_div64(HW, chunk), N), m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), y_pitch, a, b, slope, static_cast<__nv_bfloat16*>(z), z_pitch, HW, C, m.c8n,
-      m.lanes, chunk);
+  in_apply_kernel<T><<<dim3((unsigned)ceil_div64(HW, chunk), N), m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(y), y_pitch, a, b, slope, static_cast<T*>(z), z_pitch, HW, C, m.c8n, m.lanes, chunk);
   B200_LAUNCH_CHECK("in_apply_kernel");
   return 0;
+}
+
+extern "C" int b200unet_in_apply(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* z,
+                                 int64_t z_pitch, int N, int64_t HW, int C, void* stream) {
+  return in_apply_impl<__nv_bfloat16>(y, y_pitch, a, b, slope, z, z_pitch, N, HW, C, stream);
+}
+extern "C" int b200unet_in_apply_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                                     void* z, int64_t z_pitch, int N, int64_t HW, int C, void* stream) {
+  return in_apply_impl<float>(y, y_pitch, a, b, slope, z, z_pitch, N, HW, C, stream);
 }
 
 // Images per launch group.  Splitting the batch into L2-sized groups (so the apply pass re-reads dz and y from L2)
@@ -436,7 +430,8 @@ extern "C" int64_t b200unet_in_backward_workspace(int N, int64_t HW, int C) {
   return (static_cast<int64_t>(N) * P * C * 2 + static_cast<int64_t>(N) * C * 6) * 4;
 }
 
-extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream) {
+template <typename T>
+static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
   B200_CHECK_ARG(A && A->dz && A->y && A->a && A->b && A->mean && A->rstd && A->gamma && A->dy && A->dgamma &&
                      A->dbeta && A->workspace,
                  "in_backward: null pointer");
@@ -457,12 +452,12 @@ extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream)
   float* part = A->workspace;
   float* coef = part + static_cast<int64_t>(N) * P * C * 2;
   float* imgsum = coef + static_cast<int64_t>(N) * C * 4;
-  InBwdK K;
-  K.dz = static_cast<const __nv_bfloat16*>(A->dz);
+  InBwdK<T> K;
+  K.dz = static_cast<const T*>(A->dz);
   K.dzp = A->dz_pitch;
-  K.dz2 = static_cast<const __nv_bfloat16*>(A->dz2);
+  K.dz2 = static_cast<const T*>(A->dz2);
   K.dz2p = A->dz2_pitch;
-  K.y = static_cast<const __nv_bfloat16*>(A->y);
+  K.y = static_cast<const T*>(A->y);
   K.yp = A->y_pitch;
   K.a = A->a;
   K.b = A->b;
@@ -473,23 +468,30 @@ extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream)
   K.c8n = m.c8n;
   K.lanes = m.lanes;
   K.chunk = chunk;
-  const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(float);
+  const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(typename AccT<T>::type);
   const double inv_hw = 1.0 / static_cast<double>(HW);
   for (int n0 = 0; n0 < N; n0 += ipc) {
     const int nn = (N - n0 < ipc) ? N - n0 : ipc;
     K.n0 = n0;
-    in_bwd_reduce_kernel<<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+    in_bwd_reduce_kernel<T><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
     B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
     in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
                                                                      imgsum, C, n0, inv_hw);
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
     K.chunk = chunk_apply;
-    in_bwd_apply_kernel<<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
-        K, coef, static_cast<__nv_bfloat16*>(A->dy), A->dy_pitch);
+    in_bwd_apply_kernel<T><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+        K, coef, static_cast<T*>(A->dy), A->dy_pitch);
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
   in_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
   B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
+}
+
+extern "C" int b200unet_in_backward(const b200unet_in_bwd_args* A, void* stream) {
+  return in_backward_impl<__nv_bfloat16>(A, stream);
+}
+extern "C" int b200unet_in_backward_f32(const b200unet_in_bwd_args* A, void* stream) {
+  return in_backward_impl<float>(A, stream);
 }

@@ -9,32 +9,17 @@
 // where an index that falls off the output is redirected to the edge sample (that is where the clamped tap went).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "vec8.cuh"
 
 namespace b200 {
-
-__device__ __forceinline__ void unpack8r(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-
-__device__ __forceinline__ uint4 pack8r(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-}
-__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) {
-  return __ldg(reinterpret_cast<const uint4*>(p));
-}
 
 // Forward: one thread = 8 channels of one INPUT pixel -> its 2x2 output block.  The 3x3 input neighbourhood comes
 // through L1 (each input element is shared by 9 threads of the same / adjacent warps); interpolation along w first,
 // then along h (the association of ATen's upsample_bilinear2d).  grid (ceil(W*C/8 / 256), H, N): no integer division
 // by runtime values.
-__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t xp,
-                                                              __nv_bfloat16* __restrict__ out, int64_t op, int H, int W,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ x, int64_t xp,
+                                                              T* __restrict__ out, int64_t op, int H, int W,
                                                               int c8n, int c8shift) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int iw = t >> c8shift;  // c8n is a power of two on this path
@@ -43,16 +28,16 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const __nv_bfloat16
   const int ih = blockIdx.y, n = blockIdx.z;
   const int hm = ih > 0 ? ih - 1 : 0, hp = ih < H - 1 ? ih + 1 : H - 1;
   const int wm = iw > 0 ? iw - 1 : 0, wp = iw < W - 1 ? iw + 1 : W - 1;
-  const __nv_bfloat16* b = x + static_cast<int64_t>(n) * H * W * xp + c0;
+  const T* b = x + static_cast<int64_t>(n) * H * W * xp + c0;
   const int rows[3] = {hm, ih, hp};
   float L[3][8], R[3][8];  // per source row: the two output columns 2iw, 2iw+1
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const __nv_bfloat16* rp = b + static_cast<int64_t>(rows[r]) * W * xp;
+    const T* rp = b + static_cast<int64_t>(rows[r]) * W * xp;
     float a[8], c[8], d[8];
-    unpack8r(ldg16(rp + static_cast<int64_t>(wm) * xp), a);
-    unpack8r(ldg16(rp + static_cast<int64_t>(iw) * xp), c);
-    unpack8r(ldg16(rp + static_cast<int64_t>(wp) * xp), d);
+    Vec8<T>::ldg(rp + static_cast<int64_t>(wm) * xp).unpack(a);
+    Vec8<T>::ldg(rp + static_cast<int64_t>(iw) * xp).unpack(c);
+    Vec8<T>::ldg(rp + static_cast<int64_t>(wp) * xp).unpack(d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       L[r][j] = 0.75f * c[j] + 0.25f * a[j];
@@ -60,28 +45,29 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const __nv_bfloat16
     }
   }
   const int OW = 2 * W;
-  __nv_bfloat16* o = out + (static_cast<int64_t>(n) * 2 * H + 2 * ih) * OW * op + static_cast<int64_t>(2 * iw) * op + c0;
+  T* o = out + (static_cast<int64_t>(n) * 2 * H + 2 * ih) * OW * op + static_cast<int64_t>(2 * iw) * op + c0;
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.75f * L[1][j] + 0.25f * L[0][j];
-  *reinterpret_cast<uint4*>(o) = pack8r(v);
+  Vec8<T>::st(o, v);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.75f * R[1][j] + 0.25f * R[0][j];
-  *reinterpret_cast<uint4*>(o + op) = pack8r(v);
+  Vec8<T>::st(o + op, v);
   o += static_cast<int64_t>(OW) * op;
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.75f * L[1][j] + 0.25f * L[2][j];
-  *reinterpret_cast<uint4*>(o) = pack8r(v);
+  Vec8<T>::st(o, v);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.75f * R[1][j] + 0.25f * R[2][j];
-  *reinterpret_cast<uint4*>(o + op) = pack8r(v);
+  Vec8<T>::st(o + op, v);
 }
 
 // Backward (gather): one thread = 8 channels of one INPUT pixel; separable: for each of the 4 output rows
 // 2ih-1 .. 2ih+2 (clamped) combine the 4 output columns 2iw-1 .. 2iw+2 (clamped) with (.25,.75,.75,.25), then the rows
 // with the same weights.  A clamped index is where the reference's edge-replicated tap landed, so its weight stays.
-__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int64_t dp,
-                                                              __nv_bfloat16* __restrict__ dx, int64_t xp, int H, int W,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dout, int64_t dp,
+                                                              T* __restrict__ dx, int64_t xp, int H, int W,
                                                               int c8n, int c8shift) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int iw = t >> c8shift;
@@ -89,7 +75,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
   const int c0 = (t & (c8n - 1)) << 3;
   const int ih = blockIdx.y, n = blockIdx.z;
   const int OH = 2 * H, OW = 2 * W;
-  const __nv_bfloat16* b = dout + static_cast<int64_t>(n) * OH * OW * dp + c0;
+  const T* b = dout + static_cast<int64_t>(n) * OH * OW * dp + c0;
   int cols[4], rws[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -103,27 +89,28 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __nv_bfloat16
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const __nv_bfloat16* rp = b + static_cast<int64_t>(rws[a]) * OW * dp;
-    uint4 raw[4];
+    const T* rp = b + static_cast<int64_t>(rws[a]) * OW * dp;
+    Vec8<T> raw[4];
 #pragma unroll
-    for (int bb = 0; bb < 4; ++bb) raw[bb] = ldg16(rp + static_cast<int64_t>(cols[bb]) * dp);
+    for (int bb = 0; bb < 4; ++bb) raw[bb] = Vec8<T>::ldg(rp + static_cast<int64_t>(cols[bb]) * dp);
     float d0[8], d1[8], d2[8], d3[8];
-    unpack8r(raw[0], d0);
-    unpack8r(raw[1], d1);
-    unpack8r(raw[2], d2);
-    unpack8r(raw[3], d3);
+    raw[0].unpack(d0);
+    raw[1].unpack(d1);
+    raw[2].unpack(d2);
+    raw[3].unpack(d3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float hsum = 0.25f * (d0[j] + d3[j]) + 0.75f * (d1[j] + d2[j]);
       acc[j] = fmaf(wt[a], hsum, acc[j]);
     }
   }
-  *reinterpret_cast<uint4*>(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0) = pack8r(acc);
+  Vec8<T>::st(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ layout
 // NCHW fp32 -> NHWC bf16 through a 32x32 shared-memory transpose (coalesced on both sides)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t dp, int C,
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t dp, int C,
                                     int64_t HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -138,7 +125,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int64_t p = p0 + j;
     const int c = c0 + threadIdx.x;
-    if (c < C && p < HW) dst[(static_cast<int64_t>(n) * HW + p) * dp + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (c < C && p < HW) dst[(static_cast<int64_t>(n) * HW + p) * dp + c] = from_f32<T>(tile[threadIdx.x][j]);
   }
 }
 
@@ -171,38 +158,66 @@ static int ilog2_exact(int v) {
   return (1 << s) == v ? s : -1;
 }
 
-extern "C" int b200unet_upsample2x_fwd(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H,
-                                       int W, int C, void* stream) {
+template <typename T>
+static int upsample_fwd_impl(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H, int W, int C,
+                             void* stream) {
   B200_CHECK_ARG(x && out, "upsample2x_fwd: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0, "upsample2x_fwd: C and pitches must be multiples of 8");
   const int c8n = C / 8, sh = ilog2_exact(c8n);
   B200_CHECK_ARG(sh >= 0, "upsample2x_fwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_fwd: H and N must fit the grid");
-  upsample2x_fwd_kernel<<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<__nv_bfloat16*>(out), out_pitch, H, W, c8n, sh);
+  upsample2x_fwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(x), x_pitch, static_cast<T*>(out), out_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_fwd_kernel");
   return 0;
 }
 
-extern "C" int b200unet_upsample2x_bwd(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H,
-                                       int W, int C, void* stream) {
+template <typename T>
+static int upsample_bwd_impl(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H, int W,
+                             int C, void* stream) {
   B200_CHECK_ARG(dout && dx, "upsample2x_bwd: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && dout_pitch % 8 == 0 && dx_pitch % 8 == 0, "upsample2x_bwd: C and pitches must be multiples of 8");
   const int c8n = C / 8, sh = ilog2_exact(c8n);
   B200_CHECK_ARG(sh >= 0, "upsample2x_bwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_bwd: H and N must fit the grid");
-  upsample2x_bwd_kernel<<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dout), dout_pitch, static_cast<__nv_bfloat16*>(dx), dx_pitch, H, W, c8n, sh);
+  upsample2x_bwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(dout), dout_pitch, static_cast<T*>(dx), dx_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_bwd_kernel");
   return 0;
+}
+
+extern "C" int b200unet_upsample2x_fwd(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H,
+                                       int W, int C, void* stream) {
+  return upsample_fwd_impl<__nv_bfloat16>(x, x_pitch, out, out_pitch, N, H, W, C, stream);
+}
+extern "C" int b200unet_upsample2x_fwd_f32(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H,
+                                           int W, int C, void* stream) {
+  return upsample_fwd_impl<float>(x, x_pitch, out, out_pitch, N, H, W, C, stream);
+}
+extern "C" int b200unet_upsample2x_bwd(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H,
+                                       int W, int C, void* stream) {
+  return upsample_bwd_impl<__nv_bfloat16>(dout, dout_pitch, dx, dx_pitch, N, H, W, C, stream);
+}
+extern "C" int b200unet_upsample2x_bwd_f32(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N,
+                                           int H, int W, int C, void* stream) {
+  return upsample_bwd_impl<float>(dout, dout_pitch, dx, dx_pitch, N, H, W, C, stream);
 }
 
 extern "C" int b200unet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int64_t dst_pitch, int N, int C, int64_t HW,
                                               void* stream) {
   B200_CHECK_ARG(src && dst, "nchw_f32_to_nhwc_bf16: null pointer");
   dim3 grid((unsigned)ceil_div64(HW, 32), ceil_div(C, 32), N);
-  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+  nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), dst_pitch, C, HW);
+  B200_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return 0;
+}
+extern "C" int b200unet_nchw_f32_to_nhwc_f32(const float* src, void* dst, int64_t dst_pitch, int N, int C, int64_t HW,
+                                             void* stream) {
+  B200_CHECK_ARG(src && dst, "nchw_f32_to_nhwc_f32: null pointer");
+  dim3 grid((unsigned)ceil_div64(HW, 32), ceil_div(C, 32), N);
+  nchw_to_nhwc_kernel<float><<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<float*>(dst), dst_pitch, C, HW);
   B200_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return 0;
 }

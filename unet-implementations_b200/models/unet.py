@@ -196,6 +196,10 @@ class UNet(nn.Module):
         self._trace = None                                        # debug: list collecting (raw conv out, activation) per unit
         self._grad_sink = None                                    # callable(param, grad) fired as backward produces grads
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
+        # "bf16": production path (tcgen05 convs, NHWC bf16 arena).  "fp32": verification mode -- the same fused
+        # forward/backward with an fp32 arena, the storage-type templates of the norm/resample/head kernels and the
+        # direct fp32 convs; agrees with the reference to 1e-4 on loss and every gradient (tests/test_gpu_model.py)
+        self.precision = "bf16"
 
     def initialize_weights(self):
         """kaiming_normal_(fan_out, leaky_relu) on conv weights, zero conv biases, IN weight 1 / bias 0 (unet.py:386-397)."""
@@ -226,16 +230,17 @@ class UNet(nn.Module):
                 layers.append(dict(kind="dec", stage=j, idx=i, last=(i == len(us) - 1), unit=u))
         return layers
 
-    def _packed(self, conv: nn.Conv2d, need_dgrad: bool):
-        """bf16 repacks of a conv weight for the implicit-GEMM kernels, cached on the parameter's version counter."""
+    def _packed(self, conv: nn.Conv2d, need_dgrad: bool, dtype=BF16):
+        """Repacks of a conv weight for the conv kernels ([Cout,3,3,Cin] and [Cin,3,3,Cout], bf16 or fp32), cached on
+        the parameter's version counter."""
         w = conv.weight
         key = id(w)
         ver = w._version
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == ver and hit[1].device == w.device and (hit[2] is not None or not need_dgrad) \
-                and hit[3] == w.data_ptr():
+                and hit[3] == w.data_ptr() and hit[1].dtype == dtype:
             return hit[1], hit[2]
-        wf, wd = ops.pack_conv_weights(w, need_dgrad=need_dgrad)
+        wf, wd = ops.pack_conv_weights(w, need_dgrad=need_dgrad, dtype=dtype)
         self._pack_cache[key] = (ver, wf, wd, w.data_ptr())
         return wf, wd
 
@@ -286,6 +291,9 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     feats = list(model.features_per_stage)
     layers = model._layers()
     training = model.training
+    if model.precision not in ("bf16", "fp32"):
+        raise ValueError(f"b200unet: precision must be 'bf16' or 'fp32', got {model.precision!r}")
+    adt = torch.float32 if model.precision == "fp32" else BF16  # activation storage type of the arena
     need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside Function.forward; this is the autograd truth
     dev = x.device
 
@@ -303,7 +311,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
                 f"{sizes[d]} over {sizes[d + 1]} -- use an input size divisible by {2 ** (n - 1)}")
 
     # decoder concat buffers: cat[d] = [upsampled level d+1 (feats[d+1]) | skip of level d (feats[d])]
-    cat = [torch.empty((B, sizes[d][0], sizes[d][1], feats[d + 1] + feats[d]), dtype=BF16, device=dev)
+    cat = [torch.empty((B, sizes[d][0], sizes[d][1], feats[d + 1] + feats[d]), dtype=adt, device=dev)
            for d in range(n - 1)]
 
     # dropout scales, drawn in the reference's order with the reference's call
@@ -336,17 +344,17 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             cur = cat[d]
         first = L["kind"] == "enc" and L["stage"] == 0 and L["idx"] == 0
         if first:
-            if cin == 3 and cout == 32 and stride == 1:
+            if cin == 3 and cout == 32 and stride == 1 and adt == BF16:
                 y, stats = ops.stem_fprop(x, conv.weight)
                 rec["stem"] = True
             else:
-                xin = ops.nchw_to_nhwc(x, out=_padded_nhwc(B, H, W, cin, dev))
-                wf, wd = model._packed(conv, False)
+                xin = ops.nchw_to_nhwc(x, out=_padded_nhwc(B, H, W, cin, dev, adt))
+                wf, wd = model._packed(conv, False, adt)
                 y, stats = _conv_fwd(xin, wf, stride)
                 rec["xin"] = xin
                 rec["stem"] = False
         else:
-            wf, wd = model._packed(conv, need_grad)
+            wf, wd = model._packed(conv, need_grad, adt)
             y, stats = _conv_fwd(cur, wf, stride)
             rec["xin"] = cur
             rec["wd"] = wd
@@ -384,9 +392,9 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     return logits
 
 
-def _padded_nhwc(B, H, W, C, dev):
+def _padded_nhwc(B, H, W, C, dev, dtype=BF16):
     pitch = (C + 7) // 8 * 8
-    buf = torch.zeros((B, H, W, pitch), dtype=BF16, device=dev)
+    buf = torch.zeros((B, H, W, pitch), dtype=dtype, device=dev)
     return buf[..., :C]
 
 

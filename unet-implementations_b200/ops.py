@@ -15,6 +15,16 @@ from . import _lib
 from ._lib import ConvDgradArgs, ConvFpropArgs, ConvWgradArgs, InBwdArgs
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _sfx(t: torch.Tensor) -> str:
+    """Entry-point suffix for the activation storage type: bf16 (production) or fp32 (verification mode)."""
+    if t.dtype == BF16:
+        return ""
+    if t.dtype == F32:
+        return "_f32"
+    raise TypeError(f"b200unet: activations must be bf16 or fp32, got {t.dtype}")
 
 
 def _p(t):
@@ -26,8 +36,8 @@ def _stream():
 
 
 def pitch_of(t: torch.Tensor) -> int:
-    """Pixel pitch (elements) of an NHWC bf16 tensor or channel-slice view; validates the layout."""
-    assert t.dim() == 4 and t.dtype == BF16 and t.is_cuda, "expected a CUDA bf16 [N,H,W,C] tensor"
+    """Pixel pitch (elements) of an NHWC bf16/fp32 tensor or channel-slice view; validates the layout."""
+    assert t.dim() == 4 and t.dtype in (BF16, F32) and t.is_cuda, "expected a CUDA bf16/fp32 [N,H,W,C] tensor"
     n, h, w, c = t.shape
     pitch = t.stride(2)
     assert t.stride(3) == 1 and pitch >= c, f"channels must be contiguous (strides {t.stride()})"
@@ -51,14 +61,14 @@ def require_device():
 
 
 # ----------------------------------------------------------------------------------------------------- convolution
-def pack_conv_weights(w_oihw: torch.Tensor, need_dgrad: bool = True):
-    """fp32 [Cout,Cin,3,3] -> (bf16 [Cout,3,3,Cin], bf16 [Cin,3,3,Cout] or None)."""
+def pack_conv_weights(w_oihw: torch.Tensor, need_dgrad: bool = True, dtype=BF16):
+    """fp32 [Cout,Cin,3,3] -> ([Cout,3,3,Cin], [Cin,3,3,Cout] or None) in `dtype` (bf16, or fp32 for the fp32 mode)."""
     w = _f32(w_oihw.detach())
     cout, cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
-    wf = torch.empty((cout, 3, 3, cin), dtype=BF16, device=w.device)
-    wd = torch.empty((cin, 3, 3, cout), dtype=BF16, device=w.device) if need_dgrad else None
-    _lib.call("b200unet_pack_conv_weights", _p(w), _p(wf), _p(wd), cout, cin, _stream())
+    wf = torch.empty((cout, 3, 3, cin), dtype=dtype, device=w.device)
+    wd = torch.empty((cin, 3, 3, cout), dtype=dtype, device=w.device) if need_dgrad else None
+    _lib.call("b200unet_pack_conv_weights" + _sfx(wf), _p(w), _p(wf), _p(wd), cout, cin, _stream())
     return wf, wd
 
 
@@ -70,10 +80,12 @@ def conv_fprop(x, w_fprop, stride=1, out=None, want_stats=True, simt=False):
     """3x3/pad 1 conv.  Returns (y [N,OH,OW,Cout] bf16, stats fp32 [N,P,Cout,2] or None)."""
     n, h, w, cin = x.shape
     cout = w_fprop.shape[0]
-    assert w_fprop.shape == (cout, 3, 3, cin) and w_fprop.dtype == BF16 and w_fprop.is_contiguous()
+    assert w_fprop.shape == (cout, 3, 3, cin) and w_fprop.dtype == x.dtype and w_fprop.is_contiguous()
     oh, ow = conv_out_hw(h, w, stride)
-    y = out if out is not None else torch.empty((n, oh, ow, cout), dtype=BF16, device=x.device)
-    assert tuple(y.shape) == (n, oh, ow, cout)
+    y = out if out is not None else torch.empty((n, oh, ow, cout), dtype=x.dtype, device=x.device)
+    assert tuple(y.shape) == (n, oh, ow, cout) and y.dtype == x.dtype
+    f32 = x.dtype == F32
+    simt = simt or f32  # the tensor-core path is bf16-only
     stats = None
     if want_stats:
         if simt:
@@ -84,7 +96,8 @@ def conv_fprop(x, w_fprop, stride=1, out=None, want_stats=True, simt=False):
                 raise RuntimeError(f"conv_fprop: Cout={cout} outside the tensor-core envelope")
         stats = torch.empty((n, parts, cout, 2), dtype=torch.float32, device=x.device)
     a = ConvFpropArgs(_p(x), pitch_of(x), _p(w_fprop), _p(y), pitch_of(y), _p(stats), n, h, w, cin, cout, stride)
-    _lib.call("b200unet_conv_fprop_simt" if simt else "b200unet_conv_fprop", ctypes.byref(a), _stream())
+    name = "b200unet_conv_fprop_f32" if f32 else ("b200unet_conv_fprop_simt" if simt else "b200unet_conv_fprop")
+    _lib.call(name, ctypes.byref(a), _stream())
     return y, stats
 
 
@@ -93,11 +106,12 @@ def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
     n, oh, ow, cout = dy.shape
     cin = w_dgrad.shape[0]
     h, w = in_hw
-    assert w_dgrad.shape == (cin, 3, 3, cout) and w_dgrad.dtype == BF16 and w_dgrad.is_contiguous()
+    assert w_dgrad.shape == (cin, 3, 3, cout) and w_dgrad.dtype == dy.dtype and w_dgrad.is_contiguous()
     assert conv_out_hw(h, w, stride) == (oh, ow)
-    dx = out if out is not None else torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    dx = out if out is not None else torch.empty((n, h, w, cin), dtype=dy.dtype, device=dy.device)
     a = ConvDgradArgs(_p(dy), pitch_of(dy), _p(w_dgrad), _p(dx), pitch_of(dx), n, h, w, cin, cout, stride)
-    _lib.call("b200unet_conv_dgrad_simt" if simt else "b200unet_conv_dgrad", ctypes.byref(a), _stream())
+    name = "b200unet_conv_dgrad_f32" if dy.dtype == F32 else ("b200unet_conv_dgrad_simt" if simt else "b200unet_conv_dgrad")
+    _lib.call(name, ctypes.byref(a), _stream())
     return dx
 
 
@@ -107,9 +121,10 @@ def conv_wgrad(x, dy, stride=1, simt=False):
     _, oh, ow, cout = dy.shape
     assert conv_out_hw(h, w, stride) == (oh, ow)
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
-    if simt:
+    assert x.dtype == dy.dtype
+    if simt or x.dtype == F32:
         a = ConvWgradArgs(_p(x), pitch_of(x), _p(dy), pitch_of(dy), _p(dw), None, 0, n, h, w, cin, cout, stride)
-        _lib.call("b200unet_conv_wgrad_simt", ctypes.byref(a), _stream())
+        _lib.call("b200unet_conv_wgrad_f32" if x.dtype == F32 else "b200unet_conv_wgrad_simt", ctypes.byref(a), _stream())
         return dw
     nbytes = _lib.call("b200unet_conv_wgrad_workspace", n, h, w, cin, cout, stride)
     if nbytes < 0:
@@ -158,9 +173,9 @@ def in_finalize(stats, gamma, beta, drop_scale, eps, hw):
 
 def in_apply(y, a, b, slope, out=None):
     n, h, w, c = y.shape
-    z = out if out is not None else torch.empty((n, h, w, c), dtype=BF16, device=y.device)
-    assert tuple(z.shape) == (n, h, w, c)
-    _lib.call("b200unet_in_apply", _p(y), pitch_of(y), _p(a), _p(b), float(slope), _p(z), pitch_of(z), n, h * w, c,
+    z = out if out is not None else torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
+    assert tuple(z.shape) == (n, h, w, c) and z.dtype == y.dtype
+    _lib.call("b200unet_in_apply" + _sfx(y), _p(y), pitch_of(y), _p(a), _p(b), float(slope), _p(z), pitch_of(z), n, h * w, c,
               _stream())
     return z
 
@@ -173,11 +188,12 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
     nbytes = _lib.call("b200unet_in_backward_workspace", n, hw, c)
     ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=y.device)
     dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
-    dy = torch.empty((n, h, w, c), dtype=BF16, device=y.device)
+    dy = torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
+    assert dz.dtype == y.dtype and (dz2 is None or dz2.dtype == y.dtype)
     args = InBwdArgs(_p(dz), pitch_of(dz), _p(dz2), pitch_of(dz2) if dz2 is not None else 0, _p(y), pitch_of(y), _p(a),
                      _p(b), _p(mean), _p(rstd), _p(drop_scale), _p(_f32(gamma.detach())), float(slope), _p(dy),
                      pitch_of(dy), _p(dgb[0]), _p(dgb[1]), _p(ws), nbytes, n, hw, c)
-    _lib.call("b200unet_in_backward", ctypes.byref(args), _stream())
+    _lib.call("b200unet_in_backward" + _sfx(y), ctypes.byref(args), _stream())
     return dy, dgb[0], dgb[1]
 
 
@@ -185,16 +201,16 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
 def upsample2x(x, out):
     """Bilinear 2x of x [N,H,W,C] into out [N,2H,2W,C] (typically the leading channel slice of a concat buffer)."""
     n, h, w, c = x.shape
-    assert tuple(out.shape) == (n, 2 * h, 2 * w, c)
-    _lib.call("b200unet_upsample2x_fwd", _p(x), pitch_of(x), _p(out), pitch_of(out), n, h, w, c, _stream())
+    assert tuple(out.shape) == (n, 2 * h, 2 * w, c) and out.dtype == x.dtype
+    _lib.call("b200unet_upsample2x_fwd" + _sfx(x), _p(x), pitch_of(x), _p(out), pitch_of(out), n, h, w, c, _stream())
     return out
 
 
 def upsample2x_backward(dout, out=None):
     n, oh, ow, c = dout.shape
     assert oh % 2 == 0 and ow % 2 == 0
-    dx = out if out is not None else torch.empty((n, oh // 2, ow // 2, c), dtype=BF16, device=dout.device)
-    _lib.call("b200unet_upsample2x_bwd", _p(dout), pitch_of(dout), _p(dx), pitch_of(dx), n, oh // 2, ow // 2, c,
+    dx = out if out is not None else torch.empty((n, oh // 2, ow // 2, c), dtype=dout.dtype, device=dout.device)
+    _lib.call("b200unet_upsample2x_bwd" + _sfx(dout), _p(dout), pitch_of(dout), _p(dx), pitch_of(dx), n, oh // 2, ow // 2, c,
               _stream())
     return dx
 
@@ -203,7 +219,8 @@ def nchw_to_nhwc(x_nchw, out=None):
     x = _f32(x_nchw)
     n, c, h, w = x.shape
     y = out if out is not None else torch.empty((n, h, w, c), dtype=BF16, device=x.device)
-    _lib.call("b200unet_nchw_f32_to_nhwc_bf16", _p(x), _p(y), y.stride(2), n, c, h * w, _stream())
+    name = "b200unet_nchw_f32_to_nhwc_f32" if y.dtype == F32 else "b200unet_nchw_f32_to_nhwc_bf16"
+    _lib.call(name, _p(x), _p(y), y.stride(2), n, c, h * w, _stream())
     return y
 
 
@@ -220,7 +237,7 @@ def head_forward(z, weight, bias):
     n, h, w, c = z.shape
     k = weight.shape[0]
     logits = torch.empty((n, k, h, w), dtype=torch.float32, device=z.device)
-    _lib.call("b200unet_head_fwd", _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))),
+    _lib.call("b200unet_head_fwd" + _sfx(z), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))),
               _p(_f32(bias.detach())), _p(logits), n, h * w, c, k, _stream())
     return logits
 
@@ -232,10 +249,10 @@ def head_backward(dlogits, z, weight):
     dl = _f32(dlogits.contiguous())
     nbytes = _lib.call("b200unet_head_bwd_workspace", n, h * w, c, k)
     ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=z.device)
-    dz = torch.empty((n, h, w, c), dtype=BF16, device=z.device)
+    dz = torch.empty((n, h, w, c), dtype=z.dtype, device=z.device)
     dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=z.device)
     db = torch.empty((k,), dtype=torch.float32, device=z.device)
-    _lib.call("b200unet_head_bwd", _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
+    _lib.call("b200unet_head_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
               pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
     return dz, dw, db
 
