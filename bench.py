@@ -53,8 +53,7 @@ def conv_flops_per_image(size=512):
         fwd += f
         b = f if i == 0 else 2 * f
         bwd += b
-        if i > 0:
-            tc += f + b
+        tc += f + b  # every 3x3 conv runs on the tcgen05 kernels (the 3-channel stem zero-padded to K = 32)
     head = 2.0 * 3 * size * size * 32
     fwd += head
     bwd += 2 * head

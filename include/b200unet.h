@@ -212,6 +212,11 @@ int b200unet_head_bwd_f32(const float* dlogits_nchw, const void* z, int64_t z_pi
 int b200unet_nchw_f32_to_nhwc_f32(const float* src, void* dst, int64_t dst_pitch, int N, int C, int64_t HW,
                                   void* stream);
 
+/* fp32 NCHW image [N,C<=8,H,W] -> bf16 NHWC [N,H,W,32] with channels C..31 zero: the X operand of the stem's
+ * weight gradient on the tensor-core path (b200unet_conv_wgrad with Cin = 32; rows ci >= C of dW are zero).
+ * Replaces the weight-gradient half of aten::convolution_backward for encoder_stages[0].block[0] (unet.py:106). */
+int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int64_t HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

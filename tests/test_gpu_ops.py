@@ -104,11 +104,17 @@ def test_stem_conv_fprop_wgrad():
     dy, dy_ref = rand_act(n, h, w, 32, seed=6)
     yr.backward(dy_ref.permute(0, 3, 1, 2))
     assert O.rel_l2(ops.stem_wgrad(img.cuda(), dy), wt.grad) <= F32_TOL
+    # tensor-core route: the image operand is rounded to bf16 (one rounding of X: bf16 tolerance)
+    assert O.rel_l2(ops.stem_wgrad_tc(img.cuda(), dy), wt.grad) <= BF16_TOL
 
 
 @pytest.mark.parametrize("n,h,w,c,p,pitch", [(2, 16, 24, 32, 0.0, None), (3, 8, 8, 128, 0.3, 192),
                                             (2, 32, 32, 96, 0.2, None), (2, 2, 2, 512, 0.3, None),
-                                            (1, 64, 64, 64, 0.1, 96)])
+                                            (1, 64, 64, 64, 0.1, 96),
+                                            # >= 4 MB per image: the fused L2-resident backward (several image
+                                            # groups, ragged pixel ranges, with and without the second gradient)
+                                            (5, 256, 264, 32, 0.2, None), (3, 128, 136, 128, 0.3, 160),
+                                            (3, 192, 200, 64, 0.0, 96)])
 def test_instance_norm_lrelu_dropout_fwd_bwd(n, h, w, c, p, pitch):
     """unet.py:118-127 fused: IN(eps=1e-5, affine, biased variance) -> LeakyReLU(0.01) -> channel dropout."""
     from unet_implementations_b200 import ops

@@ -95,6 +95,7 @@ SIGNATURES = {
     "b200unet_head_fwd_f32": (c_int, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _P]),
     "b200unet_head_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_nchw_f32_to_nhwc_f32": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
+    "b200unet_image_to_nhwc32_bf16": (c_int, [_P, _P, _I, _I, _L, _P]),
 }
 
 # entry points that return a value rather than a status code

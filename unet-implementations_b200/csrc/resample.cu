@@ -148,6 +148,26 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int64
   }
 }
 
+
+// fp32 NCHW image (C <= 8) -> bf16 NHWC with the channels zero-padded to 32: the operand layout of the tensor-core
+// weight-gradient kernel for the stem (K = pixels; rows ci >= C of the result are zero and are dropped by the caller).
+// One thread per pixel: C coalesced plane reads, one 64-byte row written.
+__global__ void __launch_bounds__(256) image_to_nhwc32_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                               int C, int64_t HW) {
+  const int n = blockIdx.y;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= HW) return;
+  float f[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) f[c] = c < C ? __ldg(src + (static_cast<int64_t>(n) * C + c) * HW + p) : 0.f;
+  uint4* o = reinterpret_cast<uint4*>(dst + (static_cast<int64_t>(n) * HW + p) * 32);
+  o[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  o[1] = z;
+  o[2] = z;
+  o[3] = z;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -229,5 +249,14 @@ extern "C" int b200unet_nhwc_bf16_to_nchw_f32(const void* src, int64_t src_pitch
   nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), src_pitch, dst, C, HW);
   B200_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int64_t HW, void* stream) {
+  B200_CHECK_ARG(src && dst, "image_to_nhwc32_bf16: null pointer");
+  B200_CHECK_ARG(C >= 1 && C <= 8 && N <= 65535, "image_to_nhwc32_bf16: C must be in [1,8]");
+  image_to_nhwc32_kernel<<<dim3((unsigned)ceil_div64(HW, 256), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), C, HW);
+  B200_LAUNCH_CHECK("image_to_nhwc32_kernel");
   return 0;
 }

@@ -244,6 +244,17 @@ class UNet(nn.Module):
         self._pack_cache[key] = (ver, wf, wd, w.data_ptr())
         return wf, wd
 
+    def _packed_stem(self, conv: nn.Conv2d):
+        """bf16 [Cout,3,3,32] pack of the stem weight (input channels zero-padded to 32), cached like _packed."""
+        w = conv.weight
+        key = ("stem", id(w))
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr():
+            return hit[1]
+        wf = ops.pack_stem_weights(w)
+        self._pack_cache[key] = (w._version, wf, None, w.data_ptr())
+        return wf
+
     def forward(self, x):
         if x.dim() != 4 or x.size(1) != self.in_channels:
             raise ValueError(f"UNet.forward expects [B,{self.in_channels},H,W], got {tuple(x.shape)}")
@@ -344,7 +355,14 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             cur = cat[d]
         first = L["kind"] == "enc" and L["stage"] == 0 and L["idx"] == 0
         if first:
-            if cin == 3 and cout == 32 and stride == 1 and adt == BF16:
+            if cin <= 8 and cout == 32 and stride == 1 and adt == BF16 and W >= 64:
+                # stem on the tensor-core path: image -> bf16 NHWC zero-padded to 32 channels (64 B per pixel), then
+                # the narrow-output 32 -> 32 kernels; the padded copy is also the X operand of the weight gradient
+                xin32 = ops.image_to_nhwc32(x)
+                y, stats = ops.conv_fprop(xin32, model._packed_stem(conv), 1, want_stats=True)
+                rec["stem"] = True
+                rec["xin32"] = xin32 if need_grad else None
+            elif cin == 3 and cout == 32 and stride == 1 and adt == BF16:
                 y, stats = ops.stem_fprop(x, conv.weight)
                 rec["stem"] = True
             else:
@@ -460,7 +478,7 @@ def _backward_impl(ctx, dlogits):
         cin, cout = conv.in_channels, conv.out_channels
         simt = not _use_tc(cin, cout)
         if rec.get("stem") is True:
-            put(conv.weight, lambda: ops.stem_wgrad(ctx.image, dy))
+            put(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, rec.get("xin32")))
             break
         xin = rec["xin"]
         put(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt))

@@ -150,6 +150,35 @@ def stem_fprop(img_nchw, w_oihw, out=None, want_stats=True):
     return y, stats
 
 
+def image_to_nhwc32(img_nchw):
+    """fp32 NCHW image (C <= 8) -> bf16 NHWC [N,H,W,32], channels C..31 zero: the stem's operand on the tensor-core
+    path (one 64-byte row per pixel)."""
+    img = _f32(img_nchw)
+    n, c, h, w = img.shape
+    assert c <= 8
+    xp = torch.empty((n, h, w, 32), dtype=BF16, device=img.device)
+    _lib.call("b200unet_image_to_nhwc32_bf16", _p(img), _p(xp), n, c, h * w, _stream())
+    return xp
+
+
+def pack_stem_weights(w_oihw):
+    """[Cout, C<=8, 3, 3] fp32 -> bf16 [Cout,3,3,32] with the input channels zero-padded to 32."""
+    cout, c = w_oihw.shape[0], w_oihw.shape[1]
+    w32 = torch.zeros((cout, 32, 3, 3), dtype=torch.float32, device=w_oihw.device)
+    w32[:, :c] = w_oihw.detach()
+    return pack_conv_weights(w32, need_dgrad=False)[0]
+
+
+def stem_wgrad_tc(img_nchw, dy, xp=None):
+    """Stem weight gradient on the tensor-core path: the narrow-output wgrad kernel (Cin = 32 -> Cout = 32) runs on the
+    zero-padded bf16 image and the 29 zero rows are dropped.  2.5x faster than the CUDA-core kernel at 512^2 x 32."""
+    c = img_nchw.shape[1]
+    assert dy.dtype == BF16
+    if xp is None:
+        xp = image_to_nhwc32(img_nchw)
+    return conv_wgrad(xp, dy, 1)[:, :c].contiguous()
+
+
 def stem_wgrad(img_nchw, dy):
     img = _f32(img_nchw)
     n, c, h, w = img.shape
