@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int n_img = tile / tiles_per_img;
         const int t_in = tile - n_img * tiles_per_img;
-        const int th = t_in / p.tiles_w;
-        const int h0 = th * kNcTH, w0 = (t_in - th * p.tiles_w) * kNcValidW;
+        // column-major tile order inside an image: the next tile is the one below, its 2 halo rows are in L2
+        const int tw_ = t_in / p.tiles_h;
+        const int h0 = (t_in - tw_ * p.tiles_h) * kNcTH, w0 = tw_ * kNcValidW;
         const long long g0 = static_cast<long long>(it) * chunks;
         int c = (warp - static_cast<int>(g0 % kNcProducers) + kNcProducers) % kNcProducers;
         for (; c < chunks; c += kNcProducers) {
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
     // tile coordinates advance incrementally (two tiles per step): no divisions in the loop
     int tile = tile_lo + g;
     int n_img = tile / tiles_per_img;
-    int th = (tile - n_img * tiles_per_img) / p.tiles_w;
-    int tw = tile - n_img * tiles_per_img - th * p.tiles_w;
+    int tw = (tile - n_img * tiles_per_img) / p.tiles_h;
+    int th = tile - n_img * tiles_per_img - tw * p.tiles_h;
     uint32_t ph = 0;  // parity of this group's accumulator barrier
     for (; tile < tile_hi; tile += 2, ph ^= 1) {
       const int h0 = th * kNcTH, w0 = tw * kNcValidW;
@@ -313,11 +314,11 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
         acc[3] += s2b;
       }
       // next tile of this group
-      tw += 2;
-      while (tw >= p.tiles_w) {
-        tw -= p.tiles_w;
-        if (++th == p.tiles_h) {
-          th = 0;
+      th += 2;
+      while (th >= p.tiles_h) {
+        th -= p.tiles_h;
+        if (++tw == p.tiles_w) {
+          tw = 0;
           ++n_img;
         }
       }

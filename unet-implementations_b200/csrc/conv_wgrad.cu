@@ -214,7 +214,73 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* 
   dw[(static_cast<int64_t>(co) * cin + ci) * 9 + tap] = acc;
 }
 
+// Same reduction through a shared-memory transpose: a block owns 32 output channels x 8 input channels; the partials
+// are read along co (128-byte rows), the OIHW result is written as 288-byte runs (8 ci x 9 taps per output channel).
+// The plain kernel above scatters 4-byte writes 36 bytes apart: 0.6 ms per step over the 22 layers (ncu).
+__global__ void __launch_bounds__(256) wgrad_finalize_tiled_kernel(const float* __restrict__ partial,
+                                                                    float* __restrict__ dw, int S, int cin, int cout) {
+  __shared__ float tile[32][73];
+  const int co_l = threadIdx.x & 31, ci_l = threadIdx.x >> 5;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 8;
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* src = partial + (static_cast<int64_t>(tap) * cin + ci0 + ci_l) * cout + co0 + co_l;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += src[static_cast<int64_t>(s) * total];
+    tile[co_l][ci_l * 9 + tap] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * 72; idx += 256) {
+    const int c = idx / 72, r = idx - c * 72;
+    dw[(static_cast<int64_t>(co0 + c) * cin + ci0) * 9 + r] = tile[c][r];
+  }
+}
+
+// Many partials, small tensor (the narrow layers: S = 148 splits of a 9 x 32 x 32 .. 9 x 192 x 64 gradient): the sum
+// over S is the long axis, so 8 thread groups of a block share it (fixed-order combine); a block owns 32 consecutive
+// output channels of one (tap, ci).
+__global__ void __launch_bounds__(256) wgrad_finalize_splits_kernel(const float* __restrict__ partial,
+                                                                     float* __restrict__ dw, int S, int cin, int cout) {
+  __shared__ float red[8][32];
+  const int co_l = threadIdx.x & 31, z = threadIdx.x >> 5;
+  const int64_t total = static_cast<int64_t>(9) * cin * cout;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + co_l;  // [tap][ci][co] index
+  const int s_per = (S + 7) / 8;
+  const int s_lo = z * s_per, s_hi = min(S, s_lo + s_per);
+  float a0 = 0.f, a1 = 0.f;
+  int s = s_lo;
+  for (; s + 1 < s_hi; s += 2) {
+    a0 += partial[static_cast<int64_t>(s) * total + i];
+    a1 += partial[static_cast<int64_t>(s + 1) * total + i];
+  }
+  if (s < s_hi) a0 += partial[static_cast<int64_t>(s) * total + i];
+  red[z][co_l] = a0 + a1;
+  __syncthreads();
+  if (z == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][co_l];
+    const int co = static_cast<int>(i % cout);
+    const int64_t r = i / cout;
+    const int ci = static_cast<int>(r % cin);
+    const int tap = static_cast<int>(r / cin);
+    dw[(static_cast<int64_t>(co) * cin + ci) * 9 + tap] = v;
+  }
+}
+
 int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st) {
+  if (cout % 32 == 0 && S >= 16) {
+    wgrad_finalize_splits_kernel<<<(unsigned)(static_cast<int64_t>(9) * cin * cout / 32), 256, 0, st>>>(partial, dw, S, cin,
+                                                                                                        cout);
+    B200_LAUNCH_CHECK("wgrad_finalize_splits_kernel");
+    return 0;
+  }
+  if (cin % 8 == 0 && cout % 32 == 0) {
+    wgrad_finalize_tiled_kernel<<<dim3(cout / 32, cin / 8), 256, 0, st>>>(partial, dw, S, cin, cout);
+    B200_LAUNCH_CHECK("wgrad_finalize_tiled_kernel");
+    return 0;
+  }
   const int64_t total = static_cast<int64_t>(9) * cin * cout;
   wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, dw, S, cin, cout);
   B200_LAUNCH_CHECK("wgrad_finalize_kernel");

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
         const int kb = kb_begin + i;
         const int n_img = kb / blocks_per_img;
         const int b_in = kb - n_img * blocks_per_img;
+        // row-major block order (measured: column-major would keep the 3 halo rows in L2, -10 % DRAM reads, but the
+        // 32 KB jumps between consecutive blocks cost more than that: 381 vs 345 us at 512^2 x 32)
         const int bh = b_in / p.blocks_w;
         const int bw = b_in - bh * p.blocks_w;
         const int h0 = bh * kWnR, w0 = bw * 16;

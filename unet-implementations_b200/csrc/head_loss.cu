@@ -214,76 +214,94 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, 
   for (int k = 0; k < K; ++k) logits[(static_cast<int64_t>(n) * K + k) * HW + px] = acc[k];
 }
 
-// grid-stride over pixels; thread accumulates dW[K][C] and db[K] privately, block-reduces, writes one partial row.
+// grid-stride over (pixel, channel octet): thread (px, c8) computes dz for 8 channels and accumulates its 8 columns
+// of dW[K][C] (+ db on the c8 == 0 thread) -- 27 accumulators instead of K*C = 96 per thread (the one-thread-per-pixel
+// version needed 254 registers: 12 % occupancy, 2.4 TB/s).  Block reduction: butterfly over the pixel lanes of a
+// warp, then the 8 warps in fixed order; one partial row per block (deterministic).
 template <typename T, int C, int K>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ z,
                                                         int64_t zp, const float* __restrict__ w,
                                                         T* __restrict__ dz, int64_t dzp,
                                                         float* __restrict__ partial, int N, int64_t HW) {
-  __shared__ float ws[K][C];
+  constexpr int C8N = C / 8;
+  static_assert(C8N >= 1 && C8N <= 32 && (C8N & (C8N - 1)) == 0, "C/8 must be a power of two <= 32");
   __shared__ float red[8][K * C + K];
-  for (int i = threadIdx.x; i < K * C; i += 256) ws[i / C][i % C] = w[i];
-  __syncthreads();
-  float aw[K][C];
-  float ab[K];
+  const int c8 = threadIdx.x % C8N, c0 = c8 * 8;
+  float wr[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[k][i] = w[k * C + c0 + i];
+  float aw[K][8], ab[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     ab[k] = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) aw[k][c] = 0.f;
+    for (int i = 0; i < 8; ++i) aw[k][i] = 0.f;
   }
   const int64_t total = static_cast<int64_t>(N) * HW;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; g < total;
-       g += static_cast<int64_t>(gridDim.x) * 256) {
-    const int n = static_cast<int>(g / HW);
-    const int64_t px = g - static_cast<int64_t>(n) * HW;
-    float d[K];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * (256 / C8N);
+  constexpr int U = 4;  // pixels in flight per thread
+  for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * (256 / C8N) + threadIdx.x / C8N; g0 < total; g0 += U * stride) {
+    float d[U][K];
+    Vec8<T> zv[U];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      d[k] = dl[(static_cast<int64_t>(n) * K + k) * HW + px];
-      ab[k] += d[k];
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < total) {
+        const int n = static_cast<int>(g / HW);
+        const int64_t px = g - static_cast<int64_t>(n) * HW;
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[u][k] = __ldg(dl + (static_cast<int64_t>(n) * K + k) * HW + px);
+        zv[u] = Vec8<T>::ld_stream(z + g * zp + c0);
+      }
     }
-    const T* src = z + g * zp;
-    T* dst = dz + g * dzp;
 #pragma unroll
-    for (int j = 0; j < C / 8; ++j) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g >= total) break;
       float zf[8], o[8];
-      Vec8<T>::ldg(src + 8 * j).unpack(zf);
+      zv[u].unpack(zf);
+#pragma unroll
+      for (int k = 0; k < K; ++k) ab[k] += d[u][k];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float s = 0.f;
+        float sacc = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          s = fmaf(ws[k][8 * j + i], d[k], s);
-          aw[k][8 * j + i] = fmaf(d[k], zf[i], aw[k][8 * j + i]);
+          sacc = fmaf(wr[k][i], d[u][k], sacc);
+          aw[k][i] = fmaf(d[u][k], zf[i], aw[k][i]);
         }
-        o[i] = s;
+        o[i] = sacc;
       }
-      Vec8<T>::st(dst + 8 * j, o);
+      Vec8<T>::st(dz + g * dzp + c0, o);
     }
   }
-  // block reduction: shuffle tree per value, then across the 8 warps in order
+  // pixel lanes of a warp that share a channel octet: butterfly over the lane bits above log2(C8N)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
+  for (int m = C8N; m < 32; m <<= 1) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float v = aw[k][c];
+    for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[warp][k * C + c] = v;
+      for (int i = 0; i < 8; ++i) aw[k][i] += __shfl_xor_sync(0xffffffffu, aw[k][i], m);
+      ab[k] += __shfl_xor_sync(0xffffffffu, ab[k], m);
     }
-    float v = ab[k];
+  }
+  if (lane < C8N) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][K * C + k] = v;
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][k * C + c0 + i] = aw[k][i];
+      if (c8 == 0) red[warp][K * C + k] = ab[k];
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * C + K; i += 256) {
-    float s = 0.f;
+    float sacc = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
-    partial[static_cast<int64_t>(blockIdx.x) * (K * C + K) + i] = s;
+    for (int wv = 0; wv < 8; ++wv) sacc += red[wv][i];
+    partial[static_cast<int64_t>(blockIdx.x) * (K * C + K) + i] = sacc;
   }
 }
 
