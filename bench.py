@@ -329,17 +329,42 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained 1.4 PF)"
     roofline = None
+    roofline_hbm = None
     breakdown = None
+    traffic = {}
+    try:  # DRAM bytes per step and kernel family from the committed ncu launch list (tools/traffic_json.py)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except Exception:
+        pass
     if prof is not None:
         tot = prof.totals_ms()
-        conv_ms = sum(tot.get(n, (0.0, 0))[0] for n in ("b200unet_conv_fprop", "b200unet_conv_dgrad", "b200unet_conv_wgrad"))
+        conv_names = ("b200unet_conv_fprop", "b200unet_conv_dgrad", "b200unet_conv_wgrad", "b200unet_image_to_nhwc32_bf16")
+        conv_ms = sum(tot.get(n, (0.0, 0))[0] for n in conv_names)
         conv_ms_step = conv_ms / args.steps
         achieved = tc * B / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gconv_kernel/wgrad_kernel (tcgen05 implicit-GEMM fprop+dgrad+wgrad)",
+        tconv = traffic.get("conv")
+        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (gconv/nconv fprop+dgrad, wgrad/wgradn + finalize), all 22 3x3 convs",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": None, "peak_source": peak_src, "conv_ms_per_step": conv_ms_step,
+                    "traffic": (tconv["dram_read_bytes"] + tconv["dram_write_bytes"]) if tconv and B == 32 and S == 512 else None,
+                    "traffic_note": "DRAM bytes of the family per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                    "profiles/r1_step_launches.md); algorithmic conv FLOPs per step = %.3e" % (tc * B),
+                    "peak_source": peak_src, "conv_ms_per_step": conv_ms_step,
                     "conv_share_of_step": conv_ms_step / ms_per_step,
                     "whole_step_tflops": fb * B / (ms_per_step * 1e-3) / 1e12}
+        # the dominant HBM-bound family: InstanceNorm + LeakyReLU + dropout, forward apply and fused backward.
+        # Algorithmic bytes: forward read + write = 4 B/element, backward read dz, read y,
+        # write dy = 6 B/element, 65.27 M elements per image at 512^2 (scaled by the pixel count otherwise).
+        elems = 65.27e6 * (S / 512.0) ** 2 * B
+        norm_ms = sum(tot.get(n, (0.0, 0))[0] for n in ("b200unet_in_apply", "b200unet_in_backward")) / args.steps
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        if norm_ms > 0:
+            ach = elems * 10.0 / (norm_ms * 1e-3) / 1e9
+            tn = traffic.get("norm")
+            roofline_hbm = {"bound": "hbm", "kernel": "in_apply + in_backward (InstanceNorm/LeakyReLU/dropout fwd + bwd)",
+                            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                            "traffic": (tn["dram_read_bytes"] + tn["dram_write_bytes"]) if tn and B == 32 and S == 512 else None,
+                            "algorithmic_bytes_per_step": elems * 10.0, "ms_per_step": norm_ms,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"}
         breakdown = {k.replace("b200unet_", ""): {"ms_per_step": v[0] / args.steps, "calls_per_step": v[1] / args.steps}
                      for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])}
 
@@ -365,6 +390,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,
             "breakdown_ms_per_step": breakdown,
         }
