@@ -217,6 +217,24 @@ int b200unet_nchw_f32_to_nhwc_f32(const float* src, void* dst, int64_t dst_pitch
  * Replaces the weight-gradient half of aten::convolution_backward for encoder_stages[0].block[0] (unet.py:106). */
 int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int64_t HW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The steps either side of the hot path.
+ * sgd_nesterov_step: torch.optim.SGD(lr, momentum, nesterov=True, weight_decay) over `count` fp32 tensors in ONE
+ *   launch (Our_UNet/src/train.py:431-451 builds that optimizer; train.py:651-660 steps it).  Host arrays of DEVICE
+ *   pointers; arithmetic mirrors torch's foreach SGD on CUDA operation by operation (bit-exact, tests/test_gpu_aux.py).
+ *   first_step != 0 initialises the momentum buffers with the (decayed) gradient, as torch does.
+ * argmax_counts: torch.argmax(outputs, dim=1) + the per-class intersection / prediction / target pixel counts over
+ *   valid pixels that validate() turns into Dice scores (train.py:554-572).  counts9 = int64 [3][3] on the device:
+ *   [c][0] = #(pred==c & target==c), [c][1] = #(pred==c), [c][2] = #(target==c), valid pixels only; pred (int64
+ *   [N,H,W], ties -> lowest index) is optional.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_sgd_max_tensors(void);
+int b200unet_sgd_nesterov_step(float* const* params, const float* const* grads, float* const* momentum_bufs,
+                               const int64_t* numels, int count, float lr, float momentum, float weight_decay,
+                               int nesterov, int first_step, void* stream);
+int b200unet_argmax_counts(const float* logits_nchw, const int64_t* target, int ignore_index, int64_t* pred_or_null,
+                           int64_t* counts9, int N, int64_t HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
