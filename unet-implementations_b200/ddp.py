@@ -63,6 +63,16 @@ class BucketedGradAllReduce:
             self.buckets.append([start, off])
             self.last_param_of_bucket[id(params[-1])] = len(self.buckets) - 1
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        # gradients may arrive slightly out of production order (weight gradients run on a side stream and are
+        # delivered one layer later): a bucket is reduced when ALL of its parameters have arrived
+        self.bucket_size: List[int] = [0] * len(self.buckets)
+        for p in params:
+            b = 0
+            while not (self.buckets[b][0] <= self.offsets[id(p)] < self.buckets[b][1]):
+                b += 1
+            self.bucket_of[id(p)] = b
+            self.bucket_size[b] += 1
+        self.arrived: List[int] = [0] * len(self.buckets)
         self.works: list = []
         self.numel = off
         model._grad_sink = self
@@ -71,8 +81,9 @@ class BucketedGradAllReduce:
         off = self.offsets[id(p)]
         view = self.flat[off:off + p.numel()].view_as(p)
         view.copy_(g)
-        b = self.last_param_of_bucket.get(id(p))
-        if b is not None and self.world > 1:
+        b = self.bucket_of[id(p)]
+        self.arrived[b] += 1
+        if self.arrived[b] == self.bucket_size[b] and self.world > 1:
             lo, hi = self.buckets[b]
             chunk = self.flat[lo:hi]
             if self.backend == "nccl":
@@ -88,6 +99,7 @@ class BucketedGradAllReduce:
         if self.works and self.backend != "nccl":
             self.flat.mul_(1.0 / self.world)
         self.works = []
+        self.arrived = [0] * len(self.buckets)
 
 
 def broadcast_parameters(model, src: int = 0, group=None):

@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple, Type, Union
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -195,6 +197,10 @@ class UNet(nn.Module):
         self.last_dropout_masks: List[torch.Tensor] = []          # [N,C] scales used by the last training forward
         self._trace = None                                        # debug: list collecting (raw conv out, activation) per unit
         self._grad_sink = None                                    # callable(param, grad) fired as backward produces grads
+        # backward runs each weight-gradient kernel (tensor-bound) on a side stream, concurrently with the NEXT layer's
+        # InstanceNorm backward (HBM-bound) on the main stream; B200UNET_OVERLAP=0 or this flag = False serialises
+        self.overlap_wgrad = os.environ.get("B200UNET_OVERLAP", "1") != "0"
+        self._side_streams: Dict[int, torch.cuda.Stream] = {}
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
         # "bf16": production path (tcgen05 convs, NHWC bf16 arena).  "fp32": verification mode -- the same fused
         # forward/backward with an fp32 arena, the storage-type templates of the norm/resample/head kernels and the
@@ -455,6 +461,44 @@ def _backward_impl(ctx, dlogits):
     put(head.weight, lambda: dwh)
     put(head.bias, lambda: dbh)
 
+    # Weight gradients off the critical path.  The chain  norm-backward(k) -> dgrad(k) -> norm-backward(k-1) -> ...  is
+    # the critical path of backward; wgrad(k) only needs dy(k).  It is launched on a side stream once dgrad(k) has
+    # finished, so that it (tensor-bound) runs concurrently with norm-backward(k-1) (HBM-bound) on the main stream; the
+    # main stream picks the gradient up one layer later (wait on its event, then hand it to the sink / autograd).
+    main = torch.cuda.current_stream()
+    overlap = bool(model.overlap_wgrad)
+    side = None
+    if overlap:
+        side = model._side_streams.get(main.device.index)
+        if side is None:
+            side = model._side_streams[main.device.index] = torch.cuda.Stream(device=main.device)
+    pending = []  # [(param, gradient tensor, event recorded on the side stream)]
+
+    def collect():
+        while pending:
+            p, g, ev = pending.pop(0)
+            main.wait_event(ev)
+            g.record_stream(main)
+            put(p, lambda: g)
+
+    def wgrad_async(p: Optional[nn.Parameter], fn, inputs):
+        """Run fn() (a weight-gradient launch) for parameter p: on the side stream after everything enqueued on the
+        main stream so far, or inline when overlap is off."""
+        if p is None or not req[ids[id(p)]]:
+            return
+        if not overlap:
+            put(p, fn)
+            return
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            g = fn()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in inputs:  # main-stream tensors read by the side stream: keep their memory until it is done
+            if t is not None:
+                t.record_stream(side)
+        pending.append((p, g, ev))
+
     dskip: Dict[int, torch.Tensor] = {}  # encoder level -> gradient view of the skip half of dcat
     dz2 = None
     for li in range(len(saved) - 1, -1, -1):
@@ -470,6 +514,7 @@ def _backward_impl(ctx, dlogits):
         dy, dgamma, dbeta = ops.in_backward(dz, dz2, rec["y"], rec["a"], rec["b"], rec["mean"], rec["rstd"], rec["scale"],
                                             norm.weight, rec["slope"])
         rec["y"] = None
+        collect()  # the previous layer's weight gradient ran beside this norm backward
         put(norm.weight, lambda: dgamma)
         put(norm.bias, lambda: dbeta)
         # the conv bias feeds an InstanceNorm: its exact gradient is zero
@@ -478,14 +523,18 @@ def _backward_impl(ctx, dlogits):
         cin, cout = conv.in_channels, conv.out_channels
         simt = not _use_tc(cin, cout)
         if rec.get("stem") is True:
-            put(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, rec.get("xin32")))
+            xin32 = rec.get("xin32")
+            wgrad_async(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, xin32), [ctx.image, dy, xin32])
             break
         xin = rec["xin"]
-        put(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt))
-        if li == first_needed or rec.get("stem") is False:
+        last = li == first_needed or rec.get("stem") is False
+        dx = None
+        if not last:
+            wd = rec["wd"]
+            dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
+        wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt), [xin, dy])
+        if last:
             break
-        wd = rec["wd"]
-        dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         rec["xin"] = None
         if L["kind"] == "dec" and L["idx"] == 0:
             d = n - 2 - L["stage"]
@@ -494,6 +543,7 @@ def _backward_impl(ctx, dlogits):
             dz = ops.upsample2x_backward(dx[..., :c_low])
         else:
             dz = dx
+    collect()
     if sink is not None and hasattr(sink, "finish"):
         sink.finish()
     ctx.saved = None
