@@ -283,3 +283,35 @@ def test_frozen_encoder_and_amp_scaler_loop():
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
+
+
+def test_gradcam_hooks_on_inner_conv_fire():
+    """Grad-CAM (Our_UNet/utils/visualize.py:391-415) hooks decoder_stages[0].conv_block.block[0]: the forward hook must
+    see that conv's output, the backward hook d(score)/d(output).  Checked against torch's own conv ops on the tensors
+    the hooks received: output == conv2d(input), and conv.weight.grad == conv2d_weight(input, grad_output)."""
+    import torch.nn.functional as F
+    from unet_implementations_b200.models.unet import UNet
+    torch.manual_seed(3)
+    model = UNet(n_stages=3, features_per_stage=[32, 64, 64], encoder_dropout_rates=[0, 0, 0],
+                 decoder_dropout_rates=[0, 0]).cuda().eval()
+    layer = model.decoder_stages[0].conv_block.block[0]
+    got = {}
+    h1 = layer.register_forward_hook(lambda m, i, o: got.update(inp=i[0].detach(), out=o.detach()))
+    h2 = layer.register_backward_hook(lambda m, gi, go: got.update(gout=go[0].detach()))
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    out = model(x)
+    score = out[0, 1].mean()
+    model.zero_grad()
+    score.backward(retain_graph=True)
+    h1.remove()
+    h2.remove()
+    assert got["out"].shape == (2, 64, 32, 32) and got["gout"].shape == got["out"].shape and got["inp"].shape == (2, 128, 32, 32)
+    ref_out = F.conv2d(got["inp"], layer.weight.detach(), layer.bias.detach(), stride=1, padding=1)
+    assert O.rel_l2(got["out"], ref_out) <= 1e-2
+    ref_dw = torch.nn.grad.conv2d_weight(got["inp"], layer.weight.shape, got["gout"], stride=1, padding=1)
+    assert O.rel_l2(layer.weight.grad, ref_dw) <= 1e-2
+    # Grad-CAM's own arithmetic runs on them
+    cam = F.relu((got["gout"].mean(dim=(2, 3), keepdim=True) * got["out"]).sum(1))
+    assert torch.isfinite(cam).all()
+    # and no hook -> nothing fires, same logits
+    assert torch.equal(model(x), out.detach())

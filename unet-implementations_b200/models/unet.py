@@ -273,6 +273,38 @@ class UNet(nn.Module):
 # ====================================================================================================================
 # The fused forward/backward
 # ====================================================================================================================
+# ====================================================================================================================
+# Hooks on inner Conv2d modules (Grad-CAM: Our_UNet/utils/visualize.py:391-402 registers a forward and a backward hook on
+# `decoder_stages[0].conv_block.block[0]`).  Inside the fused node no nn.Module.__call__ runs, so the hooks are fired
+# by hand with what a stock module would have shown them: (input,), output = conv(input) + bias in NCHW fp32, and in
+# backward grad_output = d loss / d output.  Only observation is supported (a hook that returns a replacement raises).
+# ====================================================================================================================
+def _to_nchw_f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype == BF16 and t.stride(3) == 1:
+        return ops.nhwc_to_nchw(t)
+    return t.permute(0, 3, 1, 2).float().contiguous()
+
+
+def _fire_forward_hooks(conv: nn.Conv2d, x_nchw_or_nhwc, y_nhwc, is_nchw_input: bool):
+    out = _to_nchw_f32(y_nhwc)
+    if conv.bias is not None:
+        out = out + conv.bias.detach().view(1, -1, 1, 1)
+    inp = x_nchw_or_nhwc if is_nchw_input else _to_nchw_f32(x_nchw_or_nhwc)
+    for hook in list(conv._forward_hooks.values()):
+        if hook(conv, (inp,), out) is not None:
+            raise NotImplementedError("b200unet: a forward hook on an inner Conv2d may observe its output, not replace it")
+
+
+def _fire_backward_hooks(conv: nn.Conv2d, dx_nhwc, dy_nhwc):
+    go = (_to_nchw_f32(dy_nhwc),)
+    gi = (_to_nchw_f32(dx_nhwc),)
+    for hook in list(conv._backward_hooks.values()):
+        if hook(conv, gi, go) is not None:
+            raise NotImplementedError("b200unet: a backward hook on an inner Conv2d may observe gradients, not replace them")
+
+
 def _use_tc(cin: int, cout: int) -> bool:
     return cin % 32 == 0 and cout % 32 == 0
 
@@ -382,6 +414,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             y, stats = _conv_fwd(cur, wf, stride)
             rec["xin"] = cur
             rec["wd"] = wd
+        if conv._forward_hooks:
+            _fire_forward_hooks(conv, x if first else cur, y, first)
         scale = draw(drop, cout)
         oh, ow = y.shape[1], y.shape[2]
         mean, rstd, a, b = ops.in_finalize(stats, norm.weight, norm.bias, scale, norm.eps, oh * ow)
@@ -523,6 +557,8 @@ def _backward_impl(ctx, dlogits):
         cin, cout = conv.in_channels, conv.out_channels
         simt = not _use_tc(cin, cout)
         if rec.get("stem") is True:
+            if conv._backward_hooks:
+                _fire_backward_hooks(conv, None, dy)
             xin32 = rec.get("xin32")
             wgrad_async(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, xin32), [ctx.image, dy, xin32])
             break
@@ -533,6 +569,8 @@ def _backward_impl(ctx, dlogits):
             wd = rec["wd"]
             dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt), [xin, dy])
+        if conv._backward_hooks:
+            _fire_backward_hooks(conv, dx, dy)
         if last:
             break
         rec["xin"] = None
