@@ -1,5 +1,5 @@
 // The two steps either side of the hot path in the reference's trainer:
-//  * the optimizer step -- torch.optim.SGD(momentum, nesterov=True, weight_decay) over the model's 94 parameter
+//  * the optimizer step -- torch.optim.SGD(momentum, nesterov=True, weight_decay) over the model's 90 parameter
 //    tensors (Our_UNet/src/train.py:431-451) as ONE multi-tensor launch instead of ~5 foreach launches per step;
 //  * the validation metric -- argmax over the 3 logits + per-class intersection / prediction / target counts over
 //    the valid pixels (train.py:554-572, nine .item() host syncs per batch in the reference) as one pass with integer
