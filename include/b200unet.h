@@ -235,6 +235,30 @@ int b200unet_sgd_nesterov_step(float* const* params, const float* const* grads, 
 int b200unet_argmax_counts(const float* logits_nchw, const int64_t* target, int ignore_index, int64_t* pred_or_null,
                            int64_t* counts9, int N, int64_t HW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Autoencoder variant (BASELINE.json configs[3]; AE_pretrained/reconstruction/models/autoencoder.py:374-387,
+ * src/train.py:431): reconstruction_output = Conv2d(32 -> 3, 3x3) + Sigmoid, nn.MSELoss.  The 3x3 conv runs on the
+ * conv entry points above with its output channels zero-padded; recon_head_fwd is its epilogue (bias + sigmoid ->
+ * fp32 NCHW [N,K,H,W], K <= 4), recon_head_bwd the backward prologue: dpre = dout * out * (1 - out) written as the
+ * NHWC gradient operand with channels K..Cpad-1 zero, and db[K] = sum dpre.  mse_fwd/bwd: mean squared error over n
+ * fp32 elements and its gradient 2 (a - b) / n * grad_out.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200unet_recon_head_fwd(const void* y, int64_t y_pitch, const float* bias, float* out_nchw, int N, int64_t HW,
+                            int K, void* stream);
+int b200unet_recon_head_fwd_f32(const void* y, int64_t y_pitch, const float* bias, float* out_nchw, int N, int64_t HW,
+                                int K, void* stream);
+int64_t b200unet_recon_head_bwd_workspace(int N, int64_t HW);
+int b200unet_recon_head_bwd(const float* dout_nchw, const float* out_nchw, void* dpre, int64_t dpre_pitch, int Cpad,
+                            float* db, float* workspace, int64_t workspace_bytes, int N, int64_t HW, int K,
+                            void* stream);
+int b200unet_recon_head_bwd_f32(const float* dout_nchw, const float* out_nchw, void* dpre, int64_t dpre_pitch, int Cpad,
+                                float* db, float* workspace, int64_t workspace_bytes, int N, int64_t HW, int K,
+                                void* stream);
+int64_t b200unet_mse_workspace(int64_t n);
+int b200unet_mse_fwd(const float* a, const float* b, float* loss_out, float* workspace, int64_t workspace_bytes,
+                     int64_t n, void* stream);
+int b200unet_mse_bwd(const float* a, const float* b, const float* grad_out, float* da, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,7 +144,27 @@ def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: UNetConfig =
             x = F.interpolate(x, size=skip.shape[2:], mode="bilinear", align_corners=False)  # unet.py:220-225
         x = torch.cat([rb(x, q), skip], dim=1)  # unet.py:228 -- upsampled first, skip second
         x = conv_block(x, sd, f"decoder_stages.{j}.conv_block", 1, cfg.decoder_dropout[j], cfg, masks, training, q)
+    if "reconstruction_output.0.weight" in sd:
+        # the autoencoder variant (AE_pretrained/reconstruction/models/autoencoder.py:374-387, :436):
+        # Conv2d(32 -> 3, 3x3, pad 1, bias) + Sigmoid instead of the 1x1 segmentation head
+        pre = F.conv2d(rb(x, q), rb(sd["reconstruction_output.0.weight"], q), None, padding=1)
+        return torch.sigmoid(rb(pre, q) + sd["reconstruction_output.0.bias"].view(1, -1, 1, 1))
     return F.conv2d(rb(x, q), sd["segmentation_output.weight"], sd["segmentation_output.bias"])
+
+
+def autoencoder_training_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, target: torch.Tensor,
+                              cfg: "UNetConfig", masks=None, training: bool = True, bf16_storage: bool = False,
+                              dtype: torch.dtype = torch.float32):
+    """One reference autoencoder training step on CPU (AE_pretrained/reconstruction/src/train.py:527-549: forward,
+    nn.MSELoss (train.py:431), backward).  Returns dict(output, loss, grads)."""
+    leaves = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in sd.items()}
+    if masks is not None:
+        masks = [m.to(dtype) for m in masks]
+    out = unet_forward(leaves, x.to(dtype), cfg, masks, training, bf16_storage)
+    loss = F.mse_loss(out, target.to(dtype))
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return dict(output=out.detach(), loss=loss.detach(), grads=grads)
 
 
 def class_weights(target: torch.Tensor, ignore_index: int = 255) -> torch.Tensor:

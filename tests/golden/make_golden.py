@@ -25,6 +25,46 @@ def sd_sha256(sd):
     return h.hexdigest()
 
 
+def make_autoencoder_fixture():
+    """small_ae.pt: the UNMODIFIED reference Autoencoder (AE_pretrained/reconstruction/models/autoencoder.py) + nn.MSELoss
+    (src/train.py:431) on seeded inputs -- run in a subprocess-free way by loading the module from its file, because its
+    package name `models` collides with Our_UNet's."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_autoencoder", "/root/reference/AE_pretrained/reconstruction/models/autoencoder.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = dict(in_channels=3, out_channels=3, n_stages=3, features_per_stage=[32, 64, 64],
+               kernel_sizes=[[3, 3]] * 3, strides=[[1, 1], [2, 2], [2, 2]], n_conv_per_stage=[2] * 3,
+               n_conv_per_stage_decoder=[2] * 2, encoder_dropout_rates=[0.0, 0.05, 0.15],
+               decoder_dropout_rates=[0.15, 0.0])
+    torch.manual_seed(27)
+    model = mod.Autoencoder(**cfg)
+    g = torch.Generator().manual_seed(28)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.2)
+    x = torch.rand(2, 3, 32, 48, generator=g)           # images in [0, 1] as the AE trainer feeds them
+    target = torch.rand(2, 3, 32, 48, generator=g)
+    loss_fn = torch.nn.MSELoss()
+    model.train()
+    torch.manual_seed(99)
+    out = model(x)
+    loss = loss_fn(out, target)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.eval()
+    with torch.no_grad():
+        out_eval = model(x)
+    # default architecture: key list and same-seed init hash
+    torch.manual_seed(1234)
+    full = mod.Autoencoder()
+    torch.save({"cfg": cfg, "state_dict": {k: v.clone() for k, v in model.state_dict().items()}, "x": x, "target": target,
+                "dropout_seed": 99, "output_train": out.detach(), "loss": loss.detach(), "grads": grads,
+                "output_eval": out_eval, "default_keys": list(full.state_dict().keys()),
+                "default_sha256": sd_sha256(full.state_dict())}, os.path.join(HERE, "small_ae.pt"))
+
+
 def main():
     sys.path.insert(0, REF)
     from models.losses import SimpleLoss  # noqa: E402  (the reference's own modules)
@@ -152,7 +192,8 @@ def main():
         cases[name] = {"logits": lg.detach().clone(), "target": tg, "kwargs": kw_s, "loss": val.detach(),
                        "dlogits": lg.grad.clone()}
     torch.save(cases, os.path.join(HERE, "loss_cases.pt"))
-    for f in ["tiny_unet.pt", "small_unet.pt", "default_unet_64.pt", "loss_cases.pt"]:
+    make_autoencoder_fixture()
+    for f in ["tiny_unet.pt", "small_unet.pt", "default_unet_64.pt", "loss_cases.pt", "small_ae.pt"]:
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
     print("default UNet sha256", sha)
 

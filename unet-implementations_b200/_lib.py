@@ -99,12 +99,21 @@ SIGNATURES = {
     "b200unet_sgd_max_tensors": (c_int, []),
     "b200unet_sgd_nesterov_step": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _P]),
     "b200unet_argmax_counts": (c_int, [_P, _P, _I, _P, _P, _I, _L, _P]),
+    "b200unet_recon_head_fwd": (c_int, [_P, _L, _P, _P, _I, _L, _I, _P]),
+    "b200unet_recon_head_fwd_f32": (c_int, [_P, _L, _P, _P, _I, _L, _I, _P]),
+    "b200unet_recon_head_bwd_workspace": (c_int64, [_I, _L]),
+    "b200unet_recon_head_bwd": (c_int, [_P, _P, _P, _L, _I, _P, _P, _L, _I, _L, _I, _P]),
+    "b200unet_recon_head_bwd_f32": (c_int, [_P, _P, _P, _L, _I, _P, _P, _L, _I, _L, _I, _P]),
+    "b200unet_mse_workspace": (c_int64, [_L]),
+    "b200unet_mse_fwd": (c_int, [_P, _P, _P, _P, _L, _L, _P]),
+    "b200unet_mse_bwd": (c_int, [_P, _P, _P, _P, _L, _P]),
 }
 
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
-    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors",
+    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_recon_head_bwd_workspace",
+    "b200unet_mse_workspace",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
     "b200unet_in_backward_workspace", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",
 }

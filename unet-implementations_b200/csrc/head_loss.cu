@@ -315,6 +315,87 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ partial, int 
   else db[i - KC] = static_cast<float>(s);
 }
 
+
+// ------------------------------------------------------------------------------- reconstruction head + MSE (autoencoder)
+// AE_pretrained/reconstruction/models/autoencoder.py:374-387: reconstruction_output = Conv2d(32 -> 3, 3x3, pad 1, bias)
+// + Sigmoid.  The 3x3 conv itself runs on the conv kernels (output channels zero-padded to the kernels' granularity);
+// these kernels are its epilogue -- bias + sigmoid into the fp32 NCHW boundary tensor -- and the matching backward
+// prologue: dpre = dout * out * (1 - out) as the (padded) NHWC gradient operand of dgrad/wgrad, plus db = sum dpre.
+template <typename T>
+__global__ void __launch_bounds__(256) recon_head_fwd_kernel(const T* __restrict__ y, int64_t yp,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int64_t HW, int K) {
+  const int n = blockIdx.y;
+  const int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (px >= HW) return;
+  const T* src = y + (static_cast<int64_t>(n) * HW + px) * yp;
+  for (int k = 0; k < K; ++k) {
+    const float v = to_f32(src[k]) + bias[k];
+    out[(static_cast<int64_t>(n) * K + k) * HW + px] = 1.f / (1.f + expf(-v));
+  }
+}
+
+// grid (blocks, N); every block writes one partial row [K] of db
+template <typename T>
+__global__ void __launch_bounds__(256) recon_head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                              T* __restrict__ dpre, int64_t dp, int Cpad,
+                                                              float* __restrict__ partial, int64_t HW, int K) {
+  __shared__ float scratch[8];
+  const int n = blockIdx.y;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; px < HW; px += static_cast<int64_t>(gridDim.x) * 256) {
+    T* dst = dpre + (static_cast<int64_t>(n) * HW + px) * dp;
+    for (int k = 0; k < Cpad; ++k) {
+      float g = 0.f;
+      if (k < K) {
+        const int64_t i = (static_cast<int64_t>(n) * K + k) * HW + px;
+        const float o = out[i];
+        g = dout[i] * o * (1.f - o);
+        if (k < 4) acc[k] += g;
+      }
+      dst[k] = from_f32<T>(g);
+    }
+  }
+  for (int k = 0; k < K && k < 4; ++k) {
+    const float v = block_sum(acc[k], scratch);
+    if (threadIdx.x == 0) partial[(static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * 4 + k] = v;
+  }
+}
+
+__global__ void recon_head_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int K, float* __restrict__ db) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) s += partial[static_cast<int64_t>(r) * 4 + k];
+  db[k] = static_cast<float>(s);
+}
+
+// nn.MSELoss(reduction='mean') (AE_pretrained/reconstruction/src/train.py:431): loss = mean((a - b)^2)
+__global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ partial, int64_t n) {
+  __shared__ float scratch[8];
+  float acc = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float d = a[i] - b[i];
+    acc = fmaf(d, d, acc);
+  }
+  const float v = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+__global__ void mse_finalize_kernel(const float* __restrict__ partial, int blocks, double inv_n, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int i = 0; i < blocks; ++i) s += partial[i];
+  out[0] = static_cast<float>(s * inv_n);
+}
+__global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       const float* __restrict__ gout, float scale,
+                                                       float* __restrict__ da, int64_t n) {
+  const float g = (gout ? gout[0] : 1.f) * scale;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256)
+    da[i] = g * (a[i] - b[i]);
+}
+
 static int head_bwd_blocks() { return num_sms() * 4; }
 
 }  // namespace b200
@@ -411,4 +492,92 @@ extern "C" int b200unet_head_bwd_f32(const float* dlogits_nchw, const void* z, i
                                      int64_t workspace_bytes, int N, int64_t HW, int C, int K, void* stream) {
   return head_bwd_impl<float>(dlogits_nchw, z, z_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N, HW, C,
                               K, stream);
+}
+
+static int recon_blocks(int64_t HW, int N) {
+  int64_t per = ceil_div64(static_cast<int64_t>(num_sms()) * 8, N);
+  const int64_t mx = ceil_div64(HW, 256);
+  if (per > mx) per = mx;
+  return static_cast<int>(per < 1 ? 1 : per);
+}
+
+template <typename T>
+static int recon_head_fwd_impl(const void* y, int64_t y_pitch, const float* bias, float* out_nchw, int N, int64_t HW,
+                               int K, void* stream) {
+  B200_CHECK_ARG(y && bias && out_nchw, "recon_head_fwd: null pointer");
+  B200_CHECK_ARG(K >= 1 && K <= 4 && y_pitch >= K && N <= 65535, "recon_head_fwd: K must be in [1,4]");
+  recon_head_fwd_kernel<T><<<dim3((unsigned)ceil_div64(HW, 256), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(y), y_pitch, bias, out_nchw, HW, K);
+  B200_LAUNCH_CHECK("recon_head_fwd_kernel");
+  return 0;
+}
+extern "C" int b200unet_recon_head_fwd(const void* y, int64_t y_pitch, const float* bias, float* out_nchw, int N,
+                                       int64_t HW, int K, void* stream) {
+  return recon_head_fwd_impl<__nv_bfloat16>(y, y_pitch, bias, out_nchw, N, HW, K, stream);
+}
+extern "C" int b200unet_recon_head_fwd_f32(const void* y, int64_t y_pitch, const float* bias, float* out_nchw, int N,
+                                           int64_t HW, int K, void* stream) {
+  return recon_head_fwd_impl<float>(y, y_pitch, bias, out_nchw, N, HW, K, stream);
+}
+
+extern "C" int64_t b200unet_recon_head_bwd_workspace(int N, int64_t HW) {
+  return static_cast<int64_t>(N) * recon_blocks(HW, N) * 4 * 4;
+}
+
+template <typename T>
+static int recon_head_bwd_impl(const float* dout_nchw, const float* out_nchw, void* dpre, int64_t dpre_pitch, int Cpad,
+                               float* db, float* workspace, int64_t workspace_bytes, int N, int64_t HW, int K,
+                               void* stream) {
+  B200_CHECK_ARG(dout_nchw && out_nchw && dpre && db && workspace, "recon_head_bwd: null pointer");
+  B200_CHECK_ARG(K >= 1 && K <= 4 && Cpad >= K && dpre_pitch >= Cpad && N <= 65535, "recon_head_bwd: bad channel counts");
+  B200_CHECK_ARG(workspace_bytes >= b200unet_recon_head_bwd_workspace(N, HW), "recon_head_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = recon_blocks(HW, N);
+  recon_head_bwd_kernel<T><<<dim3(blocks, N), 256, 0, st>>>(dout_nchw, out_nchw, static_cast<T*>(dpre), dpre_pitch, Cpad,
+                                                            workspace, HW, K);
+  B200_LAUNCH_CHECK("recon_head_bwd_kernel");
+  recon_head_bwd_finalize_kernel<<<1, 32, 0, st>>>(workspace, N * blocks, K, db);
+  B200_LAUNCH_CHECK("recon_head_bwd_finalize_kernel");
+  return 0;
+}
+extern "C" int b200unet_recon_head_bwd(const float* dout_nchw, const float* out_nchw, void* dpre, int64_t dpre_pitch,
+                                       int Cpad, float* db, float* workspace, int64_t workspace_bytes, int N, int64_t HW,
+                                       int K, void* stream) {
+  return recon_head_bwd_impl<__nv_bfloat16>(dout_nchw, out_nchw, dpre, dpre_pitch, Cpad, db, workspace, workspace_bytes,
+                                            N, HW, K, stream);
+}
+extern "C" int b200unet_recon_head_bwd_f32(const float* dout_nchw, const float* out_nchw, void* dpre, int64_t dpre_pitch,
+                                           int Cpad, float* db, float* workspace, int64_t workspace_bytes, int N,
+                                           int64_t HW, int K, void* stream) {
+  return recon_head_bwd_impl<float>(dout_nchw, out_nchw, dpre, dpre_pitch, Cpad, db, workspace, workspace_bytes, N, HW,
+                                    K, stream);
+}
+
+static int mse_blocks(int64_t n) {
+  const int64_t mx = ceil_div64(n, 256 * 8);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  return static_cast<int>(mx < 1 ? 1 : (mx > cap ? cap : mx));
+}
+extern "C" int64_t b200unet_mse_workspace(int64_t n) { return static_cast<int64_t>(mse_blocks(n)) * 4; }
+
+extern "C" int b200unet_mse_fwd(const float* a, const float* b, float* loss_out, float* workspace,
+                                int64_t workspace_bytes, int64_t n, void* stream) {
+  B200_CHECK_ARG(a && b && loss_out && workspace && n > 0, "mse_fwd: null pointer or empty input");
+  B200_CHECK_ARG(workspace_bytes >= b200unet_mse_workspace(n), "mse_fwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = mse_blocks(n);
+  mse_fwd_kernel<<<blocks, 256, 0, st>>>(a, b, workspace, n);
+  B200_LAUNCH_CHECK("mse_fwd_kernel");
+  mse_finalize_kernel<<<1, 32, 0, st>>>(workspace, blocks, 1.0 / static_cast<double>(n), loss_out);
+  B200_LAUNCH_CHECK("mse_finalize_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_mse_bwd(const float* a, const float* b, const float* grad_out, float* da, int64_t n,
+                                void* stream) {
+  B200_CHECK_ARG(a && b && da && n > 0, "mse_bwd: null pointer or empty input");
+  mse_bwd_kernel<<<mse_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, grad_out,
+                                                                               static_cast<float>(2.0 / static_cast<double>(n)), da, n);
+  B200_LAUNCH_CHECK("mse_bwd_kernel");
+  return 0;
 }

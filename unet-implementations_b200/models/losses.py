@@ -77,3 +77,42 @@ class SimpleLoss(nn.Module):
             cw = torch.as_tensor(self.class_weights, dtype=torch.float32, device=input.device).contiguous()
         return _SimpleLossFunction.apply(input, target, cw, dynamic, float(self.weight_ce), float(self.weight_dice),
                                          int(self.ignore_index), float(self.smooth))
+
+
+class _MSEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, target):
+        ops.require_device()
+        with torch.cuda.device(input.device):
+            a = input.detach()
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                a = a.float().contiguous()
+            b = target.detach()
+            if b.dtype != torch.float32 or not b.is_contiguous():
+                b = b.float().contiguous()
+            out = ops.mse_forward(a, b)
+        ctx.save_for_backward(a, b)
+        ctx.in_dtype = input.dtype
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.saved_tensors
+        with torch.cuda.device(a.device):
+            da = ops.mse_backward(a, b, grad_out.float())
+        if ctx.in_dtype != torch.float32:
+            da = da.to(ctx.in_dtype)
+        return da, None
+
+
+class MSELoss(nn.Module):
+    """`nn.MSELoss()` (mean reduction) as the autoencoder trainer uses it (AE_pretrained/reconstruction/src/train.py:431):
+    one reduction kernel forward, one elementwise kernel backward (b200unet_mse_fwd / b200unet_mse_bwd)."""
+
+    def forward(self, input, target):
+        if not input.is_cuda:
+            raise RuntimeError("b200unet: MSELoss needs CUDA tensors on an sm_100 device; there is no CPU path")
+        if input.shape != target.shape:
+            raise ValueError(f"MSELoss: shapes differ: {tuple(input.shape)} vs {tuple(target.shape)}")
+        return _MSEFunction.apply(input, target)
+

@@ -189,8 +189,7 @@ class UNet(nn.Module):
             self.decoder_stages.append(UpBlock(features_per_stage[d + 1], features_per_stage[d], features_per_stage[d],
                                                kernel_sizes[d], n_convs=n_conv_per_stage_decoder[d],
                                                spatial_dropout_rate=decoder_dropout_rates[j], **common))
-        self.segmentation_output = nn.Conv2d(features_per_stage[0], num_classes, kernel_size=1, stride=1, padding=0,
-                                             bias=True)
+        self._build_head(features_per_stage[0], num_classes)
         self.initialize_weights()
         # test/DDP hooks (not part of the reference surface)
         self._mask_override: Optional[List[torch.Tensor]] = None  # inject dropout masks instead of drawing them
@@ -206,6 +205,16 @@ class UNet(nn.Module):
         # forward/backward with an fp32 arena, the storage-type templates of the norm/resample/head kernels and the
         # direct fp32 convs; agrees with the reference to 1e-4 on loss and every gradient (tests/test_gpu_model.py)
         self.precision = "bf16"
+
+    # which output layer follows the decoder: "seg1x1" = Conv2d(32 -> classes, 1x1) (unet.py:374-381);
+    # "recon3x3" = Conv2d(32 -> 3, 3x3) + Sigmoid (the autoencoder variant, models/autoencoder.py)
+    head_kind = "seg1x1"
+
+    def _build_head(self, features: int, out_channels: int):
+        self.segmentation_output = nn.Conv2d(features, out_channels, kernel_size=1, stride=1, padding=0, bias=True)
+
+    def _head_conv(self) -> nn.Conv2d:
+        return self.segmentation_output
 
     def initialize_weights(self):
         """kaiming_normal_(fan_out, leaky_relu) on conv weights, zero conv biases, IN weight 1 / bias 0 (unet.py:386-397)."""
@@ -260,6 +269,22 @@ class UNet(nn.Module):
         wf = ops.pack_stem_weights(w)
         self._pack_cache[key] = (w._version, wf, None, w.data_ptr())
         return wf
+
+    def _packed_head(self, conv: nn.Conv2d, need_dgrad: bool, dtype):
+        """Packs of a 3x3 head conv whose OUTPUT channels are zero-padded (32 for the bf16 tensor-core kernels, 8 for
+        the fp32 direct kernels), cached like _packed."""
+        w = conv.weight
+        key = ("head", id(w))
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr() \
+                and hit[1].dtype == dtype and (hit[2] is not None or not need_dgrad):
+            return hit[1], hit[2]
+        cpad = 32 if dtype == BF16 else 8
+        wp = torch.zeros((cpad, conv.in_channels, 3, 3), dtype=torch.float32, device=w.device)
+        wp[:conv.out_channels] = w.detach()
+        wf, wd = ops.pack_conv_weights(wp, need_dgrad=need_dgrad, dtype=dtype)
+        self._pack_cache[key] = (w._version, wf, wd, w.data_ptr())
+        return wf, wd
 
     def forward(self, x):
         if x.dim() != 4 or x.size(1) != self.in_channels:
@@ -430,10 +455,22 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         cur = z
         if model._trace is not None:
             model._trace.append((y, z))
-    head = model.segmentation_output
-    if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
-        raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
-    logits = ops.head_forward(cur, head.weight, head.bias)
+    head = model._head_conv()
+    if model.head_kind == "seg1x1":
+        if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
+            raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
+        logits = ops.head_forward(cur, head.weight, head.bias)
+    else:
+        # reconstruction head (autoencoder.py:374-387): 3x3 conv 32 -> K on the conv kernels with the output channels
+        # zero-padded (bf16: to the tensor-core kernels' 32; fp32: to the 8-channel vector width), then bias + sigmoid
+        if head.out_channels > 4 or head.bias is None or head.in_channels % 32 != 0:
+            raise NotImplementedError("b200unet: the reconstruction head is built for Conv2d(32k -> <=4, 3x3, bias) + Sigmoid")
+        wfh, wdh = model._packed_head(head, need_grad, adt)
+        yh, _ = ops.conv_fprop(cur, wfh, 1, want_stats=False, simt=not _use_tc(head.in_channels, wfh.shape[0]))
+        logits = ops.recon_head_forward(yh[..., :head.out_channels], head.bias)
+        if need_grad:
+            ctx.head_out = logits
+            ctx.head_wd = wdh
     model.last_dropout_masks = used_masks
     if need_grad:
         ctx.model = model
@@ -488,10 +525,19 @@ def _backward_impl(ctx, dlogits):
             first_needed = li
             break
 
-    head = model.segmentation_output
+    head = model._head_conv()
     if dlogits.dtype != torch.float32:
         dlogits = dlogits.float()
-    dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight)
+    if model.head_kind == "seg1x1":
+        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight)
+    else:
+        z_last, wdh = ctx.z_last, ctx.head_wd
+        cpad = wdh.shape[3]
+        dpre, dbh = ops.recon_head_backward(dlogits, ctx.head_out, cpad, z_last.dtype)
+        simt_h = not _use_tc(head.in_channels, cpad)
+        dz = ops.conv_dgrad(dpre, wdh, (z_last.shape[1], z_last.shape[2]), 1, simt=simt_h)
+        dwh = ops.conv_wgrad(z_last, dpre, 1, simt=simt_h)[:head.out_channels].contiguous()
+        ctx.head_out = None
     put(head.weight, lambda: dwh)
     put(head.bias, lambda: dbh)
 

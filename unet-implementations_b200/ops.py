@@ -313,3 +313,47 @@ def loss_backward(logits, target, tables, grad_out, weight_ce, weight_dice, igno
     _lib.call("b200unet_loss_bwd", _p(lg), _p(target), _p(tables), _p(go), float(weight_ce), float(weight_dice),
               int(ignore_index), _p(dl), n, h * w, _stream())
     return dl
+
+
+# --------------------------------------------------------------------------------- autoencoder head + MSE (configs[3])
+def recon_head_forward(y, bias):
+    """Epilogue of the reconstruction conv: y [N,H,W,>=K] (raw 3x3 conv output, NHWC) + bias -> sigmoid -> fp32 NCHW."""
+    n, h, w, _ = y.shape
+    k = bias.numel()
+    out = torch.empty((n, k, h, w), dtype=torch.float32, device=y.device)
+    _lib.call("b200unet_recon_head_fwd" + _sfx(y), _p(y), pitch_of(y), _p(_f32(bias.detach())), _p(out), n, h * w, k,
+              _stream())
+    return out
+
+
+def recon_head_backward(dout, out, cpad, dtype):
+    """dpre = dout * out * (1 - out) as an NHWC [N,H,W,cpad] tensor of `dtype` (channels >= K zero) and db [K]."""
+    do, o = _f32(dout.contiguous()), _f32(out)
+    n, k, h, w = o.shape
+    dpre = torch.empty((n, h, w, cpad), dtype=dtype, device=o.device)
+    db = torch.empty((k,), dtype=torch.float32, device=o.device)
+    nbytes = _lib.call("b200unet_recon_head_bwd_workspace", n, h * w)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=o.device)
+    _lib.call("b200unet_recon_head_bwd" + _sfx(dpre), _p(do), _p(o), _p(dpre), pitch_of(dpre), cpad, _p(db), _p(ws), nbytes,
+              n, h * w, k, _stream())
+    return dpre, db
+
+
+def mse_forward(a, b):
+    a, b = _f32(a), _f32(b)
+    assert a.shape == b.shape
+    n = a.numel()
+    nbytes = _lib.call("b200unet_mse_workspace", n)
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=a.device)
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    _lib.call("b200unet_mse_fwd", _p(a), _p(b), _p(out), _p(ws), nbytes, n, _stream())
+    return out
+
+
+def mse_backward(a, b, grad_out):
+    a, b = _f32(a), _f32(b)
+    da = torch.empty_like(a)
+    go = _f32(grad_out.reshape(1).contiguous()) if grad_out is not None else None
+    _lib.call("b200unet_mse_bwd", _p(a), _p(b), _p(go), _p(da), a.numel(), _stream())
+    return da
+
