@@ -122,7 +122,7 @@ def conv_block(x, sd: Dict[str, torch.Tensor], prefix: str, stride: int, rate: f
 
 def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: UNetConfig = UNetConfig(),
                  masks: Optional[List[torch.Tensor]] = None, training: bool = True,
-                 bf16_storage: bool = False) -> torch.Tensor:
+                 bf16_storage: bool = False, clip_features: Optional[torch.Tensor] = None) -> torch.Tensor:
     """UNet.forward (unet.py:399-432): encoder with 5 skips, bottleneck, 5 UpBlocks (bilinear to the skip's size,
     cat([x, skip], 1), ConvBlock -- unet.py:203-231), 1x1 head (:430).  `masks` = draw_dropout_masks(...) when
     training (consumed in order); eval mode ignores dropout (unet.py:23-24)."""
@@ -137,6 +137,21 @@ def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: UNetConfig =
         skips.append(rb(x, q))  # the activated tensor is stored once (bf16); each consumer's gradient is stored separately
     s = cfg.n_stages - 1
     x = conv_block(x, sd, f"encoder_stages.{s}", cfg.strides[s], cfg.encoder_dropout[s], cfg, masks, training, q)
+    if clip_features is not None and "clip_fusion_conv.0.weight" in sd:
+        # CLIP_UNet/models/unet.py:441-478: resize the patch features to the bottleneck, cat([x, clip], 1), then
+        # clip_fusion_conv = Conv2d(1x1, bias) -> InstanceNorm2d -> LeakyReLU (unet.py:356-364)
+        cf = clip_features.to(x.dtype)
+        if cf.shape[2:] != x.shape[2:]:
+            cf = F.interpolate(cf, size=x.shape[2:], mode="bilinear", align_corners=False)
+        w = sd["clip_fusion_conv.0.weight"]
+        if q:
+            w = w + (w.detach().bfloat16().float() - w.detach())
+        x = torch.cat([rb(x, q), rb(cf, q)], dim=1)
+        x = rb(F.conv2d(x, w, None), q)
+        if sd.get("clip_fusion_conv.0.bias") is not None:
+            x = x + sd["clip_fusion_conv.0.bias"].view(1, -1, 1, 1)
+        x = F.instance_norm(x, weight=sd["clip_fusion_conv.1.weight"], bias=sd["clip_fusion_conv.1.bias"], eps=cfg.eps)
+        x = F.leaky_relu(x, cfg.negative_slope)
     for j in range(cfg.n_stages - 1):
         skip = skips[len(skips) - 1 - j]
         x = rb(x, q)
@@ -257,7 +272,8 @@ def synthetic_batch(batch: int, size: int = 512, seed: int = 0, variant: str = "
 
 def training_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, target: torch.Tensor, cfg: UNetConfig = UNetConfig(),
                   masks: Optional[List[torch.Tensor]] = None, training: bool = True, loss_kwargs: Optional[dict] = None,
-                  bf16_storage: bool = False, dtype: torch.dtype = torch.float32):
+                  bf16_storage: bool = False, dtype: torch.dtype = torch.float32,
+                  clip_features: Optional[torch.Tensor] = None):
     """One reference training step on CPU fp32 (train.py:654-663: forward, SimpleLoss, backward) through the
     restatement above, differentiated by torch autograd.  Returns dict(logits, loss, ce, dice, grads).
     `bf16_storage=True` keeps the arithmetic but rounds to bf16 exactly where the CUDA path stores bf16 (conv
@@ -271,7 +287,7 @@ def training_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, target: torch.Te
         leaves[k] = v.detach().clone().to(dtype).requires_grad_(True)
     if masks is not None:
         masks = [m.to(dtype) for m in masks]
-    logits = unet_forward(leaves, x.to(dtype), cfg, masks, training, bf16_storage)
+    logits = unet_forward(leaves, x.to(dtype), cfg, masks, training, bf16_storage, clip_features=clip_features)
     kw = dict(loss_kwargs or {})
     if dtype != torch.float32 and kw.get("dynamic", True) and kw.get("weights") is None:
         # the reference computes the class weights in fp32 from integer counts (losses.py:44-60); keep that and only

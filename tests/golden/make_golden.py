@@ -65,6 +65,56 @@ def make_autoencoder_fixture():
                 "default_sha256": sd_sha256(full.state_dict())}, os.path.join(HERE, "small_ae.pt"))
 
 
+def make_clip_unet_fixture():
+    """small_clip_unet.pt: the UNMODIFIED reference CLIP-conditioned UNet (CLIP_UNet/models/unet.py) + the reference
+    SimpleLoss on seeded inputs; the CLIP patch features are a seeded random tensor (the encoder is a frozen third-party
+    model whose output is an input of this module)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_clip_unet", "/root/reference/CLIP_UNet/models/unet.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    spec2 = importlib.util.spec_from_file_location("ref_clip_losses", "/root/reference/CLIP_UNet/models/losses.py")
+    lmod = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(lmod)
+    cfg = dict(in_channels=3, num_classes=3, n_stages=3, features_per_stage=[32, 64, 64],
+               kernel_sizes=[[3, 3]] * 3, strides=[[1, 1], [2, 2], [2, 2]], n_conv_per_stage=[2] * 3,
+               n_conv_per_stage_decoder=[2] * 2, encoder_dropout_rates=[0.0, 0.1, 0.3],
+               decoder_dropout_rates=[0.3, 0.0], with_clip_features=True, clip_dim=32)
+    torch.manual_seed(37)
+    model = mod.UNet(**cfg)
+    g = torch.Generator().manual_seed(38)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.2)
+    x = torch.randn(2, 3, 32, 48, generator=g)
+    clip = torch.randn(2, 32, 8, 12, generator=g)
+    clip_other = torch.randn(2, 32, 5, 7, generator=g)   # a patch grid that has to be resized (unet.py:444-451)
+    target = torch.randint(0, 3, (2, 32, 48), generator=g)
+    target[torch.rand(2, 32, 48, generator=g) < 0.1] = 255
+    loss_fn = lmod.SimpleLoss(weight_dice=1.0, weight_ce=1.0, ignore_index=255, smooth=1e-5, class_weights=None,
+                              dynamic_weights=True)
+    model.train()
+    torch.manual_seed(99)
+    logits = model(x, clip)
+    loss = loss_fn(logits, target)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.eval()
+    with torch.no_grad():
+        logits_eval = model(x, clip)
+        logits_eval_resized = model(x, clip_other)
+        logits_eval_noclip = model(x)
+    torch.manual_seed(1234)
+    full = mod.UNet()
+    torch.save({"cfg": cfg, "state_dict": {k: v.clone() for k, v in model.state_dict().items()}, "x": x, "clip": clip,
+                "clip_other": clip_other, "target": target, "dropout_seed": 99, "logits_train": logits.detach(),
+                "loss": loss.detach(), "grads": grads, "logits_eval": logits_eval,
+                "logits_eval_resized": logits_eval_resized, "logits_eval_noclip": logits_eval_noclip,
+                "default_keys": list(full.state_dict().keys()), "default_sha256": sd_sha256(full.state_dict())},
+               os.path.join(HERE, "small_clip_unet.pt"))
+
+
 def main():
     sys.path.insert(0, REF)
     from models.losses import SimpleLoss  # noqa: E402  (the reference's own modules)
@@ -193,7 +243,8 @@ def main():
                        "dlogits": lg.grad.clone()}
     torch.save(cases, os.path.join(HERE, "loss_cases.pt"))
     make_autoencoder_fixture()
-    for f in ["tiny_unet.pt", "small_unet.pt", "default_unet_64.pt", "loss_cases.pt", "small_ae.pt"]:
+    make_clip_unet_fixture()
+    for f in ["tiny_unet.pt", "small_unet.pt", "default_unet_64.pt", "loss_cases.pt", "small_ae.pt", "small_clip_unet.pt"]:
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
     print("default UNet sha256", sha)
 

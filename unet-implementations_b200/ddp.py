@@ -27,7 +27,12 @@ def backward_param_order(model) -> List[nn.Parameter]:
     order: List[nn.Parameter] = []
     head = model.segmentation_output
     order += [head.weight] + ([head.bias] if head.bias is not None else [])
-    for L in reversed(model._layers()):
+    layers = model._layers()
+    fusion = model._fusion_unit() if hasattr(model, "_fusion_unit") else None
+    if fusion is not None:  # between the encoder and the decoder (models/clip_unet.py); needs the extra features every step
+        layers = [L for L in layers if L["kind"] == "enc"] + [dict(kind="fusion", unit=fusion)] + \
+                 [L for L in layers if L["kind"] == "dec"]
+    for L in reversed(layers):
         conv, norm, _, _ = L["unit"]
         order += [norm.weight, norm.bias]
         if conv.bias is not None:

@@ -23,6 +23,7 @@ import os
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 try:  # package import (unet_implementations_b200.models.unet)
     from .. import ops
@@ -183,6 +184,8 @@ class UNet(nn.Module):
                                                  n_convs=n_conv_per_stage[s],
                                                  spatial_dropout_rate=encoder_dropout_rates[s], **common))
             ch = features_per_stage[s]
+        # variant hook: modules the reference creates between the encoder and the decoder (CLIP fusion layer)
+        self._build_bottleneck(features_per_stage[-1], conv_bias, norm_op, norm_op_kwargs, nonlin, nonlin_kwargs)
         self.decoder_stages = nn.ModuleList()
         for j in range(n_stages - 1):
             d = n_stages - 2 - j
@@ -215,6 +218,13 @@ class UNet(nn.Module):
 
     def _head_conv(self) -> nn.Conv2d:
         return self.segmentation_output
+
+    def _build_bottleneck(self, features, conv_bias, norm_op, norm_op_kwargs, nonlin, nonlin_kwargs):
+        return None
+
+    def _fusion_unit(self):
+        """(conv1x1, norm, act, None) applied to cat([bottleneck, extra features]) before the decoder, or None."""
+        return None
 
     def initialize_weights(self):
         """kaiming_normal_(fan_out, leaky_relu) on conv weights, zero conv biases, IN weight 1 / bias 0 (unet.py:386-397)."""
@@ -269,6 +279,21 @@ class UNet(nn.Module):
         wf = ops.pack_stem_weights(w)
         self._pack_cache[key] = (w._version, wf, None, w.data_ptr())
         return wf
+
+    def _packed_1x1(self, conv: nn.Conv2d, need_dgrad: bool, dtype):
+        """A 1x1 conv on the 3x3 conv kernels: its weight as the centre tap of a zero 3x3 kernel (the fusion layer is
+        2.4 GFLOP per image this way, 0.6 % of the step), packed and cached like _packed."""
+        w = conv.weight
+        key = ("k1", id(w))
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr() \
+                and hit[1].dtype == dtype and (hit[2] is not None or not need_dgrad):
+            return hit[1], hit[2]
+        w3 = torch.zeros((conv.out_channels, conv.in_channels, 3, 3), dtype=torch.float32, device=w.device)
+        w3[:, :, 1, 1] = w.detach()[:, :, 0, 0]
+        wf, wd = ops.pack_conv_weights(w3, need_dgrad=need_dgrad, dtype=dtype)
+        self._pack_cache[key] = (w._version, wf, wd, w.data_ptr())
+        return wf, wd
 
     def _packed_head(self, conv: nn.Conv2d, need_dgrad: bool, dtype):
         """Packs of a 3x3 head conv whose OUTPUT channels are zero-padded (32 for the bf16 tensor-core kernels, 8 for
@@ -403,6 +428,20 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         used_masks.append(m)
         return m
 
+    # optional fusion of extra features at the bottleneck (CLIP_UNet/models/unet.py:441-478): cat([x, features], 1)
+    # -> 1x1 conv -> norm -> act.  The last encoder unit writes its activation straight into the concat buffer.
+    extra = getattr(model, "_extra_features", None)
+    fusion = model._fusion_unit() if extra is not None else None
+    catf = None
+    if fusion is not None:
+        fh, fw = sizes[-1]
+        if extra.shape[2:] != (fh, fw):
+            extra = F.interpolate(extra.float(), size=(fh, fw), mode="bilinear", align_corners=False)  # unet.py:444-451
+        catf = torch.empty((B, fh, fw, feats[-1] + extra.shape[1]), dtype=adt, device=dev)
+        ops.nchw_to_nhwc(extra.detach().float().contiguous(), out=catf[..., feats[-1]:])
+        layers = [L for L in layers if L["kind"] == "enc"] + [dict(kind="fusion", stage=0, idx=0, last=True, unit=fusion)] + \
+                 [L for L in layers if L["kind"] == "dec"]
+
     saved = []  # per layer dict
     cur = None  # current NHWC bf16 activation
     for L in layers:
@@ -435,7 +474,13 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
                 rec["xin"] = xin
                 rec["stem"] = False
         else:
-            wf, wd = model._packed(conv, need_grad, adt)
+            if L["kind"] == "fusion":
+                if conv.kernel_size != (1, 1) or conv.in_channels != catf.shape[3]:
+                    raise NotImplementedError("b200unet: the fusion layer must be a 1x1 conv over cat([bottleneck, features])")
+                cur = catf
+                wf, wd = model._packed_1x1(conv, need_grad, adt)
+            else:
+                wf, wd = model._packed(conv, need_grad, adt)
             y, stats = _conv_fwd(cur, wf, stride)
             rec["xin"] = cur
             rec["wd"] = wd
@@ -449,6 +494,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         if L["kind"] == "enc" and L["last"] and L["stage"] < n - 1:
             d = L["stage"]
             dst = cat[d][..., feats[d + 1]:]
+        elif L["kind"] == "enc" and L["last"] and catf is not None:
+            dst = catf[..., :feats[-1]]
         z = ops.in_apply(y, a, b, act.negative_slope, out=dst)
         rec.update(y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale, slope=act.negative_slope, conv=conv, norm=norm)
         saved.append(rec)
@@ -614,7 +661,10 @@ def _backward_impl(ctx, dlogits):
         if not last:
             wd = rec["wd"]
             dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
-        wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt), [xin, dy])
+        if L["kind"] == "fusion":  # 1x1 weight = centre tap of the 3x3 gradient
+            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2].contiguous(), [xin, dy])
+        else:
+            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt), [xin, dy])
         if conv._backward_hooks:
             _fire_backward_hooks(conv, dx, dy)
         if last:
@@ -625,6 +675,8 @@ def _backward_impl(ctx, dlogits):
             c_low = feats[d + 1]
             dskip[d] = dx[..., c_low:]
             dz = ops.upsample2x_backward(dx[..., :c_low])
+        elif L["kind"] == "fusion":
+            dz = dx[..., :feats[-1]]  # the extra features are inputs: their half of the gradient is dropped
         else:
             dz = dx
     collect()
