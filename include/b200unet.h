@@ -228,6 +228,11 @@ int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int
  *   [c][0] = #(pred==c & target==c), [c][1] = #(pred==c), [c][2] = #(target==c), valid pixels only; pred (int64
  *   [N,H,W], ties -> lowest index) is optional.
  * ---------------------------------------------------------------------------------------------------------- */
+ /* preprocess_u8: the per-sample tensor conversion of PetSegmentationDataset.__getitem__ (train.py:299-311) for a whole
+ *   batch on the device: uint8 HWC image [N,H,W,3] -> (x / 255 - mean) / std -> fp32 NCHW, uint8 mask [N,H,W] ->
+ *   {0,1,2,255} int64 (other values become 0).  mean3/std3 are HOST pointers.  Either half may be NULL.  Bit-exact. */
+int b200unet_preprocess_u8(const void* image_u8_nhwc, const void* mask_u8, float* image_out_nchw, int64_t* mask_out,
+                           const float* mean3, const float* std3, int N, int64_t HW, void* stream);
 int b200unet_sgd_max_tensors(void);
 int b200unet_sgd_nesterov_step(float* const* params, const float* const* grads, float* const* momentum_bufs,
                                const int64_t* numels, int count, float lr, float momentum, float weight_decay,

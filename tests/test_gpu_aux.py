@@ -86,3 +86,24 @@ def test_argmax_counts_match_reference_validate():
     # all-ignored batch: union == 0 -> 1.0 (train.py:571-572)
     _, c0 = metrics.argmax_counts(logits.cuda(), torch.full((3, 37, 53), 255, dtype=torch.int64, device="cuda"), want_pred=False)
     assert int(c0.sum()) == 0 and torch.equal(metrics.dice_from_counts(c0).cpu(), torch.ones(3))
+
+
+def test_preprocess_u8_bit_exact_with_reference_dataset_arithmetic():
+    """train.py:299-311: image.float().permute(2,0,1) / 255.0, (image - mean) / std, mask clean-up, .long()."""
+    import numpy as np
+    from unet_implementations_b200 import data
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (3, 40, 56, 3), generator=g, dtype=torch.uint8)
+    mask = torch.randint(0, 3, (3, 40, 56), generator=g, dtype=torch.uint8)
+    mask[torch.rand(3, 40, 56, generator=g) < 0.1] = 255
+    mask[torch.rand(3, 40, 56, generator=g) < 0.05] = 7   # stray label -> 0
+    out, mout = data.preprocess_batch(img.cuda(), mask.cuda())
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    for b in range(3):
+        ref = (torch.from_numpy(img[b].numpy()).float().permute(2, 0, 1) / 255.0 - mean) / std
+        assert torch.equal(out[b].cpu(), ref)
+        m = mask[b].numpy()
+        refm = torch.from_numpy(np.where((m > 2) & (m != 255), 0, m)).long()
+        assert torch.equal(mout[b].cpu(), refm)
+    assert mout.dtype == torch.int64 and out.dtype == torch.float32
