@@ -186,6 +186,13 @@ int b200unet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int64_t dst_pitc
 int b200unet_nhwc_bf16_to_nchw_f32(const void* src, int64_t src_pitch, float* dst, int N, int C, int64_t HW,
                                    void* stream);
 
+/* Stride-2 data gradient for Cin in {32, 64} with the four input-pixel parity classes stacked on N (one launch, N =
+ * 4*Cin, dy read once) instead of four narrow launches.  `wt` of the args is the pack produced by
+ * b200unet_pack_s2_dgrad_weights from the ordinary dgrad pack ([Cin][3][3][Cout] -> [4*Cin][4][Cout]). */
+int b200unet_conv_dgrad_s2_supported(int Cin, int Cout);
+int b200unet_pack_s2_dgrad_weights(const void* wt, void* ws, int Cin, int Cout, void* stream);
+int b200unet_conv_dgrad_s2(const b200unet_conv_dgrad_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * fp32 verification mode (`UNet(...).precision = "fp32"`): the same operators with fp32 NHWC activations, fp32
  * packed weights and fp32 arithmetic -- north_star's "1e-4 in fp32 mode".  Argument structs, layouts and

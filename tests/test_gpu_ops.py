@@ -28,6 +28,8 @@ CONV_CASES = [
     (1, 8, 8, 512, 512, 1), (1, 8, 8, 512, 512, 2), (1, 8, 8, 1024, 512, 1), (1, 8, 8, 768, 256, 1),
     (1, 8, 16, 384, 128, 1), (1, 16, 16, 192, 64, 1), (2, 16, 32, 96, 32, 1),
     (2, 13, 21, 64, 64, 1), (2, 13, 21, 64, 96, 2), (1, 5, 7, 32, 32, 1), (3, 2, 2, 64, 64, 2),
+    # stride 2 with Cin in {32, 64}: parity-stacked dgrad (even, odd and ragged sizes, BK = 32 and 64)
+    (2, 16, 32, 32, 64, 2), (1, 13, 21, 32, 96, 2), (2, 18, 10, 64, 128, 2), (1, 7, 9, 32, 32, 2),
     # wide images: the narrow-output kernels (column taps stacked on N, 30-of-32 column tiles, ragged edges)
     (1, 12, 70, 32, 32, 1), (1, 9, 64, 96, 32, 1), (2, 8, 96, 64, 64, 1), (1, 6, 121, 64, 32, 1), (1, 7, 90, 32, 64, 1),
 ]
@@ -53,6 +55,12 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, cin, cout, stride):
     yr.backward(dy_ref.permute(0, 3, 1, 2))
     dx = ops.conv_dgrad(dy, wd, (h, w), stride)
     assert O.rel_l2(dx.float(), xr.grad.permute(0, 2, 3, 1)) <= BF16_TOL
+    ws2 = ops.pack_s2_dgrad_weights(wd) if stride == 2 else None
+    if ws2 is not None:  # stride 2, Cin in {32, 64}: the parity-stacked single-launch form, written into a pitched buffer
+        buf = torch.full((n, h, w, cin + 8), 3.0, dtype=torch.bfloat16, device="cuda")
+        ops.conv_dgrad_s2(dy, ws2, (h, w), out=buf[..., :cin])
+        assert O.rel_l2(buf[..., :cin].float(), xr.grad.permute(0, 2, 3, 1)) <= BF16_TOL
+        assert float((buf[..., cin:].float() - 3).abs().max()) == 0
     dw = ops.conv_wgrad(x, dy, stride)
     assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3)
     assert O.rel_l2(dw, w_ref.grad) <= F32_TOL

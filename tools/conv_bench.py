@@ -62,7 +62,11 @@ def main():
             tot["fprop"] += t
             line += f"| fprop {t * 1e3:7.1f} us {flops / t / 1e9:6.0f} TF/s "
         if "dgrad" in only:
-            t = timeit(lambda: ops.conv_dgrad(dy, wd, (h, h), s, out=dx))
+            ws2 = ops.pack_s2_dgrad_weights(wd) if s == 2 else None  # parity-stacked single launch (Cin <= 64)
+            if ws2 is not None:
+                t = timeit(lambda: ops.conv_dgrad_s2(dy, ws2, (h, h), out=dx))
+            else:
+                t = timeit(lambda: ops.conv_dgrad(dy, wd, (h, h), s, out=dx))
             tot["dgrad"] += t
             line += f"| dgrad {t * 1e3:7.1f} us {flops / t / 1e9:6.0f} TF/s "
         if "wgrad" in only:

@@ -58,6 +58,9 @@ SIGNATURES = {
     "b200unet_conv_fprop_partials": (c_int, [_I, _I, _I, _I]),
     "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
     "b200unet_conv_dgrad": (c_int, [POINTER(ConvDgradArgs), _P]),
+    "b200unet_conv_dgrad_s2_supported": (c_int, [_I, _I]),
+    "b200unet_pack_s2_dgrad_weights": (c_int, [_P, _P, _I, _I, _P]),
+    "b200unet_conv_dgrad_s2": (c_int, [POINTER(ConvDgradArgs), _P]),
     "b200unet_conv_wgrad_workspace": (c_int64, [_I, _I, _I, _I, _I, _I]),
     "b200unet_conv_wgrad": (c_int, [POINTER(ConvWgradArgs), _P]),
     "b200unet_conv_fprop_simt_partials": (c_int, [_I, _I]),
@@ -114,6 +117,7 @@ SIGNATURES = {
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
     "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_recon_head_bwd_workspace",
+    "b200unet_conv_dgrad_s2_supported",
     "b200unet_mse_workspace",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",
     "b200unet_in_backward_workspace", "b200unet_head_bwd_workspace", "b200unet_loss_workspace",

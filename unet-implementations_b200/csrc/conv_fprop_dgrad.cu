@@ -52,6 +52,8 @@ struct GConvParams {
   int cout;  // total N of the GEMM
   int tiles_per_cta;
   int stat_slots;  // P: partial-sum slots per image in `stats` ([N][P][cout][2])
+  int out_split;   // 0: one output map.  > 0: output channel block j*out_split.. goes to output map j (the parity
+                   // sub-lattices of the stride-2 data gradient stacked on N), channel coordinate relative to the block
   float* stats;
   long long* debug;  // optional [gridDim.x][8] cycle counters (developer instrumentation; NULL in production)
 };
@@ -59,10 +61,10 @@ struct GConvParams {
 struct GConvMaps {
   CUtensorMap src[kMaxLoads];  // one per patch load (the box height is part of the descriptor)
   CUtensorMap w;
-  CUtensorMap out;
+  CUtensorMap out[4];
 };
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
 struct GConvCfg {
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kASlotBytes = (kTH + 2) * kTW * kRowBytes;              // largest patch (10 rows)
@@ -70,7 +72,7 @@ struct GConvCfg {
   static constexpr int kBTileTx = BN * BK * 2;
   static constexpr int kBResBytes = 72 * 1024;                                 // resident weight slab budget
   static constexpr int kBBytes = B_RES ? kBResBytes : B_SLOTS * kBTileBytes;
-  static constexpr int kOC = (BN % 64 == 0) ? 64 : 32;                         // channels per TMA-store box
+  static constexpr int kOC = OC_ ? OC_ : ((BN % 64 == 0) ? 64 : 32);           // channels per TMA-store box
   static constexpr int kStageBufBytes = 128 * kOC * 2;                         // one staging buffer (two are used)
   static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBBytes + 2 * kStageBufBytes + 1024;
   static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
@@ -84,10 +86,10 @@ struct GConvCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
 __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_constant__ GConvMaps maps,
                                                                  const __grid_constant__ GConvParams p) {
-  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
   constexpr int kBBar = B_RES ? 1 : B_SLOTS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
@@ -392,7 +394,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (et == 0) {
-          tma_store_4d(&maps.out, stg, n0 + jb * OC, w0, h0, n_img);
+          const int ch = n0 + jb * OC;
+          if (p.out_split > 0) {
+            const int sel = ch / p.out_split;
+            tma_store_4d(&maps.out[sel], stg, ch - sel * p.out_split, w0, h0, n_img);
+          } else {
+            tma_store_4d(&maps.out[0], stg, ch, w0, h0, n_img);
+          }
           tma_store_commit();
         }
         if (do_stats) {
@@ -553,12 +561,12 @@ static long long* debug_buffer() {
   return state ? buf : nullptr;
 }
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
 static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStream_t st) {
   GConvParams p = p_in;
   p.debug = debug_buffer();
-  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
-  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, B_RES>;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
+  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -588,6 +596,8 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
 }
 
 static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, int BN, cudaStream_t st) {
+  if (p.out_split == 32 && BK == 64 && BN == 128) return launch_gconv<64, 128, 4, 4, false, 32>(maps, p, st);
+  if (p.out_split == 32 && BK == 32 && BN == 128) return launch_gconv<32, 128, 8, 4, false, 32>(maps, p, st);
   // resident weights: one N tile and the whole (taps x chunks) slab inside the 72 KB budget
   const int btile = ((BN * BK * 2 + 1023) / 1024) * 1024;
   const bool res = (p.cout == BN) && (BN <= 96) &&
@@ -667,7 +677,7 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
   if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
   if ((rc = make_weight_map(&maps.w, a->w, a->Cout, 9 * a->Cin, BK, BN))) return rc;
   const int OC = (BN % 64 == 0) ? 64 : 32;
-  if ((rc = make_act_map(&maps.out, static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->N, OH, OW, a->Cout, 1, 1, 0,
+  if ((rc = make_act_map(&maps.out[0], static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->N, OH, OW, a->Cout, 1, 1, 0,
                          0, OC, kTW, kTH)))
     return rc;
   return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
@@ -710,7 +720,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
     for (int kw = 0; kw < 3; ++kw)
       for (int kh = 2; kh >= 0; --kh) taps[n++] = TapSpec{0, 1 - kh, 1 - kw, (kh * 3 + kw) * a->Cout};  // row offsets 0,1,2
     if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
-    if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, kTW, kTH))) return rc;
+    if ((rc = make_act_map(&maps.out[0], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, kTW, kTH))) return rc;
     return dispatch_gconv(maps, p, BK, BN, st);
   }
   // stride 2: one launch per parity class (ph,pw) of the input pixel; ih = 2a + ph receives
@@ -736,9 +746,86 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
       for (int j = 0; j < nkw; ++j)
         for (int i = 0; i < nkh; ++i) taps[n++] = TapSpec{0, dhs[i], dws[j], (khs[i] * 3 + kws[j]) * a->Cout};
       if ((rc = build_loads(taps, n, lat, BK, &p, &maps))) return rc;
-      if ((rc = make_act_map(&maps.out, dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, OC, kTW, kTH)))
+      if ((rc = make_act_map(&maps.out[0], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, OC, kTW, kTH)))
         return rc;
       if ((rc = dispatch_gconv(maps, p, BK, BN, st))) return rc;
     }
   return 0;
+}
+
+// ------------------------------------------------------------------------------ stride-2 data gradient, parities on N
+// The four parity classes (ph, pw) of the input pixel of a stride-2 conv use 1, 2, 2 and 4 of the 9 taps; run as four
+// launches each is a narrow GEMM (N = Cin: 25 % of the tensor array for Cin = 32) that re-reads dy.  For Cin <= 64 the
+// classes are STACKED ON N instead: one launch over the coarse grid (a, b) with
+//     D[(a, b), (ph, pw, ci)] = sum over the 4 shifts (dh, dw) in {0,1}^2 and co of dy[a + dh, b + dw, co] * Ws[(ph, pw, ci)][(dh, dw)][co]
+// N = 4 * Cin (128 / 256: full tensor rate), dy read once; Ws holds W[kh(ph, dh)][kw(pw, dw)] where the class uses that
+// shift and zero elsewhere (7 of 16 blocks); the epilogue stores channel block (ph, pw) through that class's
+// sub-lattice tensor map.   dx[2a + ph] = sum_dh dy[a + dh] * W[kh]:  ph = 0: (dh = 0, kh = 1);  ph = 1: (dh = 0, kh = 2), (dh = 1, kh = 0).
+__global__ void pack_s2_dgrad_weights_kernel(const __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ ws, int Cin,
+                                             int Cout) {
+  // wt [Cin][3][3][Cout] -> ws [4*Cin][4][Cout]
+  const int64_t total = static_cast<int64_t>(4) * Cin * 4 * Cout;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % Cout);
+  int64_t r = i / Cout;
+  const int shift = static_cast<int>(r % 4);
+  r /= 4;
+  const int ci = static_cast<int>(r % Cin);
+  const int par = static_cast<int>(r / Cin);
+  const int ph = par >> 1, pw = par & 1, dh = shift >> 1, dw = shift & 1;
+  const int kh = ph == 0 ? (dh == 0 ? 1 : -1) : (dh == 0 ? 2 : 0);
+  const int kw = pw == 0 ? (dw == 0 ? 1 : -1) : (dw == 0 ? 2 : 0);
+  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+  if (kh >= 0 && kw >= 0) v = wt[((static_cast<int64_t>(ci) * 3 + kh) * 3 + kw) * Cout + co];
+  ws[i] = v;
+}
+
+extern "C" int b200unet_conv_dgrad_s2_supported(int Cin, int Cout) {
+  return (Cin == 32 || Cin == 64) && Cout % 32 == 0 && Cout > 0;
+}
+
+extern "C" int b200unet_pack_s2_dgrad_weights(const void* wt, void* ws, int Cin, int Cout, void* stream) {
+  B200_CHECK_ARG(wt && ws, "pack_s2_dgrad_weights: null pointer");
+  const int64_t total = static_cast<int64_t>(16) * Cin * Cout;
+  pack_s2_dgrad_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(wt), static_cast<__nv_bfloat16*>(ws), Cin, Cout);
+  B200_LAUNCH_CHECK("pack_s2_dgrad_weights_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_conv_dgrad_s2(const b200unet_conv_dgrad_args* a, void* stream) {
+  B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad_s2: null pointer");
+  B200_CHECK_ARG(a->stride == 2 && b200unet_conv_dgrad_s2_supported(a->Cin, a->Cout), "conv_dgrad_s2: needs stride 2, Cin in {32, 64}");
+  B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad_s2: pitches must be multiples of 8 elements");
+  B200_CHECK_ARG(a->H >= 2 && a->W >= 2, "conv_dgrad_s2: input must be at least 2x2");
+  const int OH = (a->H - 1) / 2 + 1, OW = (a->W - 1) / 2 + 1;
+  const int BK = pick_bk(a->Cout), BN = 4 * a->Cin;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);
+  const __nv_bfloat16* dx = static_cast<const __nv_bfloat16*>(a->dx);
+  GConvParams p{};
+  GConvMaps maps;
+  p.N = a->N;
+  p.OH = OH;  // the coarse grid: one tile pixel = one 2x2 block of dx
+  p.OW = OW;
+  p.tiles_w = ceil_div(OW, kTW);
+  p.tiles_h = ceil_div(OH, kTH);
+  p.cin = a->Cout;
+  p.cout = BN;
+  p.stats = nullptr;
+  p.out_split = a->Cin;
+  int rc;
+  SrcLattice lat[1] = {SrcLattice{dy, a->dy_pitch, a->N, OH, OW, a->Cout, 1, 1, 0, 0}};
+  TapSpec taps[4];
+  int n = 0;
+  for (int dw = 0; dw < 2; ++dw)
+    for (int dh = 0; dh < 2; ++dh) taps[n++] = TapSpec{0, dh, dw, (dh * 2 + dw) * a->Cout};
+  if ((rc = build_loads(taps, 4, lat, BK, &p, &maps))) return rc;
+  if ((rc = make_weight_map(&maps.w, a->wt, BN, 4 * a->Cout, BK, BN))) return rc;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw)
+      if ((rc = make_act_map(&maps.out[ph * 2 + pw], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, a->Cin, kTW,
+                             kTH)))
+        return rc;
+  return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
 }

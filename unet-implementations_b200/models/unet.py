@@ -280,6 +280,17 @@ class UNet(nn.Module):
         self._pack_cache[key] = (w._version, wf, None, w.data_ptr())
         return wf
 
+    def _packed_s2(self, conv: nn.Conv2d, wd: torch.Tensor):
+        """Parity-stacked dgrad pack of a stride-2 conv with Cin in {32, 64} (ops.pack_s2_dgrad_weights), cached on the
+        identity of the ordinary dgrad pack it is derived from; None when the path does not apply."""
+        key = ("s2", id(conv.weight))
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] is wd:
+            return hit[1]
+        ws = ops.pack_s2_dgrad_weights(wd)
+        self._pack_cache[key] = (wd, ws, None, None)
+        return ws
+
     def _packed_1x1(self, conv: nn.Conv2d, need_dgrad: bool, dtype):
         """A 1x1 conv on the 3x3 conv kernels: its weight as the centre tap of a zero 3x3 kernel (the fusion layer is
         2.4 GFLOP per image this way, 0.6 % of the step), packed and cached like _packed."""
@@ -660,7 +671,11 @@ def _backward_impl(ctx, dlogits):
         dx = None
         if not last:
             wd = rec["wd"]
-            dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
+            ws2 = model._packed_s2(conv, wd) if (stride == 2 and not simt and wd.dtype == BF16) else None
+            if ws2 is not None:
+                dx = ops.conv_dgrad_s2(dy, ws2, (xin.shape[1], xin.shape[2]))
+            else:
+                dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         if L["kind"] == "fusion":  # 1x1 weight = centre tap of the 3x3 gradient
             wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2].contiguous(), [xin, dy])
         else:

@@ -101,6 +101,29 @@ def conv_fprop(x, w_fprop, stride=1, out=None, want_stats=True, simt=False):
     return y, stats
 
 
+def pack_s2_dgrad_weights(w_dgrad):
+    """bf16 dgrad pack [Cin,3,3,Cout] of a stride-2 conv with Cin in {32, 64} -> the parity-stacked pack
+    [4*Cin,4,Cout] of b200unet_conv_dgrad_s2, or None when that path does not apply."""
+    cin, _, _, cout = w_dgrad.shape
+    if w_dgrad.dtype != BF16 or _lib.call("b200unet_conv_dgrad_s2_supported", cin, cout) != 1:
+        return None
+    ws = torch.empty((4 * cin, 4, cout), dtype=BF16, device=w_dgrad.device)
+    _lib.call("b200unet_pack_s2_dgrad_weights", _p(w_dgrad), _p(ws), cin, cout, _stream())
+    return ws
+
+
+def conv_dgrad_s2(dy, w_stacked, in_hw, out=None):
+    """Stride-2 data gradient with the parity classes stacked on N (one launch).  w_stacked from pack_s2_dgrad_weights."""
+    n, oh, ow, cout = dy.shape
+    cin = w_stacked.shape[0] // 4
+    h, w = in_hw
+    assert conv_out_hw(h, w, 2) == (oh, ow) and w_stacked.shape == (4 * cin, 4, cout) and dy.dtype == BF16
+    dx = out if out is not None else torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    a = ConvDgradArgs(_p(dy), pitch_of(dy), _p(w_stacked), _p(dx), pitch_of(dx), n, h, w, cin, cout, 2)
+    _lib.call("b200unet_conv_dgrad_s2", ctypes.byref(a), _stream())
+    return dx
+
+
 def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
     """Gradient wrt the conv input.  dy [N,OH,OW,Cout]; w_dgrad [Cin,3,3,Cout]; returns dx [N,H,W,Cin] bf16."""
     n, oh, ow, cout = dy.shape
