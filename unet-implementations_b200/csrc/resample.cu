@@ -62,9 +62,13 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
   Vec8<T>::st(o + op, v);
 }
 
-// Backward (gather): one thread = 8 channels of one INPUT pixel; separable: for each of the 4 output rows
-// 2ih-1 .. 2ih+2 (clamped) combine the 4 output columns 2iw-1 .. 2iw+2 (clamped) with (.25,.75,.75,.25), then the rows
-// with the same weights.  A clamped index is where the reference's edge-replicated tap landed, so its weight stays.
+// Backward (gather), separable: din[ih, iw] = sum_a wt[a] * hsum(row 2ih-1+a),  hsum(r) = sum_b wt[b] * d[r, 2iw-1+b],
+// wt = (.25, .75, .75, .25), indices clamped (a clamped index is where the reference's edge-replicated tap landed, so its
+// weight stays).  One thread = 8 channels of one input COLUMN and kUpRows consecutive input rows: it walks the
+// 2*kUpRows + 2 output rows once, forms each row's horizontal sum (4 loads) and adds it into the (at most two) input
+// rows that use it -- 4 + 4/kUpRows loads per input pixel instead of 16.
+constexpr int kUpRows = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dout, int64_t dp,
                                                               T* __restrict__ dx, int64_t xp, int H, int W,
@@ -73,38 +77,53 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
   const int iw = t >> c8shift;
   if (iw >= W) return;
   const int c0 = (t & (c8n - 1)) << 3;
-  const int ih = blockIdx.y, n = blockIdx.z;
+  const int ih0 = blockIdx.y * kUpRows, n = blockIdx.z;
   const int OH = 2 * H, OW = 2 * W;
   const T* b = dout + static_cast<int64_t>(n) * OH * OW * dp + c0;
-  int cols[4], rws[4];
+  int cols[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    int ow = 2 * iw - 1 + a, oh = 2 * ih - 1 + a;
+    const int ow = 2 * iw - 1 + a;
     cols[a] = ow < 0 ? 0 : (ow >= OW ? OW - 1 : ow);
-    rws[a] = oh < 0 ? 0 : (oh >= OH ? OH - 1 : oh);
   }
-  const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-  float acc[8];
+  float acc[kUpRows][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r = 0; r < kUpRows; ++r)
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const T* rp = b + static_cast<int64_t>(rws[a]) * OW * dp;
+    for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+  // output rows 2*ih0 - 1 .. 2*ih0 + 2*kUpRows (unclamped index k = 0 .. 2*kUpRows + 1); input row ih0 + r uses
+  // k = 2r .. 2r + 3 with weights (.25, .75, .75, .25)
+#pragma unroll
+  for (int k = 0; k < 2 * kUpRows + 2; ++k) {
+    const int oh_u = 2 * ih0 - 1 + k;
+    const int oh = oh_u < 0 ? 0 : (oh_u >= OH ? OH - 1 : oh_u);
+    const T* rp = b + static_cast<int64_t>(oh) * OW * dp;
     Vec8<T> raw[4];
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) raw[bb] = Vec8<T>::ldg(rp + static_cast<int64_t>(cols[bb]) * dp);
-    float d0[8], d1[8], d2[8], d3[8];
+    float d0[8], d1[8], d2[8], d3[8], hs[8];
     raw[0].unpack(d0);
     raw[1].unpack(d1);
     raw[2].unpack(d2);
     raw[3].unpack(d3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float hsum = 0.25f * (d0[j] + d3[j]) + 0.75f * (d1[j] + d2[j]);
-      acc[j] = fmaf(wt[a], hsum, acc[j]);
+    for (int j = 0; j < 8; ++j) hs[j] = 0.25f * (d0[j] + d3[j]) + 0.75f * (d1[j] + d2[j]);
+    // rows that use output row k: r = (k - a) / 2 for a in {0..3} with k - a even and 0 <= r < kUpRows
+#pragma unroll
+    for (int r = 0; r < kUpRows; ++r) {
+      const int a = k - 2 * r;
+      if (a >= 0 && a < 4) {
+        const float wgt = (a == 0 || a == 3) ? 0.25f : 0.75f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(wgt, hs[j], acc[r][j]);
+      }
     }
   }
-  Vec8<T>::st(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0, acc);
+#pragma unroll
+  for (int r = 0; r < kUpRows; ++r) {
+    const int ih = ih0 + r;
+    if (ih < H) Vec8<T>::st(dx + ((static_cast<int64_t>(n) * H + ih) * W + iw) * xp + c0, acc[r]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ layout
@@ -200,7 +219,7 @@ static int upsample_bwd_impl(const void* dout, int64_t dout_pitch, void* dx, int
   const int c8n = C / 8, sh = ilog2_exact(c8n);
   B200_CHECK_ARG(sh >= 0, "upsample2x_bwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_bwd: H and N must fit the grid");
-  upsample2x_bwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  upsample2x_bwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), ceil_div(H, kUpRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const T*>(dout), dout_pitch, static_cast<T*>(dx), dx_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_bwd_kernel");
   return 0;
