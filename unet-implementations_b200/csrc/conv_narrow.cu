@@ -14,8 +14,8 @@
 //     shuffle; lanes 0 and 31 are halo: a tile produces 4 x 30 outputs and tiles step by 30 columns (94 % of M);
 //   * the weights need no second packing: a 4-D tensor map over the packed [Cout][3][3][Cin] matrix delivers the
 //     [(co, kw) x BK] tile of one kh directly; the whole slab stays resident in shared memory.
-// Persistent CTAs (384 threads): warps 0..1 = TMA producers, warp 2 = TMEM owner + lean MMA-issuing thread, warps
-// 4..7 and 8..11 = TWO epilogue groups.  The epilogue (tcgen05.ld, 2 shuffles per channel, pack, staging, statistics)
+// Persistent CTAs (384 / 512 threads): warps 0..1 = TMA producers, warp 2 = TMEM owner + lean MMA-issuing thread,
+// warps 4.. = NG epilogue groups of four warps (3 for Cout = 32, 2 for Cout = 64: TMEM holds NG accumulators).  The epilogue (tcgen05.ld, 2 shuffles per channel, pack, staging, statistics)
 // is ~800 instructions per tile and warp with one warp per scheduler, i.e. several times the 6..12 MMAs of a tile
 // (ncu: tensor pipe 12 % busy with a single group), so consecutive tiles alternate between the groups: group g owns
 // TMEM accumulator buffer g, staging buffer g and its own named barriers / bulk-store groups.
@@ -27,7 +27,8 @@ namespace b200 {
 
 constexpr int kNcTH = 4, kNcTW = 32, kNcValidW = 30;  // tile rows / columns (lanes) / valid output columns
 constexpr int kNcPatchRows = kNcTH + 2;
-constexpr int kNcProducers = 2, kNcMmaWarp = 2, kNcEpiWarp0 = 4, kNcThreads = 32 * 12;
+constexpr int kNcProducers = 2, kNcMmaWarp = 2, kNcEpiWarp0 = 4;
+constexpr int kNcMaxGroups = 3;
 
 struct NConvParams {
   int N, H, W, tiles_w, tiles_h;
@@ -43,8 +44,9 @@ struct NConvMaps {
   CUtensorMap out;  // box (CO, 30, 4, 1)
 };
 
-template <int BK, int CO, int A_SLOTS>
+template <int BK, int CO, int A_SLOTS, int NG = 2>
 struct NConvCfg {
+  static constexpr int kThreads = 32 * (kNcEpiWarp0 + 4 * NG);
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kASlotBytes = kNcPatchRows * kNcTW * kRowBytes;  // 24 KB (BK = 64) / 12 KB
   static constexpr int kWin16 = (kNcTW * kRowBytes) >> 4;               // one image row of the patch, 16-byte units
@@ -52,10 +54,11 @@ struct NConvCfg {
   static constexpr int kBTileBytes = kNeff * kRowBytes;                 // [(co, kw) x BK] of one kh: 6 / 24 KB
   static constexpr int kBResBytes = 80 * 1024;
   static constexpr int kStageBufBytes = ((kNcTH * kNcValidW * CO * 2 + 1023) / 1024) * 1024;
-  static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBResBytes + 2 * kStageBufBytes + 1024;
+  static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBResBytes + NG * kStageBufBytes + 1024;
   static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
   static constexpr uint32_t kSbo = 8 * kRowBytes;
-  static constexpr uint32_t kTmemCols = (2 * kNeff <= 256) ? 256 : 512;
+  static constexpr uint32_t kTmemCols = (NG * kNeff <= 256) ? 256 : 512;
+  static_assert(NG * kNeff <= 512 && NG <= kNcMaxGroups, "accumulators must fit in TMEM");
   static_assert(kBTileBytes % 1024 == 0, "weight tiles must keep the swizzle alignment");
   static_assert(A_SLOTS % kNcProducers == 0, "each producer owns a fixed subset of slots");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -63,14 +66,14 @@ struct NConvCfg {
 
 // REV = false (fprop): patch window kh pairs with weight row kh, column tap kw of channel co at accumulator column
 // 3*co + kw.  REV = true (dgrad): both reversed (window kh pairs with weight row 2 - kh, the taps swap sides).
-template <int BK, int CO, int A_SLOTS, bool REV>
-__global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
-                                                                 const __grid_constant__ NConvParams p) {
-  using Cfg = NConvCfg<BK, CO, A_SLOTS>;
+template <int BK, int CO, int A_SLOTS, bool REV, int NG>
+__global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
+                                                                                 const __grid_constant__ NConvParams p) {
+  using Cfg = NConvCfg<BK, CO, A_SLOTS, NG>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
   __shared__ __align__(8) uint64_t b_full;
-  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[NG], tmem_empty_bar[NG];
   __shared__ uint32_t tmem_base_holder;
 
   const int warp = threadIdx.x >> 5;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
       mbar_init(&a_empty[s], 1);
     }
     mbar_init(&b_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NG; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);
     }
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
       uint32_t aslot = 0, aph = 0;
       int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));
+        const int buf = it % NG;  // accumulator (= epilogue group) of this tile
+        mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it / NG) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * Cfg::kNeff;
         uint32_t acc = 0;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
     auto flush = [&](int img) {
       const int first_tile = img * tiles_per_img;
       const int b0 = first_tile / p.tiles_per_cta;
-      const int slot = ((static_cast<int>(blockIdx.x) - b0) * 2 + g) * 4 + q;
+      const int slot = ((static_cast<int>(blockIdx.x) - b0) * NG + g) * 4 + q;
       float* dst = p.stats + (static_cast<size_t>(img) * p.stat_slots + slot) * CO * 2;
       if (CO == 64) {
         *reinterpret_cast<float4*>(dst + (2 * lane) * 2) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -205,13 +208,13 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
       }
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     };
-    // tile coordinates advance incrementally (two tiles per step): no divisions in the loop
+    // tile coordinates advance incrementally (NG tiles per step): no divisions in the loop
     int tile = tile_lo + g;
     int n_img = tile / tiles_per_img;
     int tw = (tile - n_img * tiles_per_img) / p.tiles_h;
     int th = tile - n_img * tiles_per_img - tw * p.tiles_h;
     uint32_t ph = 0;  // parity of this group's accumulator barrier
-    for (; tile < tile_hi; tile += 2, ph ^= 1) {
+    for (; tile < tile_hi; tile += NG, ph ^= 1) {
       const int h0 = th * kNcTH, w0 = tw * kNcValidW;
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
@@ -222,22 +225,23 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
       if (et == 0) tma_store_wait_read_all();  // this group's previous store has read the staging buffer
       named_bar_sync(bar_a, 128);
 #pragma unroll 1
-      for (int c0 = 0; c0 < CO; c0 += 32) {
-        // 32 output channels = 96 accumulator columns (co, kw) starting at 3 * c0
-        uint32_t v[96];
-        tmem_ld_32x32(t_addr + 3 * c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld_32x32(t_addr + 3 * c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tmem_ld_32x32(t_addr + 3 * c0 + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      for (int c0 = 0; c0 < CO; c0 += 16) {
+        // 16 output channels = 48 accumulator columns (co, kw) starting at 3 * c0 (48 live registers: the kernel has to
+        // fit 128 registers per thread with three epilogue groups)
+        uint32_t v[48];
+        tmem_ld_32x16(t_addr + 3 * c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld_32x16(t_addr + 3 * c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_32x16(t_addr + 3 * c0 + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
         tmem_ld_wait();
-        if (c0 + 32 >= CO) {
+        if (c0 + 16 >= CO) {
           // all TMEM reads of this warp are done: hand the accumulator back before the arithmetic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
         }
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float o[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -250,25 +254,16 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
           pk[j] = pack_bf16x2(o[0], o[1]);
         }
         if (col_ok) {
-          if (CO == 64) {
-            const uint32_t base = smem_u32(stg) + srow * 128;
+          // two 16-byte chunks (8 channels each) of this pixel's staging row, swizzled like the TMA store box
+          const uint32_t base = smem_u32(stg) + srow * (CO * 2);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int cj = (c0 >> 3) + i;
-              const uint32_t addr = base + (((cj ^ (srow & 7)) & 7) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
-                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
-                           : "memory");
-            }
-          } else {
-            const uint32_t base = smem_u32(stg) + srow * 64;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t addr = base + (((i ^ ((srow >> 1) & 3)) & 3) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
-                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
-                           : "memory");
-            }
+          for (int i = 0; i < 2; ++i) {
+            const int cj = (c0 >> 3) + i;
+            const uint32_t addr = (CO == 64) ? base + (((cj ^ (srow & 7)) & 7) << 4)
+                                             : base + (((cj ^ ((srow >> 1) & 3)) & 3) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                         "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                         : "memory");
           }
         }
       }
@@ -314,7 +309,7 @@ __global__ void __launch_bounds__(kNcThreads, 1) nconv_kernel(const __grid_const
         acc[3] += s2b;
       }
       // next tile of this group
-      th += 2;
+      th += NG;
       while (th >= p.tiles_h) {
         th -= p.tiles_h;
         if (++tw == p.tiles_w) {
@@ -349,7 +344,7 @@ static NConvGrid nconv_grid(int N, int H, int W) {
   g.tiles_per_cta = static_cast<int>(ceil_div64(total, num_sms()));
   if (g.tiles_per_cta < 1) g.tiles_per_cta = 1;
   g.grid = static_cast<int>(ceil_div64(total, g.tiles_per_cta));
-  g.stat_slots = 8 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);  // (CTA, group, lane quarter)
+  g.stat_slots = 4 * kNcMaxGroups * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);  // (CTA, group, lane quarter)
   return g;
 }
 
@@ -362,11 +357,11 @@ bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
 
 int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
 
-template <int BK, int CO, int A_SLOTS, bool REV>
+template <int BK, int CO, int A_SLOTS, bool REV, int NG>
 static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& g, cudaStream_t st) {
   // p.stat_slots = P of the caller's buffer (>= this kernel's own slot count); unused slots stay zero
-  using Cfg = NConvCfg<BK, CO, A_SLOTS>;
-  auto kern = nconv_kernel<BK, CO, A_SLOTS, REV>;
+  using Cfg = NConvCfg<BK, CO, A_SLOTS, NG>;
+  auto kern = nconv_kernel<BK, CO, A_SLOTS, REV, NG>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -374,7 +369,7 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
   }
   if (p.stats)
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
-  kern<<<g.grid, kNcThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  kern<<<g.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("nconv_kernel");
   return 0;
 }
@@ -413,10 +408,13 @@ int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* ou
                              BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)))
       return rc;
   }
-#define NC(bk, co, as) \
+  // epilogue groups: two everywhere.  Three (possible for Cout = 32: three accumulators of 96 columns, 128 registers)
+  // were measured equal to two (301 / 265 us fprop / dgrad at 512^2 x 32): with two groups the epilogue is no longer
+  // the bottleneck; the kernel then runs at ~16 B/cycle/SM of L2<->SM traffic (3.9 TB/s of DRAM) for both widths
+#define NC(bk, co, as, ng) \
   if (BK == bk && n_channels == co) \
-    return rev ? launch_nconv<bk, co, as, true>(maps, p, g, st) : launch_nconv<bk, co, as, false>(maps, p, g, st);
-  NC(64, 64, 4) NC(64, 32, 4) NC(32, 64, 8) NC(32, 32, 8)
+    return rev ? launch_nconv<bk, co, as, true, ng>(maps, p, g, st) : launch_nconv<bk, co, as, false, ng>(maps, p, g, st);
+  NC(64, 64, 4, 2) NC(64, 32, 4, 2) NC(32, 64, 8, 2) NC(32, 32, 8, 2)
 #undef NC
   return set_error(kErrUnsupported, "no nconv instantiation for BK=%d N=%d", BK, n_channels);
 }
