@@ -52,6 +52,7 @@ struct GConvParams {
   int cout;  // total N of the GEMM
   int tiles_per_cta;
   int stat_slots;  // P: partial-sum slots per image in `stats` ([N][P][cout][2])
+  int mt;          // M tiles (of 128 pixels = 8 image rows) per CTA tile: 1, or 2 when the kernel shares each weight tile
   int out_split;   // 0: one output map.  > 0: output channel block j*out_split.. goes to output map j (the parity
                    // sub-lattices of the stride-2 data gradient stacked on N), channel coordinate relative to the block
   float* stats;
@@ -64,10 +65,14 @@ struct GConvMaps {
   CUtensorMap out[4];
 };
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
+// MT = 2: the CTA tile is TWO vertically adjacent 8 x 16 patches (one 18-row TMA patch per column shift, two
+// accumulators); every streamed weight tile feeds both, which halves the dominant L2->SM stream of the N = 128 layers
+// (their MMA thread waited on weight tiles 35 % of the time: 204 -> 126 KB per 128 pixels and chunk).
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
 struct GConvCfg {
   static constexpr int kRowBytes = BK * 2;
-  static constexpr int kASlotBytes = (kTH + 2) * kTW * kRowBytes;              // largest patch (10 rows)
+  static constexpr int kTHc = kTH * MT;                                         // image rows of a CTA tile
+  static constexpr int kASlotBytes = (kTHc + 2) * kTW * kRowBytes;             // largest patch (10 / 18 rows)
   static constexpr int kBTileBytes = ((BN * BK * 2 + 1023) / 1024) * 1024;     // one [BN x BK] weight tile
   static constexpr int kBTileTx = BN * BK * 2;
   static constexpr int kBResBytes = 72 * 1024;                                 // resident weight slab budget
@@ -77,8 +82,9 @@ struct GConvCfg {
   static constexpr int kSmemBytes = A_SLOTS * kASlotBytes + kBBytes + 2 * kStageBufBytes + 1024;
   static constexpr uint32_t kSwz = (BK == 64) ? kSwz128 : kSwz64;
   static constexpr uint32_t kSbo = 8 * kRowBytes;
-  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                        : (2 * BN <= 256) ? 256 : 512;  // two accumulator buffers
+  static constexpr uint32_t kTmemCols = (2 * MT * BN <= 32) ? 32 : (2 * MT * BN <= 64) ? 64 : (2 * MT * BN <= 128) ? 128
+                                        : (2 * MT * BN <= 256) ? 256 : 512;  // two buffers of MT accumulators
+  static_assert(2 * MT * BN <= 512, "accumulators must fit in TMEM");
   // producers: A loads go to warps [0, NA), B tiles (streaming) to warps [4 - NB, 4)
   static constexpr int NA = B_RES ? ((A_SLOTS % 4 == 0) ? 4 : (A_SLOTS % 2 == 0) ? 2 : 1)
                                   : ((A_SLOTS % 2 == 0) ? 2 : 1);
@@ -86,10 +92,10 @@ struct GConvCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
 __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_constant__ GConvMaps maps,
                                                                  const __grid_constant__ GConvParams p) {
-  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT>;
   constexpr int kBBar = B_RES ? 1 : B_SLOTS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
           // column-major tile order inside an image: the next tile is the one BELOW, so the 2 halo rows of its
           // patches are still in L2 (row-major order re-fetched them from HBM: +25 % DRAM reads at 256^2 / 512^2)
           const int tw = t_in / p.tiles_h;
-          const int h0 = (t_in - tw * p.tiles_h) * kTH, w0 = tw * kTW;
+          const int h0 = (t_in - tw * p.tiles_h) * Cfg::kTHc, w0 = tw * kTW;
           const long long g0 = static_cast<long long>(it) * loads_per_tile;  // global load index of this tile's first
           int i = (warp - static_cast<int>(g0 % Cfg::NA) + Cfg::NA) % Cfg::NA;
           for (; i < loads_per_tile; i += Cfg::NA) {
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // epilogue drained this buffer
         if (p.debug) dbg_te += clock64() - t0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem = tmem_base + buf * (MT * BN);
         uint32_t acc = 0;
         uint32_t b_res = b_lo0;  // next resident weight tile
         for (int c = 0; c < chunks; ++c) {
@@ -265,10 +271,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
               }
               const uint32_t at_lo = a_lo + (s1 ? static_cast<uint32_t>(t) : static_cast<uint32_t>(p.loads[l].rowoff[t])) * kWin;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16_lean(d_tmem, at_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
-                acc = 1;
+              for (int mt = 0; mt < MT; ++mt) {  // the same weight tile for every M tile: window 8 image rows further down
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_lean(d_tmem + mt * BN, at_lo + mt * (kTH * kWin) + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc | k);
               }
+              acc = 1;
               if (!B_RES) {
                 umma_commit_u32(b_empty0 + bslot * 8);
                 if (++bslot == B_SLOTS) { bslot = 0; bph ^= 1; }
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       const int n_img = m_tile / tiles_per_img;
       const int t_in = m_tile - n_img * tiles_per_img;
       const int tw = t_in / p.tiles_h;
-      const int h0 = (t_in - tw * p.tiles_h) * kTH, w0 = tw * kTW;
+      const int h0_tile = (t_in - tw * p.tiles_h) * Cfg::kTHc, w0 = tw * kTW;
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
@@ -350,7 +358,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       if (p.debug) dbg_tf += clock64() - t0;
       tc_fence_after();
 #pragma unroll 1
-      for (int jb = 0; jb < BN / OC; ++jb, sbuf ^= 1) {
+      for (int mtj = 0; mtj < MT * (BN / OC); ++mtj, sbuf ^= 1) {
+        const int mt = mtj / (BN / OC), jb = mtj - mt * (BN / OC);  // M tile of the CTA tile, channel block
+        const int h0 = h0_tile + mt * kTH;
         // the store issued two groups ago read this staging buffer
         if (et == 0) tma_store_wait_read_1();
         named_bar_sync(1, 128);
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
 #pragma unroll 1
         for (int c0 = jb * OC; c0 < (jb + 1) * OC; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c0, v);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + c0, v);
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
             }
           }
         }
-        if (jb == BN / OC - 1) {
+        if (mtj == MT * (BN / OC) - 1) {
           // this warp's TMEM reads of the tile are complete: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -479,7 +489,12 @@ struct SrcLattice {
   int N, H, W, C, hstep, wstep, hoff, woff;
 };
 
-// Group taps that share (lattice, column shift) into patch loads and build one tensor map per load.
+// M tiles per CTA tile (GConvCfg MT): 2 for the streamed-weight N = 128 configuration with 128-byte rows.
+static int pick_mt(int BK, int BN, int cout_total, int out_split) {
+  return (BK == 64 && BN == 128 && out_split == 0 && cout_total >= 128) ? 2 : 1;
+}
+
+// Group taps that share (lattice, column shift) into patch loads and build one tensor map per load.  p->mt must be set.
 static int build_loads(const TapSpec* taps, int ntaps, const SrcLattice* lat, int BK, GConvParams* p, GConvMaps* maps) {
   p->nloads = 0;
   p->ntaps_total = ntaps;
@@ -498,7 +513,7 @@ static int build_loads(const TapSpec* taps, int ntaps, const SrcLattice* lat, in
     ALoad& L = p->loads[p->nloads];
     L.dh = dh_min;
     L.dw = taps[i].dw;
-    L.rows = kTH + (dh_max - dh_min);
+    L.rows = kTH * p->mt + (dh_max - dh_min);
     L.ntaps = n;
     for (int k = 0; k < n; ++k) {
       used[idx[k]] = true;
@@ -523,9 +538,9 @@ struct GConvGrid {
 };
 // Persistent grid: contiguous tile ranges of equal length; P = partial-sum slots per image = 4 (lane quarters) x the
 // largest number of CTAs whose range can intersect one image.
-static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN) {
+static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN, int mt = 1) {
   GConvGrid g;
-  const long long per_img = static_cast<long long>(ceil_div(OW, kTW)) * ceil_div(OH, kTH) * (cout / BN);
+  const long long per_img = static_cast<long long>(ceil_div(OW, kTW)) * ceil_div(OH, kTH * mt) * (cout / BN);
   const long long total = per_img * N;
   const int sms = num_sms();
   g.tiles_per_cta = static_cast<int>(ceil_div64(total, sms));
@@ -542,6 +557,8 @@ int conv_stat_slots(int N, int OH, int OW, int Cout) {
   int slots = gconv_grid(N, OH, OW, Cout, BN64).stat_slots;
   const int s32 = gconv_grid(N, OH, OW, Cout, BN32).stat_slots;
   if (s32 > slots) slots = s32;
+  const int s2 = gconv_grid(N, OH, OW, Cout, BN64, 2).stat_slots;  // the two-M-tile variant of the N = 128 layers
+  if (s2 > slots) slots = s2;
   if (Cout == 32 || Cout == 64) {
     const int sn = nconv_stat_slots(N, OH, OW);
     if (sn > slots) slots = sn;
@@ -561,19 +578,20 @@ static long long* debug_buffer() {
   return state ? buf : nullptr;
 }
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
 static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStream_t st) {
   GConvParams p = p_in;
   p.debug = debug_buffer();
-  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
-  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_>;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT>;
+  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT>;
+  if (p.mt != MT) return set_error(kErrInvalid, "gconv: tile height multiplier %d does not match the kernel (%d)", p.mt, MT);
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * p.N * (p.cout / BN);
-  GConvGrid gg = gconv_grid(p.N, p.OH, p.OW, p.cout, BN);
+  GConvGrid gg = gconv_grid(p.N, p.OH, p.OW, p.cout, BN, MT);
   const int grid = gg.grid;
   p.tiles_per_cta = gg.tiles_per_cta;
   p.stat_slots = conv_stat_slots(p.N, p.OH, p.OW, p.cout);  // P of the caller's buffer (>= gg.stat_slots)
@@ -606,6 +624,7 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
   if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
   GC(64, 256, 3, 4, false)
   GC(64, 192, 4, 4, false)
+  if (BK == 64 && BN == 128 && !res && p.mt == 2) return launch_gconv<64, 128, 3, 4, false, 0, 2>(maps, p, st);
   GC(64, 128, 4, 4, false)
   GC(64, 64, 6, 4, false)
   GC(64, 64, 4, 1, true)
@@ -647,8 +666,9 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
   p.N = a->N;
   p.OH = OH;
   p.OW = OW;
+  p.mt = pick_mt(BK, BN, a->Cout, 0);
   p.tiles_w = ceil_div(OW, kTW);
-  p.tiles_h = ceil_div(OH, kTH);
+  p.tiles_h = ceil_div(OH, kTH * p.mt);
   p.cin = a->Cin;
   p.cout = a->Cout;
   p.stats = a->stats;
@@ -709,8 +729,9 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
     p.N = a->N;
     p.OH = a->H;
     p.OW = a->W;
+    p.mt = pick_mt(BK, BN, a->Cin, 0);
     p.tiles_w = ceil_div(a->W, kTW);
-    p.tiles_h = ceil_div(a->H, kTH);
+    p.tiles_h = ceil_div(a->H, kTH * p.mt);
     p.cin = a->Cout;
     p.cout = a->Cin;
     p.stats = nullptr;
@@ -733,8 +754,9 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
       p.N = a->N;
       p.OH = Hs;
       p.OW = Ws;
+      p.mt = pick_mt(BK, BN, a->Cin, 0);
       p.tiles_w = ceil_div(Ws, kTW);
-      p.tiles_h = ceil_div(Hs, kTH);
+      p.tiles_h = ceil_div(Hs, kTH * p.mt);
       p.cin = a->Cout;
       p.cout = a->Cin;
       p.stats = nullptr;
@@ -808,6 +830,7 @@ extern "C" int b200unet_conv_dgrad_s2(const b200unet_conv_dgrad_args* a, void* s
   p.N = a->N;
   p.OH = OH;  // the coarse grid: one tile pixel = one 2x2 block of dx
   p.OW = OW;
+  p.mt = 1;
   p.tiles_w = ceil_div(OW, kTW);
   p.tiles_h = ceil_div(OH, kTH);
   p.cin = a->Cout;
