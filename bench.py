@@ -247,6 +247,11 @@ def main():
     for _ in range(args.warmup):
         step(image_d, mask_d)
     torch.cuda.synchronize()
+    # clock / power sampling starts before the untimed pre-steps (NVML's first queries are slow and share driver locks
+    # with kernel launches) and runs through all timed regions
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     # untimed pre-steps: the step runs at the 1 kW power cap and the SM clock it sustains drifts for the first second;
     # all three timed regions below then see the same steady state (these steps are not counted in `warmup`)
     presteps = 30
@@ -273,12 +278,33 @@ def main():
         return ms
 
     # ---- resident-input throughput (+ live per-entry-point timing for the roofline)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = _lib.call("b200unet_launch_count")
-    ms = timed(lambda: step(image_d, mask_d), args.steps)
-    launches = _lib.call("b200unet_launch_count") - l0
+    # per-step events inside the region expose a one-off stall (another tenant's driver call, a host hiccup): a region
+    # whose slowest step is > 1.5x its median step is measured once more and the fact is recorded in the JSON line
+    remeasured = None
+    for attempt in range(2):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        counter = [0]
+
+        def marked_step():
+            if counter[0] == 0:
+                marks[0].record()
+            step(image_d, mask_d)
+            counter[0] += 1
+            marks[counter[0]].record()
+
+        if sampler and attempt == 0:
+            sampler.samples.clear()  # keep only what was sampled during the timed regions
+        l0 = _lib.call("b200unet_launch_count")
+        ms = timed(marked_step, args.steps)
+        launches = _lib.call("b200unet_launch_count") - l0
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+        worst, med = per[-1], per[len(per) // 2]
+        flag = torch.tensor([1.0 if worst > 1.5 * med else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() == 0.0 or attempt == 1:
+            break
+        remeasured = f"first attempt had a {worst:.1f} ms step against a median of {med:.1f} ms ({ms / args.steps:.2f} ms/step); measured again"
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -438,6 +464,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "remeasured": remeasured,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
