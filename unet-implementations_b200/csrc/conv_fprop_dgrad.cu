@@ -490,8 +490,14 @@ struct SrcLattice {
 };
 
 // M tiles per CTA tile (GConvCfg MT): 2 for the streamed-weight N = 128 configuration with 128-byte rows.
-static int pick_mt(int BK, int BN, int cout_total, int out_split) {
-  return (BK == 64 && BN == 128 && out_split == 0 && cout_total >= 128) ? 2 : 1;
+static bool gconv_weights_resident(int BK, int BN, int cout_total, int k_channels, int ntaps) {
+  // one N tile and the whole (taps x chunks) slab inside the 72 KB budget
+  const int btile = ((BN * BK * 2 + 1023) / 1024) * 1024;
+  return (cout_total == BN) && (BN <= 96) && (static_cast<long long>(ntaps) * (k_channels / BK) * btile <= 72 * 1024);
+}
+static int pick_mt(int BK, int BN, int cout_total, int k_channels, int ntaps) {
+  if (BK != 64 || gconv_weights_resident(BK, BN, cout_total, k_channels, ntaps)) return 1;
+  return BN == 128 ? 2 : (BN == 64 ? 4 : 1);  // as many accumulators as TMEM holds twice (double buffering)
 }
 
 // Group taps that share (lattice, column shift) into patch loads and build one tensor map per load.  p->mt must be set.
@@ -557,7 +563,7 @@ int conv_stat_slots(int N, int OH, int OW, int Cout) {
   int slots = gconv_grid(N, OH, OW, Cout, BN64).stat_slots;
   const int s32 = gconv_grid(N, OH, OW, Cout, BN32).stat_slots;
   if (s32 > slots) slots = s32;
-  const int s2 = gconv_grid(N, OH, OW, Cout, BN64, 2).stat_slots;  // the two-M-tile variant of the N = 128 layers
+  const int s2 = gconv_grid(N, OH, OW, Cout, BN64, BN64 == 64 ? 4 : 2).stat_slots;  // the multi-M-tile variants
   if (s2 > slots) slots = s2;
   if (Cout == 32 || Cout == 64) {
     const int sn = nconv_stat_slots(N, OH, OW);
@@ -617,14 +623,13 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
   if (p.out_split == 32 && BK == 64 && BN == 128) return launch_gconv<64, 128, 4, 4, false, 32>(maps, p, st);
   if (p.out_split == 32 && BK == 32 && BN == 128) return launch_gconv<32, 128, 8, 4, false, 32>(maps, p, st);
   // resident weights: one N tile and the whole (taps x chunks) slab inside the 72 KB budget
-  const int btile = ((BN * BK * 2 + 1023) / 1024) * 1024;
-  const bool res = (p.cout == BN) && (BN <= 96) &&
-                   (static_cast<long long>(p.ntaps_total) * (p.cin / BK) * btile <= 72 * 1024);
+  const bool res = gconv_weights_resident(BK, BN, p.cout, p.cin, p.ntaps_total);
 #define GC(bk, bn, as, bs, r) \
   if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
   GC(64, 256, 3, 4, false)
   GC(64, 192, 4, 4, false)
   if (BK == 64 && BN == 128 && !res && p.mt == 2) return launch_gconv<64, 128, 3, 4, false, 0, 2>(maps, p, st);
+  if (BK == 64 && BN == 64 && !res && p.mt == 4) return launch_gconv<64, 64, 2, 4, false, 0, 4>(maps, p, st);
   GC(64, 128, 4, 4, false)
   GC(64, 64, 6, 4, false)
   GC(64, 64, 4, 1, true)
@@ -666,7 +671,7 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
   p.N = a->N;
   p.OH = OH;
   p.OW = OW;
-  p.mt = pick_mt(BK, BN, a->Cout, 0);
+  p.mt = pick_mt(BK, BN, a->Cout, a->Cin, 9);
   p.tiles_w = ceil_div(OW, kTW);
   p.tiles_h = ceil_div(OH, kTH * p.mt);
   p.cin = a->Cin;
@@ -729,7 +734,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
     p.N = a->N;
     p.OH = a->H;
     p.OW = a->W;
-    p.mt = pick_mt(BK, BN, a->Cin, 0);
+    p.mt = pick_mt(BK, BN, a->Cin, a->Cout, 9);
     p.tiles_w = ceil_div(a->W, kTW);
     p.tiles_h = ceil_div(a->H, kTH * p.mt);
     p.cin = a->Cout;
@@ -754,7 +759,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
       p.N = a->N;
       p.OH = Hs;
       p.OW = Ws;
-      p.mt = pick_mt(BK, BN, a->Cin, 0);
+      p.mt = pick_mt(BK, BN, a->Cin, a->Cout, (ph ? 2 : 1) * (pw ? 2 : 1));
       p.tiles_w = ceil_div(Ws, kTW);
       p.tiles_h = ceil_div(Hs, kTH * p.mt);
       p.cin = a->Cout;
