@@ -273,9 +273,14 @@ def main():
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
+            every = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            timed.per_rank_ms = [round(v.item() / k, 3) for v in every]  # per step, for the record
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         return ms
+
+    timed.per_rank_ms = None
 
     # ---- resident-input throughput (+ live per-entry-point timing for the roofline)
     # per-step events inside the region expose a one-off stall (another tenant's driver call, a host hiccup): a region
@@ -296,6 +301,7 @@ def main():
             sampler.samples.clear()  # keep only what was sampled during the timed regions
         l0 = _lib.call("b200unet_launch_count")
         ms = timed(marked_step, args.steps)
+        per_rank_resident = timed.per_rank_ms
         launches = _lib.call("b200unet_launch_count") - l0
         per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
         worst, med = per[-1], per[len(per) // 2]
@@ -465,6 +471,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "remeasured": remeasured,
+            "per_rank_ms_per_step": per_rank_resident,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
