@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "conv_common.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -36,6 +37,7 @@ struct NConvParams {
     int tiles_per_cta;
   int stat_slots;
   float* stats;
+  long long* debug;  // optional [gridDim.x][8] cycle counters (developer instrumentation; NULL in production)
 };
 
 struct NConvMaps {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
             tma_load_4d(smem_b + (c * 3 + kh) * Cfg::kBTileBytes, &maps.w, &b_full, c * BK, 0, kh, 0);
       }
       tma_prefetch_desc(&maps.src);
+      long long dbg_wait = 0, dbg_issue = 0;
       int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int n_img = tile / tiles_per_img;
@@ -133,10 +136,20 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
           const long long g = g0 + c;
           const int slot = static_cast<int>(g % A_SLOTS);
           const uint32_t ph = static_cast<uint32_t>((g / A_SLOTS) & 1);
+          const long long t0 = p.debug ? clock64() : 0;
           mbar_wait(&a_empty[slot], ph ^ 1);
+          const long long t1 = p.debug ? clock64() : 0;
           mbar_expect_tx(&a_full[slot], Cfg::kASlotBytes);
           tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src, &a_full[slot], c * BK, w0 - 1, h0 - 1, n_img);
+          if (p.debug) {
+            dbg_wait += t1 - t0;
+            dbg_issue += clock64() - t1;
+          }
         }
+      }
+      if (p.debug && warp == 0) {
+        p.debug[blockIdx.x * 8 + 0] = dbg_wait;
+        p.debug[blockIdx.x * 8 + 1] = dbg_issue;
       }
     }
   } else if (warp == kNcMmaWarp) {
@@ -150,16 +163,22 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
       mbar_wait(&b_full, 0);
       tc_fence_after();
       uint32_t aslot = 0, aph = 0;
+      long long dbg_te = 0, dbg_af = 0;
+      const long long dbg_m0 = clock64();
       int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int buf = it % NG;  // accumulator (= epilogue group) of this tile
+        const long long t0 = p.debug ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it / NG) & 1) ^ 1));
+        if (p.debug) dbg_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * Cfg::kNeff;
         uint32_t acc = 0;
         uint32_t b_c = b_lo0;
         for (int c = 0; c < chunks; ++c, b_c += 3 * kBTile16) {
+          const long long t1 = p.debug ? clock64() : 0;
           mbar_wait_u32(a_full0 + aslot * 8, aph);
+          if (p.debug) dbg_af += clock64() - t1;
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + aslot * kASlot16;
 #pragma unroll
@@ -176,6 +195,11 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
           if (++aslot == A_SLOTS) { aslot = 0; aph ^= 1; }
         }
         umma_commit(&tmem_full_bar[buf]);
+      }
+      if (p.debug) {
+        p.debug[blockIdx.x * 8 + 2] = dbg_te;
+        p.debug[blockIdx.x * 8 + 3] = dbg_af;
+        p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_m0;
       }
     }
   } else if (warp >= kNcEpiWarp0) {
@@ -214,16 +238,24 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
     int tw = (tile - n_img * tiles_per_img) / p.tiles_h;
     int th = tile - n_img * tiles_per_img - tw * p.tiles_h;
     uint32_t ph = 0;  // parity of this group's accumulator barrier
+    long long dbg_tf = 0, dbg_sw = 0;
+    const long long dbg_e0 = clock64();
     for (; tile < tile_hi; tile += NG, ph ^= 1) {
       const int h0 = th * kNcTH, w0 = tw * kNcValidW;
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
       }
+      const long long t0 = p.debug ? clock64() : 0;
       mbar_wait(&tmem_full_bar[g], ph);
+      const long long t1 = p.debug ? clock64() : 0;
       tc_fence_after();
       if (et == 0) tma_store_wait_read_all();  // this group's previous store has read the staging buffer
       named_bar_sync(bar_a, 128);
+      if (p.debug) {
+        dbg_tf += t1 - t0;
+        dbg_sw += clock64() - t1;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < CO; c0 += 16) {
         // 16 output channels = 48 accumulator columns (co, kw) starting at 3 * c0 (48 live registers: the kernel has to
@@ -320,6 +352,11 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
     }
     if (do_stats && acc_img >= 0) flush(acc_img);
     if (et == 0) tma_store_wait_all();
+    if (p.debug && et == 0 && g == 0) {
+      p.debug[blockIdx.x * 8 + 5] = dbg_tf;
+      p.debug[blockIdx.x * 8 + 6] = clock64() - dbg_e0;
+      p.debug[blockIdx.x * 8 + 7] = dbg_sw;
+    }
   }
 
   tc_fence_before();
@@ -357,6 +394,17 @@ bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
 
 int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
 
+static long long* nconv_debug_buffer() {
+  static long long* buf = nullptr;
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("B200UNET_GCONV_DEBUG");
+    state = (e && e[0] == '1') ? 1 : 0;
+    if (state) cudaMalloc(&buf, 148 * 8 * sizeof(long long));
+  }
+  return state ? buf : nullptr;
+}
+
 template <int BK, int CO, int A_SLOTS, bool REV, int NG>
 static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& g, cudaStream_t st) {
   // p.stat_slots = P of the caller's buffer (>= this kernel's own slot count); unused slots stay zero
@@ -369,8 +417,21 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
   }
   if (p.stats)
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
+  p.debug = nconv_debug_buffer();
+  if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
   kern<<<g.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("nconv_kernel");
+  if (p.debug) {  // developer instrumentation (B200UNET_GCONV_DEBUG=1): per-tile cycle counts of CTA 0
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.debug, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long tiles = g.tiles_per_cta, gt = (tiles + NG - 1) / NG;
+    fprintf(stderr,
+            "nconv<%d,%d,%d,%d,%d> K %d tiles/CTA %lld | per tile: producer0 wait %lld issue %lld | mma total %lld "
+            "wait_tmem_empty %lld wait_a_full %lld | epilogue group 0 per ITS tile: total %lld wait_tmem_full %lld store+bar %lld\n",
+            BK, CO, A_SLOTS, (int)REV, NG, p.cin, tiles, h[0] / tiles, h[1] / tiles, h[4] / tiles, h[2] / tiles, h[3] / tiles,
+            h[6] / gt, h[5] / gt, h[7] / gt);
+  }
   return 0;
 }
 
