@@ -9,6 +9,14 @@ namespace b200 {
 // box) / ~200 cycles (2-D box) on B200 regardless of the box size (tools/micro/tma_rate.cu), so ONE producer thread
 // caps a CTA at one box per ~420 cycles (< 20 B/cycle/SM with 8 KB boxes): the loads are spread over four producer
 // warps (one elected lane each), which issue concurrently.
+// Per-role cycle counters in the conv kernels (B200UNET_GCONV_DEBUG=1 prints them) exist only in a build with
+// -DB200UNET_INSTRUMENT (make INSTRUMENT=1): even predicated-off clock reads in the single MMA-issuing thread cost
+// ~15 % on the short-tile kernels.
+#ifdef B200UNET_INSTRUMENT
+constexpr bool kInstr = true;
+#else
+constexpr bool kInstr = false;
+#endif
 constexpr int kProducerWarps = 4;                 // warps 0..3: TMA producers
 constexpr int kMmaWarp = 4;                       // warp 4: TMEM owner + single-thread MMA issuer
 constexpr int kEpiWarp0 = 5;                      // warps 5..8: epilogue (TMEM lane quarter = warp % 4)

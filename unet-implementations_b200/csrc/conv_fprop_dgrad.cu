@@ -179,18 +179,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
             const int c = i / p.nloads;
             const int l = i - c * p.nloads;
             const ALoad& L = p.loads[l];
-            const long long t0 = p.debug ? clock64() : 0;
+            const long long t0 = (kInstr && p.debug) ? clock64() : 0;
             mbar_wait(&a_empty[slot], ph ^ 1);
-            const long long t1 = p.debug ? clock64() : 0;
+            const long long t1 = (kInstr && p.debug) ? clock64() : 0;
             mbar_expect_tx(&a_full[slot], L.rows * kTW * Cfg::kRowBytes);
             tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src[l], &a_full[slot], c * BK, w0 + L.dw, h0 + L.dh, n_img);
-            if (p.debug) {
+            if (kInstr && p.debug) {
               dbg_wait += t1 - t0;
               dbg_issue += clock64() - t1;
             }
           }
         }
-        if (p.debug && warp == 0) {
+        if (kInstr && p.debug && warp == 0) {
           p.debug[blockIdx.x * 8 + 0] = dbg_wait;
           p.debug[blockIdx.x * 8 + 1] = dbg_issue;
         }
@@ -237,13 +237,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       }
       const bool s1 = p.s1 != 0;
       uint32_t aslot = 0, aph = 0, bslot = 0, bph = 0;  // ring positions and phase parities (run across tiles)
-      long long dbg_te = 0, dbg_af = 0, dbg_total0 = clock64();
+      long long dbg_te = 0, dbg_af = 0, dbg_total0 = kInstr ? clock64() : 0;
       int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int buf = it & 1;
-        const long long t0 = p.debug ? clock64() : 0;
+        const long long t0 = (kInstr && p.debug) ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // epilogue drained this buffer
-        if (p.debug) dbg_te += clock64() - t0;
+        if (kInstr && p.debug) dbg_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (MT * BN);
         uint32_t acc = 0;
@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
           const int nl = s1 ? 3 : p.nloads;
 #pragma unroll 3
           for (int l = 0; l < nl; ++l) {
-            const long long t1 = p.debug ? clock64() : 0;
+            const long long t1 = (kInstr && p.debug) ? clock64() : 0;
             mbar_wait_u32(a_full0 + aslot * 8, aph);
-            if (p.debug) dbg_af += clock64() - t1;
+            if (kInstr && p.debug) dbg_af += clock64() - t1;
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + aslot * kASlot16;
             const int nt = s1 ? 3 : p.loads[l].ntaps;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         }
         umma_commit(&tmem_full_bar[buf]);
       }
-      if (p.debug) {
+      if (kInstr && p.debug) {
         p.debug[blockIdx.x * 8 + 2] = dbg_te;
         p.debug[blockIdx.x * 8 + 3] = dbg_af;
         p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_total0;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       }
     };
     int it = 0;
-    long long dbg_tf = 0, dbg_e0 = clock64();
+    long long dbg_tf = 0, dbg_e0 = kInstr ? clock64() : 0;
     uint32_t sbuf = 0;  // staging buffer toggle (runs across tiles)
     for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
       const int m_tile = tile / n_tiles;
@@ -353,9 +353,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       // rows of this warp's quarter that lie inside the image (rows below / right of it hold TMA zero-fill garbage
       // of the accumulator and must not enter the statistics)
       const int buf = it & 1;
-      const long long t0 = p.debug ? clock64() : 0;
+      const long long t0 = (kInstr && p.debug) ? clock64() : 0;
       mbar_wait(&tmem_full_bar[buf], static_cast<uint32_t>((it >> 1) & 1));
-      if (p.debug) dbg_tf += clock64() - t0;
+      if (kInstr && p.debug) dbg_tf += clock64() - t0;
       tc_fence_after();
 #pragma unroll 1
       for (int mtj = 0; mtj < MT * (BN / OC); ++mtj, sbuf ^= 1) {
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     }
     if (do_stats && acc_img >= 0) flush(acc_img);
     if (et == 0) tma_store_wait_all();
-    if (p.debug && et == 0) {
+    if (kInstr && p.debug && et == 0) {
       p.debug[blockIdx.x * 8 + 5] = dbg_tf;
       p.debug[blockIdx.x * 8 + 6] = clock64() - dbg_e0;
     }
@@ -602,10 +602,10 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
   p.tiles_per_cta = gg.tiles_per_cta;
   p.stat_slots = conv_stat_slots(p.N, p.OH, p.OW, p.cout);  // P of the caller's buffer (>= gg.stat_slots)
   if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * p.cout * 2 * sizeof(float), st));
-  if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
+  if (kInstr && p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
   kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("gconv_kernel");
-  if (p.debug) {
+  if (kInstr && p.debug) {
     long long h[8];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.debug, sizeof(h), cudaMemcpyDeviceToHost);

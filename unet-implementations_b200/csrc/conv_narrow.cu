@@ -136,18 +136,18 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
           const long long g = g0 + c;
           const int slot = static_cast<int>(g % A_SLOTS);
           const uint32_t ph = static_cast<uint32_t>((g / A_SLOTS) & 1);
-          const long long t0 = p.debug ? clock64() : 0;
+          const long long t0 = (kInstr && p.debug) ? clock64() : 0;
           mbar_wait(&a_empty[slot], ph ^ 1);
-          const long long t1 = p.debug ? clock64() : 0;
+          const long long t1 = (kInstr && p.debug) ? clock64() : 0;
           mbar_expect_tx(&a_full[slot], Cfg::kASlotBytes);
           tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src, &a_full[slot], c * BK, w0 - 1, h0 - 1, n_img);
-          if (p.debug) {
+          if (kInstr && p.debug) {
             dbg_wait += t1 - t0;
             dbg_issue += clock64() - t1;
           }
         }
       }
-      if (p.debug && warp == 0) {
+      if (kInstr && p.debug && warp == 0) {
         p.debug[blockIdx.x * 8 + 0] = dbg_wait;
         p.debug[blockIdx.x * 8 + 1] = dbg_issue;
       }
@@ -164,21 +164,21 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
       tc_fence_after();
       uint32_t aslot = 0, aph = 0;
       long long dbg_te = 0, dbg_af = 0;
-      const long long dbg_m0 = clock64();
+      const long long dbg_m0 = kInstr ? clock64() : 0;
       int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
         const int buf = it % NG;  // accumulator (= epilogue group) of this tile
-        const long long t0 = p.debug ? clock64() : 0;
+        const long long t0 = (kInstr && p.debug) ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], static_cast<uint32_t>(((it / NG) & 1) ^ 1));
-        if (p.debug) dbg_te += clock64() - t0;
+        if (kInstr && p.debug) dbg_te += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * Cfg::kNeff;
         uint32_t acc = 0;
         uint32_t b_c = b_lo0;
         for (int c = 0; c < chunks; ++c, b_c += 3 * kBTile16) {
-          const long long t1 = p.debug ? clock64() : 0;
+          const long long t1 = (kInstr && p.debug) ? clock64() : 0;
           mbar_wait_u32(a_full0 + aslot * 8, aph);
-          if (p.debug) dbg_af += clock64() - t1;
+          if (kInstr && p.debug) dbg_af += clock64() - t1;
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + aslot * kASlot16;
 #pragma unroll
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
         }
         umma_commit(&tmem_full_bar[buf]);
       }
-      if (p.debug) {
+      if (kInstr && p.debug) {
         p.debug[blockIdx.x * 8 + 2] = dbg_te;
         p.debug[blockIdx.x * 8 + 3] = dbg_af;
         p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_m0;
@@ -239,20 +239,20 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
     int th = tile - n_img * tiles_per_img - tw * p.tiles_h;
     uint32_t ph = 0;  // parity of this group's accumulator barrier
     long long dbg_tf = 0, dbg_sw = 0;
-    const long long dbg_e0 = clock64();
+    const long long dbg_e0 = kInstr ? clock64() : 0;
     for (; tile < tile_hi; tile += NG, ph ^= 1) {
       const int h0 = th * kNcTH, w0 = tw * kNcValidW;
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
       }
-      const long long t0 = p.debug ? clock64() : 0;
+      const long long t0 = (kInstr && p.debug) ? clock64() : 0;
       mbar_wait(&tmem_full_bar[g], ph);
-      const long long t1 = p.debug ? clock64() : 0;
+      const long long t1 = (kInstr && p.debug) ? clock64() : 0;
       tc_fence_after();
       if (et == 0) tma_store_wait_read_all();  // this group's previous store has read the staging buffer
       named_bar_sync(bar_a, 128);
-      if (p.debug) {
+      if (kInstr && p.debug) {
         dbg_tf += t1 - t0;
         dbg_sw += clock64() - t1;
       }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
     }
     if (do_stats && acc_img >= 0) flush(acc_img);
     if (et == 0) tma_store_wait_all();
-    if (p.debug && et == 0 && g == 0) {
+    if (kInstr && p.debug && et == 0 && g == 0) {
       p.debug[blockIdx.x * 8 + 5] = dbg_tf;
       p.debug[blockIdx.x * 8 + 6] = clock64() - dbg_e0;
       p.debug[blockIdx.x * 8 + 7] = dbg_sw;
@@ -418,10 +418,10 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
   if (p.stats)
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
   p.debug = nconv_debug_buffer();
-  if (p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
+  if (kInstr && p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
   kern<<<g.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
   B200_LAUNCH_CHECK("nconv_kernel");
-  if (p.debug) {  // developer instrumentation (B200UNET_GCONV_DEBUG=1): per-tile cycle counts of CTA 0
+  if (kInstr && p.debug) {  // developer instrumentation (B200UNET_GCONV_DEBUG=1): per-tile cycle counts of CTA 0
     long long h[8];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.debug, sizeof(h), cudaMemcpyDeviceToHost);

@@ -79,13 +79,17 @@ __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(const float* __r
 __global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks, const float* __restrict__ class_w,
                                      int dynamic, float weight_ce, float weight_dice, float smooth,
                                      float* __restrict__ loss_out, float* __restrict__ tables, int N) {
-  // one block; thread (b*12 + v) reduces value v of image b
+  // one block of 32 warps; warp w reduces values i = w, w + 32, ... (value v of image b): lanes stride over the
+  // partials, fixed-order shuffle tree (the serial version took 46 us on the critical path between forward and backward)
   extern __shared__ double sred[];  // [N][12]
-  for (int i = threadIdx.x; i < N * kLossVals; i += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < N * kLossVals; i += nwarps) {
     const int b = i / kLossVals, v = i - b * kLossVals;
     double s = 0.0;
-    for (int k = 0; k < blocks; ++k) s += part[(static_cast<int64_t>(b) * blocks + k) * kLossVals + v];
-    sred[i] = s;
+    for (int k = lane; k < blocks; k += 32) s += part[(static_cast<int64_t>(b) * blocks + k) * kLossVals + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sred[i] = s;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -305,16 +309,22 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
 }
 
-__global__ void head_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int KC, int K,
-                                         float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= KC + K) return;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += partial[static_cast<int64_t>(b) * (KC + K) + i];
-  if (i < KC) dw[i] = static_cast<float>(s);
-  else db[i - KC] = static_cast<float>(s);
+// one block of 32 warps: warp w reduces values i = w, w + 32, ... over the `blocks` partial rows (lanes stride over the
+// rows, fixed-order shuffle tree)
+__global__ void __launch_bounds__(1024) head_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int KC,
+                                                                  int K, float* __restrict__ dw, float* __restrict__ db) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < KC + K; i += 32) {
+    double s = 0.0;
+    for (int b = lane; b < blocks; b += 32) s += partial[static_cast<int64_t>(b) * (KC + K) + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (i < KC) dw[i] = static_cast<float>(s);
+      else db[i - KC] = static_cast<float>(s);
+    }
+  }
 }
-
 
 // ------------------------------------------------------------------------------- reconstruction head + MSE (autoencoder)
 // AE_pretrained/reconstruction/models/autoencoder.py:374-387: reconstruction_output = Conv2d(32 -> 3, 3x3, pad 1, bias)
@@ -420,7 +430,7 @@ extern "C" int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target
   B200_LAUNCH_CHECK("loss_fwd_kernel");
   const size_t smem = static_cast<size_t>(N) * kLossVals * sizeof(double);
   B200_CHECK_ARG(smem <= 48 * 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
-  loss_finalize_kernel<<<1, 256, smem, st>>>(workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
+  loss_finalize_kernel<<<1, 1024, smem, st>>>(workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
                                              loss_out, tables, N);
   B200_LAUNCH_CHECK("loss_finalize_kernel");
   return 0;
@@ -476,7 +486,7 @@ static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pit
   head_bwd_kernel<T, 32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
                                                     static_cast<T*>(dz), dz_pitch, workspace, N, HW);
   B200_LAUNCH_CHECK("head_bwd_kernel");
-  head_bwd_finalize_kernel<<<1, 128, 0, st>>>(workspace, blocks, K * C, K, dw, db);
+  head_bwd_finalize_kernel<<<1, 1024, 0, st>>>(workspace, blocks, K * C, K, dw, db);
   B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
   return 0;
 }

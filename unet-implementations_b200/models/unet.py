@@ -610,14 +610,17 @@ def _backward_impl(ctx, dlogits):
         side = model._side_streams.get(main.device.index)
         if side is None:
             side = model._side_streams[main.device.index] = torch.cuda.Stream(device=main.device)
-    pending = []  # [(param, gradient tensor, event recorded on the side stream)]
+    pending = []  # [(param, gradient tensor, event recorded on the side stream, tensors the side stream reads)]
 
     def collect():
         while pending:
-            p, g, ev = pending.pop(0)
+            p, g, ev, _inputs = pending.pop(0)
             main.wait_event(ev)
             g.record_stream(main)
             put(p, lambda: g)
+            # _inputs (main-stream tensors the side stream was reading) are released only here, after the main stream
+            # has been ordered behind the side-stream work: no record_stream on the big activations, whose deferred
+            # reuse made the caching allocator grow and stall now and then (100 ms steps in bench.py)
 
     def wgrad_async(p: Optional[nn.Parameter], fn, inputs):
         """Run fn() (a weight-gradient launch) for parameter p: on the side stream after everything enqueued on the
@@ -632,10 +635,7 @@ def _backward_impl(ctx, dlogits):
             g = fn()
             ev = torch.cuda.Event()
             ev.record(side)
-        for t in inputs:  # main-stream tensors read by the side stream: keep their memory until it is done
-            if t is not None:
-                t.record_stream(side)
-        pending.append((p, g, ev))
+        pending.append((p, g, ev, list(inputs)))
 
     dskip: Dict[int, torch.Tensor] = {}  # encoder level -> gradient view of the skip half of dcat
     dz2 = None
