@@ -193,6 +193,27 @@ int b200unet_conv_dgrad_s2_supported(int Cin, int Cout);
 int b200unet_pack_s2_dgrad_weights(const void* wt, void* ws, int Cin, int Cout, void* stream);
 int b200unet_conv_dgrad_s2(const b200unet_conv_dgrad_args* a, void* stream);
 
+/* Consumers with the producer's apply pass fused in.  When the activated tensor z = leaky_relu(a*y + b) of a unit has
+ * ONE consumer -- the 2x upsample of the next decoder stage (unet.py:219-225) or the segmentation head (unet.py:430) --
+ * that consumer reads the unit's RAW conv output y with its folded affine (a, b from b200unet_in_finalize) and applies
+ * InstanceNorm/LeakyReLU/dropout on the fly: b200unet_in_apply is skipped for the unit and z is never written or
+ * re-read.  head_norm_bwd recomputes z from y for dW.  Same arguments as the plain entry points plus (a, b, slope). */
+int b200unet_upsample2x_norm_fwd(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, void* out,
+                                 int64_t out_pitch, int N, int H, int W, int C, void* stream);
+int b200unet_head_norm_fwd(const void* y, int64_t y_pitch, const float* a, const float* b, float slope, const float* w,
+                           const float* bias, float* logits_nchw, int N, int64_t HW, int C, int K, void* stream);
+int b200unet_head_norm_bwd(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a, const float* b,
+                           float slope, const float* w, void* dz, int64_t dz_pitch, float* dw, float* db,
+                           float* workspace, int64_t workspace_bytes, int N, int64_t HW, int C, int K, void* stream);
+int b200unet_upsample2x_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                                     void* out, int64_t out_pitch, int N, int H, int W, int C, void* stream);
+int b200unet_head_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                               const float* w, const float* bias, float* logits_nchw, int N, int64_t HW, int C, int K,
+                               void* stream);
+int b200unet_head_norm_bwd_f32(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a, const float* b,
+                               float slope, const float* w, void* dz, int64_t dz_pitch, float* dw, float* db,
+                               float* workspace, int64_t workspace_bytes, int N, int64_t HW, int C, int K, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * fp32 verification mode (`UNet(...).precision = "fp32"`): the same operators with fp32 NHWC activations, fp32
  * packed weights and fp32 arithmetic -- north_star's "1e-4 in fp32 mode".  Argument structs, layouts and

@@ -217,3 +217,34 @@ def test_full_size_layer_properties():
     z = ops.in_apply(y1, a, b, 1.0).float()  # slope 1 = identity activation
     assert float((z.mean(dim=(1, 2)) - beta).abs().max()) <= 5e-3
     assert float((z.var(dim=(1, 2), unbiased=False).sqrt() - gamma).abs().max()) <= 5e-3
+
+
+def test_consumers_with_the_apply_pass_fused_in():
+    """upsample2x / head with (a, b, slope): the producer's InstanceNorm+LeakyReLU(+dropout) apply pass runs inside its
+    single consumer.  Against the unfused sequence on fp32 CPU math of the same bf16 raw conv output."""
+    from unet_implementations_b200 import ops
+    n, h, w, c = 2, 12, 20, 32
+    y, y_ref = rand_act(n, h, w, c, seed=21, scale=1.5)
+    g = torch.Generator().manual_seed(22)
+    a = (torch.rand(n, c, generator=g) + 0.3) * torch.where(torch.rand(n, c, generator=g) < 0.2, 0.0, 1.0)  # dropped channels: a = b = 0
+    b = torch.randn(n, c, generator=g) * (a != 0)
+    z_ref = F.leaky_relu(y_ref * a[:, None, None, :] + b[:, None, None, :], 0.01)
+    ad, bd = a.cuda().contiguous(), b.cuda().contiguous()
+    # upsample
+    out = torch.zeros(n, 2 * h, 2 * w, c + 32, dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x(y, out[..., :c], norm=(ad, bd, 0.01))
+    up_ref = F.interpolate(z_ref.permute(0, 3, 1, 2), size=(2 * h, 2 * w), mode="bilinear", align_corners=False)
+    assert O.rel_l2(out[..., :c].float(), up_ref.permute(0, 2, 3, 1)) <= BF16_TOL
+    assert float(out[..., c:].float().abs().max()) == 0.0
+    # head forward / backward
+    wt = torch.randn(3, c, 1, 1, generator=g).requires_grad_(True)
+    bias = torch.randn(3, generator=g).requires_grad_(True)
+    zr = z_ref.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    lr = F.conv2d(zr, wt, bias)
+    logits = ops.head_forward(y, wt.detach().cuda(), bias.detach().cuda(), norm=(ad, bd, 0.01))
+    assert O.rel_l2(logits, lr) <= F32_TOL
+    dl = torch.randn(n, 3, h, w, generator=g)
+    lr.backward(dl)
+    dz, dw, db = ops.head_backward(dl.cuda(), y, wt.detach().cuda(), norm=(ad, bd, 0.01))
+    assert O.rel_l2(dz.float(), zr.grad.permute(0, 2, 3, 1)) <= BF16_TOL
+    assert O.rel_l2(dw, wt.grad) <= F32_TOL and O.rel_l2(db, bias.grad) <= F32_TOL

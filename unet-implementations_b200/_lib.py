@@ -99,6 +99,12 @@ SIGNATURES = {
     "b200unet_head_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_nchw_f32_to_nhwc_f32": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
     "b200unet_image_to_nhwc32_bf16": (c_int, [_P, _P, _I, _I, _L, _P]),
+    "b200unet_upsample2x_norm_fwd": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_upsample2x_norm_fwd_f32": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _I, _P]),
+    "b200unet_head_norm_fwd": (c_int, [_P, _L, _P, _P, _F, _P, _P, _P, _I, _L, _I, _I, _P]),
+    "b200unet_head_norm_fwd_f32": (c_int, [_P, _L, _P, _P, _F, _P, _P, _P, _I, _L, _I, _I, _P]),
+    "b200unet_head_norm_bwd": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
+    "b200unet_head_norm_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_preprocess_u8": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _P]),
     "b200unet_sgd_max_tensors": (c_int, []),
     "b200unet_sgd_nesterov_step": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _P]),

@@ -189,16 +189,25 @@ constexpr int kHeadMaxC = 64;
 constexpr int kHeadMaxK = 4;
 
 // one thread per pixel: logits[k] = b[k] + sum_c W[k][c] * z[c]
+// Optional fused producer (na, nb): z is then the RAW conv output of the last unit and the activation
+// leaky_relu(na[n,c] * y + nb[n,c]) is applied on the fly (that unit's apply pass never runs; backward recomputes it).
 template <typename T, int C, int K>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, int64_t zp,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        float* __restrict__ logits, int64_t HW) {
+                                                        float* __restrict__ logits, int64_t HW,
+                                                        const float* __restrict__ na, const float* __restrict__ nb,
+                                                        float slope) {
   __shared__ float ws[K][C];
   __shared__ float bs[K];
+  __shared__ float sa[C], sb[C];
+  const int n = blockIdx.y;
   for (int i = threadIdx.x; i < K * C; i += 256) ws[i / C][i % C] = w[i];
   if (threadIdx.x < K) bs[threadIdx.x] = bias[threadIdx.x];
+  if (na && threadIdx.x < C) {
+    sa[threadIdx.x] = na[n * C + threadIdx.x];
+    sb[threadIdx.x] = nb[n * C + threadIdx.x];
+  }
   __syncthreads();
-  const int n = blockIdx.y;
   const int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (px >= HW) return;
   const T* src = z + (static_cast<int64_t>(n) * HW + px) * zp;
@@ -209,6 +218,13 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, 
   for (int j = 0; j < C / 8; ++j) {
     float zf[8];
     Vec8<T>::ldg(src + 8 * j).unpack(zf);
+    if (na) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(sa[8 * j + i], zf[i], sb[8 * j + i]);
+        zf[i] = t > 0.f ? t : t * slope;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -226,7 +242,9 @@ template <typename T, int C, int K>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ z,
                                                         int64_t zp, const float* __restrict__ w,
                                                         T* __restrict__ dz, int64_t dzp,
-                                                        float* __restrict__ partial, int N, int64_t HW) {
+                                                        float* __restrict__ partial, int N, int64_t HW,
+                                                        const float* __restrict__ na, const float* __restrict__ nb,
+                                                        float slope) {
   constexpr int C8N = C / 8;
   static_assert(C8N >= 1 && C8N <= 32 && (C8N & (C8N - 1)) == 0, "C/8 must be a power of two <= 32");
   __shared__ float red[8][K * C + K];
@@ -266,6 +284,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       if (g >= total) break;
       float zf[8], o[8];
       zv[u].unpack(zf);
+      if (na) {  // z = leaky_relu(na * y + nb), recomputed from the raw conv output (per-image affine: L1-resident)
+        const int n = static_cast<int>(g / HW);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0)), a1 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0)), b1 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0) + 1);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(av[i], zf[i], bv[i]);
+          zf[i] = t > 0.f ? t : t * slope;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) ab[k] += d[u][k];
 #pragma unroll
@@ -449,13 +479,14 @@ extern "C" int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target
 
 template <typename T>
 static int head_fwd_impl(const void* z, int64_t z_pitch, const float* w, const float* bias, float* logits_nchw, int N,
-                         int64_t HW, int C, int K, void* stream) {
+                         int64_t HW, int C, int K, void* stream, const float* na = nullptr, const float* nb = nullptr,
+                         float slope = 0.f) {
   B200_CHECK_ARG(z && w && bias && logits_nchw, "head_fwd: null pointer");
   B200_CHECK_ARG(z_pitch % 8 == 0, "head_fwd: pitch must be a multiple of 8");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_fwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
   dim3 grid((unsigned)ceil_div64(HW, 256), N);
   head_fwd_kernel<T, 32, 3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(z), z_pitch, w,
-                                                                                  bias, logits_nchw, HW);
+                                                                                  bias, logits_nchw, HW, na, nb, slope);
   B200_LAUNCH_CHECK("head_fwd_kernel");
   return 0;
 }
@@ -476,7 +507,8 @@ extern "C" int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K) 
 template <typename T>
 static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
                          int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
-                         int64_t HW, int C, int K, void* stream) {
+                         int64_t HW, int C, int K, void* stream, const float* na = nullptr, const float* nb = nullptr,
+                         float slope = 0.f) {
   B200_CHECK_ARG(dlogits_nchw && z && w && dz && dw && db && workspace, "head_bwd: null pointer");
   B200_CHECK_ARG(z_pitch % 8 == 0 && dz_pitch % 8 == 0, "head_bwd: pitches must be multiples of 8");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_bwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
@@ -484,7 +516,7 @@ static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pit
   B200_CHECK_ARG(workspace_bytes >= b200unet_head_bwd_workspace(N, HW, C, K), "head_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   head_bwd_kernel<T, 32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
-                                                    static_cast<T*>(dz), dz_pitch, workspace, N, HW);
+                                                    static_cast<T*>(dz), dz_pitch, workspace, N, HW, na, nb, slope);
   B200_LAUNCH_CHECK("head_bwd_kernel");
   head_bwd_finalize_kernel<<<1, 1024, 0, st>>>(workspace, blocks, K * C, K, dw, db);
   B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
@@ -591,3 +623,35 @@ extern "C" int b200unet_mse_bwd(const float* a, const float* b, const float* gra
   B200_LAUNCH_CHECK("mse_bwd_kernel");
   return 0;
 }
+
+// Head with the last unit's InstanceNorm/LeakyReLU/dropout apply fused in: y is that unit's RAW conv output, (a, b) its
+// folded per-(n, c) affine (b200unet_in_finalize), slope the LeakyReLU slope.
+extern "C" int b200unet_head_norm_fwd(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                                      const float* w, const float* bias, float* logits_nchw, int N, int64_t HW, int C,
+                                      int K, void* stream) {
+  B200_CHECK_ARG(a && b, "head_norm_fwd: null affine");
+  return head_fwd_impl<__nv_bfloat16>(y, y_pitch, w, bias, logits_nchw, N, HW, C, K, stream, a, b, slope);
+}
+extern "C" int b200unet_head_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                                          const float* w, const float* bias, float* logits_nchw, int N, int64_t HW,
+                                          int C, int K, void* stream) {
+  B200_CHECK_ARG(a && b, "head_norm_fwd: null affine");
+  return head_fwd_impl<float>(y, y_pitch, w, bias, logits_nchw, N, HW, C, K, stream, a, b, slope);
+}
+extern "C" int b200unet_head_norm_bwd(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
+                                      const float* b, float slope, const float* w, void* dz, int64_t dz_pitch, float* dw,
+                                      float* db, float* workspace, int64_t workspace_bytes, int N, int64_t HW, int C,
+                                      int K, void* stream) {
+  B200_CHECK_ARG(a && b, "head_norm_bwd: null affine");
+  return head_bwd_impl<__nv_bfloat16>(dlogits_nchw, y, y_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N,
+                                      HW, C, K, stream, a, b, slope);
+}
+extern "C" int b200unet_head_norm_bwd_f32(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
+                                          const float* b, float slope, const float* w, void* dz, int64_t dz_pitch,
+                                          float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
+                                          int64_t HW, int C, int K, void* stream) {
+  B200_CHECK_ARG(a && b, "head_norm_bwd: null affine");
+  return head_bwd_impl<float>(dlogits_nchw, y, y_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N, HW, C, K,
+                              stream, a, b, slope);
+}
+

@@ -17,10 +17,14 @@ namespace b200 {
 // through L1 (each input element is shared by 9 threads of the same / adjacent warps); interpolation along w first,
 // then along h (the association of ATen's upsample_bilinear2d).  grid (ceil(W*C/8 / 256), H, N): no integer division
 // by runtime values.
+// Optional fused producer: with (na, nb) the input is a RAW conv output y and every loaded value becomes
+// leaky_relu(na[n,c] * y + nb[n,c]) first -- the InstanceNorm/LeakyReLU/dropout apply pass of the layer that feeds the
+// upsample (its only consumer), so the activated low-resolution tensor is never written or re-read.
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ x, int64_t xp,
                                                               T* __restrict__ out, int64_t op, int H, int W,
-                                                              int c8n, int c8shift) {
+                                                              int c8n, int c8shift, const float* __restrict__ na,
+                                                              const float* __restrict__ nb, float slope) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int iw = t >> c8shift;  // c8n is a power of two on this path
   if (iw >= W) return;
@@ -31,6 +35,15 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
   const T* b = x + static_cast<int64_t>(n) * H * W * xp + c0;
   const int rows[3] = {hm, ih, hp};
   float L[3][8], R[3][8];  // per source row: the two output columns 2iw, 2iw+1
+  float ra[8], rb[8];
+  if (na) {
+    const int C = c8n << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ra[j] = na[n * C + c0 + j];
+      rb[j] = nb[n * C + c0 + j];
+    }
+  }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const T* rp = b + static_cast<int64_t>(rows[r]) * W * xp;
@@ -38,6 +51,15 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
     Vec8<T>::ldg(rp + static_cast<int64_t>(wm) * xp).unpack(a);
     Vec8<T>::ldg(rp + static_cast<int64_t>(iw) * xp).unpack(c);
     Vec8<T>::ldg(rp + static_cast<int64_t>(wp) * xp).unpack(d);
+    if (na) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t0 = fmaf(ra[j], a[j], rb[j]), t1 = fmaf(ra[j], c[j], rb[j]), t2 = fmaf(ra[j], d[j], rb[j]);
+        a[j] = t0 > 0.f ? t0 : t0 * slope;
+        c[j] = t1 > 0.f ? t1 : t1 * slope;
+        d[j] = t2 > 0.f ? t2 : t2 * slope;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       L[r][j] = 0.75f * c[j] + 0.25f * a[j];
@@ -199,14 +221,14 @@ static int ilog2_exact(int v) {
 
 template <typename T>
 static int upsample_fwd_impl(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H, int W, int C,
-                             void* stream) {
+                             void* stream, const float* na = nullptr, const float* nb = nullptr, float slope = 0.f) {
   B200_CHECK_ARG(x && out, "upsample2x_fwd: null pointer");
   B200_CHECK_ARG(C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0, "upsample2x_fwd: C and pitches must be multiples of 8");
   const int c8n = C / 8, sh = ilog2_exact(c8n);
   B200_CHECK_ARG(sh >= 0, "upsample2x_fwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_fwd: H and N must fit the grid");
   upsample2x_fwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), H, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const T*>(x), x_pitch, static_cast<T*>(out), out_pitch, H, W, c8n, sh);
+      static_cast<const T*>(x), x_pitch, static_cast<T*>(out), out_pitch, H, W, c8n, sh, na, nb, slope);
   B200_LAUNCH_CHECK("upsample2x_fwd_kernel");
   return 0;
 }
@@ -232,6 +254,17 @@ extern "C" int b200unet_upsample2x_fwd(const void* x, int64_t x_pitch, void* out
 extern "C" int b200unet_upsample2x_fwd_f32(const void* x, int64_t x_pitch, void* out, int64_t out_pitch, int N, int H,
                                            int W, int C, void* stream) {
   return upsample_fwd_impl<float>(x, x_pitch, out, out_pitch, N, H, W, C, stream);
+}
+extern "C" int b200unet_upsample2x_norm_fwd(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
+                                            void* out, int64_t out_pitch, int N, int H, int W, int C, void* stream) {
+  B200_CHECK_ARG(a && b, "upsample2x_norm_fwd: null affine");
+  return upsample_fwd_impl<__nv_bfloat16>(y, y_pitch, out, out_pitch, N, H, W, C, stream, a, b, slope);
+}
+extern "C" int b200unet_upsample2x_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b,
+                                                float slope, void* out, int64_t out_pitch, int N, int H, int W, int C,
+                                                void* stream) {
+  B200_CHECK_ARG(a && b, "upsample2x_norm_fwd: null affine");
+  return upsample_fwd_impl<float>(y, y_pitch, out, out_pitch, N, H, W, C, stream, a, b, slope);
 }
 extern "C" int b200unet_upsample2x_bwd(const void* dout, int64_t dout_pitch, void* dx, int64_t dx_pitch, int N, int H,
                                        int W, int C, void* stream) {

@@ -455,7 +455,10 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
 
     saved = []  # per layer dict
     cur = None  # current NHWC bf16 activation
-    for L in layers:
+    # (a, b, slope) when `cur` is a RAW conv output whose apply pass is fused into its single consumer -- the 2x
+    # upsample of the next decoder stage or the 1x1 head -- instead of being run (and written) on its own
+    cur_norm = None
+    for li_f, L in enumerate(layers):
         conv, norm, act, drop = L["unit"]
         cin, cout = conv.in_channels, conv.out_channels
         stride = conv.stride[0]
@@ -463,9 +466,10 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         if L["kind"] == "dec" and L["idx"] == 0:
             d = n - 2 - L["stage"]
             c_low = feats[d + 1]
-            ops.upsample2x(cur, cat[d][..., :c_low])
+            ops.upsample2x(cur, cat[d][..., :c_low], norm=cur_norm)
             rec["low"] = cur  # only its shape matters in backward
             cur = cat[d]
+            cur_norm = None
         first = L["kind"] == "enc" and L["stage"] == 0 and L["idx"] == 0
         if first:
             if cin <= 8 and cout == 32 and stride == 1 and adt == BF16 and W >= 64:
@@ -507,7 +511,13 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             dst = cat[d][..., feats[d + 1]:]
         elif L["kind"] == "enc" and L["last"] and catf is not None:
             dst = catf[..., :feats[-1]]
-        z = ops.in_apply(y, a, b, act.negative_slope, out=dst)
+        nxt = layers[li_f + 1] if li_f + 1 < len(layers) else None
+        fuse_into_consumer = model._trace is None and dst is None and (
+            (nxt is not None and nxt["kind"] == "dec" and nxt["idx"] == 0) or (nxt is None and model.head_kind == "seg1x1"))
+        if fuse_into_consumer:
+            z, cur_norm = y, (a, b, act.negative_slope)
+        else:
+            z, cur_norm = ops.in_apply(y, a, b, act.negative_slope, out=dst), None
         rec.update(y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale, slope=act.negative_slope, conv=conv, norm=norm)
         saved.append(rec)
         cur = z
@@ -517,7 +527,9 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     if model.head_kind == "seg1x1":
         if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
             raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
-        logits = ops.head_forward(cur, head.weight, head.bias)
+        logits = ops.head_forward(cur, head.weight, head.bias, norm=cur_norm)
+        if need_grad:
+            ctx.head_norm = cur_norm
     else:
         # reconstruction head (autoencoder.py:374-387): 3x3 conv 32 -> K on the conv kernels with the output channels
         # zero-padded (bf16: to the tensor-core kernels' 32; fp32: to the 8-channel vector width), then bias + sigmoid
@@ -587,7 +599,7 @@ def _backward_impl(ctx, dlogits):
     if dlogits.dtype != torch.float32:
         dlogits = dlogits.float()
     if model.head_kind == "seg1x1":
-        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight)
+        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm)
     else:
         z_last, wdh = ctx.z_last, ctx.head_wd
         cpad = wdh.shape[3]

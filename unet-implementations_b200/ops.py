@@ -250,11 +250,18 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
 
 
 # ------------------------------------------------------------------------------------------------------- resampling
-def upsample2x(x, out):
-    """Bilinear 2x of x [N,H,W,C] into out [N,2H,2W,C] (typically the leading channel slice of a concat buffer)."""
+def upsample2x(x, out, norm=None):
+    """Bilinear 2x of x [N,H,W,C] into out [N,2H,2W,C] (typically the leading channel slice of a concat buffer).
+    norm = (a, b, slope): x is a RAW conv output and leaky_relu(a*x + b) is applied on the fly (the producer's apply
+    pass fused into this, its only, consumer)."""
     n, h, w, c = x.shape
     assert tuple(out.shape) == (n, 2 * h, 2 * w, c) and out.dtype == x.dtype
-    _lib.call("b200unet_upsample2x_fwd" + _sfx(x), _p(x), pitch_of(x), _p(out), pitch_of(out), n, h, w, c, _stream())
+    if norm is None:
+        _lib.call("b200unet_upsample2x_fwd" + _sfx(x), _p(x), pitch_of(x), _p(out), pitch_of(out), n, h, w, c, _stream())
+    else:
+        a, b, slope = norm
+        _lib.call("b200unet_upsample2x_norm_fwd" + _sfx(x), _p(x), pitch_of(x), _p(a), _p(b), float(slope), _p(out),
+                  pitch_of(out), n, h, w, c, _stream())
     return out
 
 
@@ -284,18 +291,24 @@ def nhwc_to_nchw(x):
 
 
 # ------------------------------------------------------------------------------------------------------ head + loss
-def head_forward(z, weight, bias):
-    """1x1 conv C->K on bf16 NHWC z; returns fp32 NCHW logits."""
+def head_forward(z, weight, bias, norm=None):
+    """1x1 conv C->K on NHWC z; returns fp32 NCHW logits.  norm = (a, b, slope): z is the RAW conv output of the last
+    unit and its InstanceNorm/LeakyReLU/dropout apply is fused in."""
     n, h, w, c = z.shape
     k = weight.shape[0]
     logits = torch.empty((n, k, h, w), dtype=torch.float32, device=z.device)
-    _lib.call("b200unet_head_fwd" + _sfx(z), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))),
-              _p(_f32(bias.detach())), _p(logits), n, h * w, c, k, _stream())
+    if norm is None:
+        _lib.call("b200unet_head_fwd" + _sfx(z), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))),
+                  _p(_f32(bias.detach())), _p(logits), n, h * w, c, k, _stream())
+    else:
+        a, b, slope = norm
+        _lib.call("b200unet_head_norm_fwd" + _sfx(z), _p(z), pitch_of(z), _p(a), _p(b), float(slope),
+                  _p(_f32(weight.detach().reshape(k, c))), _p(_f32(bias.detach())), _p(logits), n, h * w, c, k, _stream())
     return logits
 
 
-def head_backward(dlogits, z, weight):
-    """Returns (dz bf16 NHWC, dW [K,C,1,1], db [K])."""
+def head_backward(dlogits, z, weight, norm=None):
+    """Returns (dz NHWC, dW [K,C,1,1], db [K]).  norm as in head_forward (z recomputed from the raw conv output)."""
     n, h, w, c = z.shape
     k = weight.shape[0]
     dl = _f32(dlogits.contiguous())
@@ -304,8 +317,14 @@ def head_backward(dlogits, z, weight):
     dz = torch.empty((n, h, w, c), dtype=z.dtype, device=z.device)
     dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=z.device)
     db = torch.empty((k,), dtype=torch.float32, device=z.device)
-    _lib.call("b200unet_head_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
-              pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
+    if norm is None:
+        _lib.call("b200unet_head_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
+                  pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
+    else:
+        a, b, slope = norm
+        _lib.call("b200unet_head_norm_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(a), _p(b), float(slope),
+                  _p(_f32(weight.detach().reshape(k, c))), _p(dz), pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c,
+                  k, _stream())
     return dz, dw, db
 
 
