@@ -238,38 +238,6 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK<T> K
   }
 }
 
-// dgamma[c] = sum_n s_n * rstd_n * T2_n, dbeta[c] = sum_n s_n * T1_n straight from the block partials, in the SAME launch
-// as the per-image finalize (grid (images + 1, C/32): the extra row of blocks does this sum): one 7 us launch less per
-// layer.  Thread (pg, c) sums the (image, partial) pairs j = pg, pg + 8, ... in double; fixed-order combine.
-__device__ void in_bwd_param_block(const float* __restrict__ part, int P, const float* __restrict__ rstd,
-                                   const float* __restrict__ drop, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, int N, int C, double (*red)[32][2]) {
-  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
-  const int c = blockIdx.y * 32 + cl;
-  double db = 0.0, dg = 0.0;
-  if (c < C) {
-    for (int j = pg; j < N * P; j += 8) {
-      const int n = j / P;
-      const float2 v = reinterpret_cast<const float2*>(part)[static_cast<int64_t>(j) * C + c];
-      const double sc = drop ? static_cast<double>(drop[n * C + c]) : 1.0;
-      db += sc * v.x;
-      dg += sc * static_cast<double>(rstd[n * C + c]) * v.y;
-    }
-  }
-  red[pg][cl][0] = db;
-  red[pg][cl][1] = dg;
-  __syncthreads();
-  if (pg != 0 || c >= C) return;
-  db = dg = 0.0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    db += red[k][cl][0];
-    dg += red[k][cl][1];
-  }
-  dbeta[c] = static_cast<float>(db);
-  dgamma[c] = static_cast<float>(dg);
-}
-
 // per (n, c):  S1 = s*T1 = sum g,  S2 = s*rstd*T2 = sum g*xh;  dy = A1*m*dz - A2*(y - mean) - A3 with
 //   A1 = gamma*rstd*s,  A2 = gamma*rstd*rstd*S2/HW,  A3 = gamma*rstd*S1/HW.    grid (images, C/32), 256 threads
 __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __restrict__ part, int P,
@@ -277,13 +245,8 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
                                                                const float* __restrict__ rstd,
                                                                const float* __restrict__ drop,
                                                                float* __restrict__ coef, float* __restrict__ imgsum,
-                                                               int C, int n0, double inv_hw, int images,
-                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                               int C, int n0, double inv_hw) {
   __shared__ double red[8][32][2];
-  if (static_cast<int>(blockIdx.x) == images) {  // the extra block row: parameter gradients over the whole batch
-    in_bwd_param_block(part, P, rstd, drop, dgamma, dbeta, images, C, red);
-    return;
-  }
   const int n = n0 + blockIdx.x;
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + cl;
@@ -319,6 +282,22 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
   reinterpret_cast<float4*>(coef)[i] = k4;
   imgsum[i * 2 + 0] = static_cast<float>(S1);
   imgsum[i * 2 + 1] = static_cast<float>(S2);
+}
+
+// dgamma[c] = sum_n S2, dbeta[c] = sum_n S1 (fixed order).  (Summing the block partials of the whole batch inside the
+// finalize launch instead was tried: one launch less, but the extra block row is a 150 .. 2000-load serial chain on
+// the critical path.)
+__global__ void in_bwd_param_kernel(const float* __restrict__ imgsum, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dg = 0.0, db = 0.0;
+  for (int n = 0; n < N; ++n) {
+    db += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 0];
+    dg += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 1];
+  }
+  dgamma[c] = static_cast<float>(dg);
+  dbeta[c] = static_cast<float>(db);
 }
 
 // grid (blocks_per_image, images)
@@ -493,14 +472,13 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
   K.chunk = chunk;
   const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(typename AccT<T>::type);
   const double inv_hw = 1.0 / static_cast<double>(HW);
-  B200_CHECK_ARG(ipc == N, "in_backward: the batch is one launch group");  // the finalize launch also sums over the batch
   for (int n0 = 0; n0 < N; n0 += ipc) {
     const int nn = (N - n0 < ipc) ? N - n0 : ipc;
     K.n0 = n0;
     in_bwd_reduce_kernel<T><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
     B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
-    in_bwd_finalize_kernel<<<dim3(nn + 1, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
-                                                                         imgsum, C, n0, inv_hw, nn, A->dgamma, A->dbeta);
+    in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
+                                                                     imgsum, C, n0, inv_hw);
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
     K.chunk = chunk_apply;
     in_bwd_apply_kernel<T><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
@@ -508,6 +486,8 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
+  in_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+  B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
 }
 
