@@ -36,6 +36,24 @@ def _worker(rank, world, port, q):
     red.finish()
     ok = all(torch.allclose(views[id(p)], expect[id(p)], atol=1e-6) for p in order)
     ok &= all(views[id(p)].shape == p.shape and views[id(p)].data_ptr() % 16 == 0 for p in order)
+    # second step through the same reducer, with every conv weight delivered ONE LAYER LATE (what the side-stream weight
+    # gradients of models/unet.py do): a bucket must wait for all of its gradients, in whatever order they arrive
+    late, held = [], None
+    for p in order:
+        if p.dim() == 4 and p.shape[-1] == 3:   # a 3x3 conv weight: hold it back until the next one shows up
+            if held is not None:
+                late.append(held)
+            held = p
+        else:
+            late.append(p)
+    late.append(held)
+    assert len(late) == len(order) and [id(p) for p in late] != [id(p) for p in order]
+    g2 = torch.Generator().manual_seed(8)
+    vals = {id(p): torch.randn(p.shape, generator=g2) for p in order}
+    for p in late:
+        views[id(p)] = red(p, vals[id(p)] * (rank + 1))     # mean over ranks = vals * (1 + 2) / 2
+    red.finish()
+    ok &= all(torch.allclose(views[id(p)], vals[id(p)] * (world + 1) / 2.0, atol=1e-5) for p in order)
     q.put((rank, bool(ok), w0))
     dist.destroy_process_group()
 
