@@ -471,6 +471,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "remeasured": remeasured,
+            "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "per_rank_ms_per_step": per_rank_resident,
             "clocks": clocks,
             "roofline": roofline,
