@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int total_tiles = tiles_per_img * p.N;
-  const int chunks = p.cin / BK;
+  const int chunks = (p.cin + BK - 1) / BK;  // the last chunk may be partly out of range: TMA zero-fills it, the MMAs skip it
   const int tile_lo = min(static_cast<int>(blockIdx.x) * p.tiles_per_cta, total_tiles);
   const int tile_hi = min(tile_lo + p.tiles_per_cta, total_tiles);
 
@@ -181,14 +181,17 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
           if (kInstr && p.debug) dbg_af += clock64() - t1;
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + aslot * kASlot16;
+          const int ksteps = min(BK, p.cin - c * BK) >> 4;  // K = 16 steps of this chunk that hold real channels
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             // window kh of the patch pairs with weight row kh (fprop) or 2 - kh (dgrad)
             const uint32_t b_lo = b_c + (REV ? (2 - kh) : kh) * kBTile16;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16_lean(d_tmem, a_lo + kh * Cfg::kWin16 + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
-              acc = 1;
+              if (k < ksteps) {
+                umma_bf16_lean(d_tmem, a_lo + kh * Cfg::kWin16 + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc);
+                acc = 1;
+              }
             }
           }
           umma_commit_u32(a_empty0 + aslot * 8);
@@ -385,11 +388,18 @@ static NConvGrid nconv_grid(int N, int H, int W) {
   return g;
 }
 
+// K chunk.  64 channels = 128-byte operand rows run the MMAs at full rate; K-major operands with 64-byte rows (64 B
+// swizzle) were measured at ~120 cycles per N = 96 MMA instead of 64.  For 96 channels the 32-channel tail therefore
+// also uses a 64-channel box: the TMA zero-fills the channels past k_channels and the MMA loop skips their K = 16
+// steps (d4c1 fprop 632 -> 596 us).  For 32 channels the doubled shared-memory fill costs more than the faster MMAs
+// save (313 -> 345 us), so those layers keep 64-byte rows.
+static int nconv_bk(int k_channels) { return k_channels > 32 ? 64 : 32; }
+
 bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
   if (stride != 1 || (n_channels != 32 && n_channels != 64) || k_channels % 32 != 0 || k_channels <= 0) return false;
   if (W < 64) return false;  // the 30-of-32 column tiling only pays on wide images
-  const int BK = (k_channels % 64 == 0) ? 64 : 32;
-  return static_cast<long long>(k_channels / BK) * 3 * (3 * n_channels * BK * 2) <= 80 * 1024;  // resident weights
+  const int BK = nconv_bk(k_channels);
+  return static_cast<long long>(ceil_div(k_channels, BK)) * 3 * (3 * n_channels * BK * 2) <= 80 * 1024;  // resident weights
 }
 
 int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
@@ -439,7 +449,7 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
 // out: [N,H,W,n_channels] (y / dx); rev = 0 fprop, 1 dgrad
 int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
                  int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st) {
-  const int BK = (k_channels % 64 == 0) ? 64 : 32;
+  const int BK = nconv_bk(k_channels);
   const NConvGrid g = nconv_grid(N, H, W);
   NConvParams p{};
   NConvMaps maps;
