@@ -32,6 +32,8 @@ CONV_CASES = [
     (2, 16, 32, 32, 64, 2), (1, 13, 21, 32, 96, 2), (2, 18, 10, 64, 128, 2), (1, 7, 9, 32, 32, 2),
     # wide images: the narrow-output kernels (column taps stacked on N, 30-of-32 column tiles, ragged edges)
     (1, 12, 70, 32, 32, 1), (1, 9, 64, 96, 32, 1), (2, 8, 96, 64, 64, 1), (1, 6, 121, 64, 32, 1), (1, 7, 90, 32, 64, 1),
+    # 32 -> 32 on dense tensors at least 128 wide: pixel pairs as operand rows (60-of-64 column tiles); odd width -> nconv
+    (1, 12, 128, 32, 32, 1), (2, 9, 190, 32, 32, 1), (3, 5, 250, 32, 32, 1), (1, 6, 129, 32, 32, 1),
 ]
 
 
@@ -64,6 +66,24 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, cin, cout, stride):
     dw = ops.conv_wgrad(x, dy, stride)
     assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3)
     assert O.rel_l2(dw, w_ref.grad) <= F32_TOL
+
+
+def test_conv_32_to_32_wide_on_channel_slices():
+    """The pair-row kernel needs dense tensors; a 32-channel slice of a wider buffer (in or out) must take the generic
+    narrow kernel and still be right, leaving the other channels untouched."""
+    from unet_implementations_b200 import ops
+    xb, xb_ref = rand_act(1, 8, 136, 96, seed=14)
+    x, x_ref = xb[..., 64:96], xb_ref[..., 64:96]
+    g = torch.Generator().manual_seed(15)
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.08
+    wf, _ = ops.pack_conv_weights(wt.cuda(), need_dgrad=False)
+    yr = F.conv2d(x_ref.permute(0, 3, 1, 2), wt.bfloat16().float(), padding=1).permute(0, 2, 3, 1)
+    out = torch.full((1, 8, 136, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    y, stats = ops.conv_fprop(x, wf, 1, out=out[..., 32:64])
+    assert O.rel_l2(out[..., 32:64].float(), yr) <= BF16_TOL
+    assert float((out[..., :32].float() - 7).abs().max()) == 0
+    y2, _ = ops.conv_fprop(x, wf, 1)  # pitched in, dense out
+    assert O.rel_l2(y2.float(), yr) <= BF16_TOL
 
 
 def test_conv_reads_and_writes_channel_slices_of_a_concat_buffer():

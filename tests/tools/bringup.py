@@ -2,14 +2,14 @@
 one-line verdict per case.  Not part of the product or of the parity suite (tests/ uses the CPU oracle);
 it exists so that a faulting kernel cannot take the other checks down with it.
 
-    python tools/bringup.py list
-    python tools/bringup.py <case> [<case> ...]
+    python tests/tools/bringup.py list
+    python tests/tools/bringup.py <case> [<case> ...]
 """
 import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import torch
 import torch.nn.functional as F

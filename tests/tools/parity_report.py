@@ -1,12 +1,12 @@
 """Developer tool: error of the CUDA path against the fp32 CPU oracle, next to the error of the oracle itself when it
 is run under bf16 autocast on the CPU (the yardstick for what bf16 storage costs); and the fp32 verification mode of the
 CUDA path, the fp32 oracle and the bf16 CUDA path against the fp64 oracle.  Not part of the test suite.
-    python tools/parity_report.py [size ...]  -> gpurun_out/parity_report.json, gpurun_out/parity_report.md"""
+    python tests/tools/parity_report.py [size ...]  -> gpurun_out/parity_report.json, gpurun_out/parity_report.md"""
 import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from oracle import unet_oracle as O

@@ -1,6 +1,6 @@
 """Developer tool: layer-by-layer forward difference between the CUDA path and the matched-precision oracle."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import unet_oracle as O
 from unet_implementations_b200.models.unet import UNet

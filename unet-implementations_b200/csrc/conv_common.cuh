@@ -74,6 +74,12 @@ bool nconv_supported(int k_channels, int n_channels, int stride, int W);
 int nconv_stat_slots(int N, int H, int W);
 int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
                  int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st);
+// 32 -> 32 channels on dense tensors with pixel pairs as 128-byte operand rows (conv_pair.cu); taken by nconv_launch
+// when it applies.
+bool pconv_supported(int k_channels, int n_channels, int stride, int W, int64_t src_pitch, int64_t out_pitch);
+int pconv_stat_slots(int N, int H, int W);
+int pconv_launch(const void* src, const void* wpack, void* out, float* stats, int N, int H, int W, int rev, int stat_slots,
+                 cudaStream_t st);
 // Partial-sum slots per image of the fprop statistics buffer [N][P][Cout][2]: one value for both fprop kernels
 // (conv_fprop_dgrad.cu), so that the caller can size the buffer without knowing which kernel will run.
 int conv_stat_slots(int N, int OH, int OW, int Cout);

@@ -402,7 +402,10 @@ bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
   return static_cast<long long>(ceil_div(k_channels, BK)) * 3 * (3 * n_channels * BK * 2) <= 80 * 1024;  // resident weights
 }
 
-int nconv_stat_slots(int N, int H, int W) { return nconv_grid(N, H, W).stat_slots; }
+int nconv_stat_slots(int N, int H, int W) {
+  const int a = nconv_grid(N, H, W).stat_slots, b = pconv_stat_slots(N, H, W);  // either kernel may run for Cout = 32
+  return a > b ? a : b;
+}
 
 static long long* nconv_debug_buffer() {
   static long long* buf = nullptr;
@@ -449,6 +452,8 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
 // out: [N,H,W,n_channels] (y / dx); rev = 0 fprop, 1 dgrad
 int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
                  int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st) {
+  if (pconv_supported(k_channels, n_channels, 1, W, src_pitch, out_pitch))
+    return pconv_launch(src, wpack, out, stats, N, H, W, rev, stat_slots, st);
   const int BK = nconv_bk(k_channels);
   const NConvGrid g = nconv_grid(N, H, W);
   NConvParams p{};

@@ -240,6 +240,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Column sums over the 32 lanes of a warp for 32 per-lane values: after the call lane l holds
 // sum over lanes of v[l] in v[0] (recursive-halving exchange: 31 shuffles instead of 160).
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
