@@ -420,7 +420,7 @@ def main():
         conv_ms_step = conv_ms / prof_steps
         achieved = tc * B / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
         tconv = traffic.get("conv")
-        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (gconv/nconv fprop+dgrad, wgrad/wgradn + finalize), all 22 3x3 convs",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (gconv/nconv/pconv fprop+dgrad, wgrad/wgradn + finalize), all 22 3x3 convs",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": (tconv["dram_read_bytes"] + tconv["dram_write_bytes"]) if tconv and B == 32 and S == 512 else None,
                     "traffic_note": "DRAM bytes of the family per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, "

@@ -54,7 +54,8 @@ def _worker(rank, world, port, q):
         views[id(p)] = red(p, vals[id(p)] * (rank + 1))     # mean over ranks = vals * (1 + 2) / 2
     red.finish()
     ok &= all(torch.allclose(views[id(p)], vals[id(p)] * (world + 1) / 2.0, atol=1e-5) for p in order)
-    q.put((rank, bool(ok), w0))
+    # bytes, not a tensor: a tensor travels as a shared-memory handle that dies with this process if the parent is slow
+    q.put((rank, bool(ok), w0.numpy().tobytes()))
     dist.destroy_process_group()
 
 
@@ -70,4 +71,4 @@ def test_bucketed_allreduce_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
-    assert torch.equal(res[0][2], res[1][2])  # identical replicas after the broadcast
+    assert res[0][2] == res[1][2]  # identical replicas after the broadcast

@@ -10,6 +10,6 @@ L=$(python -c "import json;print(json.loads(open('gpurun_out/plain.log').read().
 echo "launches per step: $L"
 # torch's own small kernels (fills, RNG) are interleaved: count ALL launches of the 3 warm-up steps by a first cheap pass
 timeout ${NCU_TIMEOUT:-900} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:'gconv|nconv|wgrad|in_|stem|upsample|head_|loss_|pack_weights|image_to|stats_partial' -s $((3*L)) -c $L \
+    -k regex:'gconv|nconv|pconv|wgrad|in_|stem|upsample|head_|loss_|pack_weights|image_to|stats_partial' -s $((3*L)) -c $L \
     --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "ncu launches rc=$?"; wc -l gpurun_out/launches.csv

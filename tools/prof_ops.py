@@ -66,7 +66,9 @@ def main():
             c = 32 * 512 // hw
             x = torch.randn(B, hw, hw, c, device="cuda").bfloat16()
             out = torch.empty(B, 2 * hw, 2 * hw, c, device="cuda", dtype=torch.bfloat16)
-            ops.upsample2x(x, out)
+            a = torch.rand(B, c, device="cuda") + 0.5
+            b = torch.randn(B, c, device="cuda") * 0.1
+            ops.upsample2x(x, out, norm=(a, b, 0.01))  # as in the model: the producer's norm apply fused in
             ops.upsample2x_backward(out)
         elif case == "stem":
             img = torch.randn(B, 3, 512, 512, device="cuda")

@@ -6,7 +6,7 @@ import json
 import re
 import sys
 
-FAMILIES = [("conv", r"gconv|nconv|wgrad|image_to_nhwc32|pack_weights"), ("norm", r"^in_"), ("resample", r"upsample"),
+FAMILIES = [("conv", r"gconv|nconv|pconv|wgrad|image_to_nhwc32|pack_weights"), ("norm", r"^in_"), ("resample", r"upsample"),
             ("head", r"^head_"), ("loss", r"^loss_"), ("stem_simt", r"^stem_")]
 rows = list(csv.reader(open(sys.argv[1])))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
