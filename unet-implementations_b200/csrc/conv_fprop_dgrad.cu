@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
               const int r = q * 32 + ((OC == 64) ? (i0 + i) : (2 * (i0 + i) + static_cast<int>(par)));
               const uint32_t off = (OC == 64) ? (r * 128 + (((cw ^ (r & 7)) & 7) << 4) + wi)
                                               : (r * 64 + (((cw ^ ((r >> 1) & 3)) & 3) << 4) + wi);
-              w[i] = *reinterpret_cast<const uint32_t*>(sbase + off);
+              w[i] = lds_u32(smem_u32(sbase) + off);
               if (!full && !((h0 + (r >> 4) < p.OH) && (w0 + (r & 15) < p.OW))) w[i] = 0;  // outside the image
             }
 #pragma unroll

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
             const int r = q * kNcValidW + col;
             const uint32_t off = (CO == 64) ? (r * 128 + (((cw ^ (r & 7)) & 7) << 4) + wi)
                                             : (r * 64 + (((cw ^ ((r >> 1) & 3)) & 3) << 4) + wi);
-            w[i] = *reinterpret_cast<const uint32_t*>(stg + off);
+            w[i] = lds_u32(smem_u32(stg) + off);
             if (!row_in || w0 + col >= p.W) w[i] = 0;
           }
 #pragma unroll

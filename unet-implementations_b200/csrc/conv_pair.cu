@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(PConvCfg::kThreads, 1) pconv_kernel(const __gr
           const int r = q * kPcValidW + col;
           uint4 w = make_uint4(0u, 0u, 0u, 0u);
           if (row_in && col < kPcValidW && w0 + col < p.Wp)
-            w = *reinterpret_cast<const uint4*>(stg + r * 128 + (((ch ^ (r & 7)) & 7) << 4));
+            w = lds_v4(smem_u32(stg) + r * 128 + (((ch ^ (r & 7)) & 7) << 4));
           const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
