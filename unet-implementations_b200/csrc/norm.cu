@@ -287,14 +287,32 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
 // dgamma[c] = sum_n S2, dbeta[c] = sum_n S1 (fixed order).  (Summing the block partials of the whole batch inside the
 // finalize launch instead was tried: one launch less, but the extra block row is a 150 .. 2000-load serial chain on
 // the critical path.)
-__global__ void in_bwd_param_kernel(const float* __restrict__ imgsum, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int N, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// grid (C/32), 256 threads: thread (ng = t/32, c = t%32) sums images n = ng, ng+8, ... in double (independent loads),
+// fixed-order combine across the 8 groups -- the kernel sits between the apply pass and the next data gradient
+__global__ void __launch_bounds__(256) in_bwd_param_kernel(const float* __restrict__ imgsum, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int N, int C) {
+  __shared__ double red[8][32][2];
+  const int cl = threadIdx.x & 31, ng = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double dg = 0.0, db = 0.0;
-  for (int n = 0; n < N; ++n) {
-    db += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 0];
-    dg += imgsum[(static_cast<int64_t>(n) * C + c) * 2 + 1];
+  if (c < C) {
+    const float2* sp = reinterpret_cast<const float2*>(imgsum) + c;
+#pragma unroll 4
+    for (int n = ng; n < N; n += 8) {
+      const float2 v = sp[static_cast<int64_t>(n) * C];
+      db += v.x;
+      dg += v.y;
+    }
+  }
+  red[ng][cl][0] = db;
+  red[ng][cl][1] = dg;
+  __syncthreads();
+  if (ng != 0 || c >= C) return;
+  db = dg = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    db += red[k][cl][0];
+    dg += red[k][cl][1];
   }
   dgamma[c] = static_cast<float>(dg);
   dbeta[c] = static_cast<float>(db);
@@ -486,7 +504,7 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
-  in_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+  in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
   B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
 }
