@@ -106,3 +106,43 @@ def test_full_size_argmax_counters_and_loss_shift_invariance(full):
     shift = torch.randn(B, 1, S, S, device="cuda")                     # softmax(z + s) == softmax(z) per pixel
     moved = loss_fn(logits + shift, target)
     assert abs(float(moved) - float(base)) <= 1e-5 * abs(float(base)) + 1e-6
+
+
+# (Cin, Cout, stride, H = W) of the benchmark step at batch 32: one layer per tensor-core kernel family / dispatch path
+FULL_LAYERS = [
+    ("e0c2", 32, 32, 1, 512),    # pair-row kernel fprop + dgrad, wgradn<32,32>
+    ("d4c1", 96, 32, 1, 512),    # nconv with the zero-filled K tail, gconv<32,96> dgrad, wgradn over three chunks
+    ("e1c1", 32, 64, 2, 512),    # stride 2: parity sub-lattices, parity-stacked dgrad
+    ("d3c1", 192, 64, 1, 256),   # four M tiles per weight tile, N = 192 dgrad, wgradn<64,64>
+    ("e2c2", 128, 128, 1, 128),  # two M tiles per weight tile, wgrad<64,128>
+    ("d1c1", 768, 256, 1, 64),   # streamed weights N = 256, wgrad<64,256>
+    ("e5c2", 512, 512, 1, 16),   # two N tiles, fewer tiles than SMs
+]
+
+
+@pytest.mark.parametrize("name,cin,cout,stride,hw", FULL_LAYERS)
+def test_full_size_tensor_core_convs_against_the_direct_kernels(name, cin, cout, stride, hw):
+    """At the real layer shapes (batch 32) the CPU oracle is out of reach; the independent implementation is the
+    direct CUDA-core convolution (conv_simt.cu: one thread per output, plain loops, no tiling / TMA / swizzle), itself
+    checked against F.conv2d at small sizes (tests/test_gpu_ops.py).  Same bf16 operands, fp32 accumulation in both:
+    outputs agree to accumulation-order noise; the InstanceNorm partial sums equal the sums of the stored output."""
+    from unet_implementations_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, hw, hw, cin, device="cuda", generator=g).bfloat16()
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5
+    wf, wd = ops.pack_conv_weights(wt)
+    y, stats = ops.conv_fprop(x, wf, stride)
+    y_ref, _ = ops.conv_fprop(x, wf, stride, want_stats=False, simt=True)
+    assert O.rel_l2(y.float(), y_ref.float()) <= 2e-3
+    yf = y.float()
+    s_ref = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1)
+    assert O.rel_l2(stats.sum(dim=1), s_ref) <= 1e-4
+    oh = y.shape[1]
+    dy = torch.randn(B, oh, oh, cout, device="cuda", generator=g).bfloat16()
+    dx_ref = ops.conv_dgrad(dy, wd, (hw, hw), stride, simt=True)
+    assert O.rel_l2(ops.conv_dgrad(dy, wd, (hw, hw), stride).float(), dx_ref.float()) <= 2e-3
+    if stride == 2 and cin <= 64:  # the form the model uses for these layers
+        dx2 = torch.empty_like(dx_ref)
+        ops.conv_dgrad_s2(dy, ops.pack_s2_dgrad_weights(wd), (hw, hw), out=dx2)
+        assert O.rel_l2(dx2.float(), dx_ref.float()) <= 2e-3
+    assert O.rel_l2(ops.conv_wgrad(x, dy, stride), ops.conv_wgrad(x, dy, stride, simt=True)) <= 1e-3
