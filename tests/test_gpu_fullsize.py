@@ -146,3 +146,102 @@ def test_full_size_tensor_core_convs_against_the_direct_kernels(name, cin, cout,
         ops.conv_dgrad_s2(dy, ops.pack_s2_dgrad_weights(wd), (hw, hw), out=dx2)
         assert O.rel_l2(dx2.float(), dx_ref.float()) <= 2e-3
     assert O.rel_l2(ops.conv_wgrad(x, dy, stride), ops.conv_wgrad(x, dy, stride, simt=True)) <= 1e-3
+
+
+def _act(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).bfloat16()
+
+
+def test_full_size_norm_kernels_against_torch_fp32():
+    """InstanceNorm + LeakyReLU + channel dropout forward / backward (unet.py:118-127, :22-35) at the largest tensor of the
+    step ([32, 512, 512, 32] bf16, with the skip-connection's second gradient operand) against torch's own fp32 ops and
+    autograd run on the same GPU from the same bf16-rounded operands."""
+    import torch.nn.functional as F
+
+    from unet_implementations_b200 import ops
+    c, p = 32, 0.2
+    y = _act((B, S, S, c), 1, 1.7)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    gamma = (torch.rand(c, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    drop = (torch.rand(B, c, device="cuda", generator=g) > p).float().div(1 - p)
+    yf = y.float()
+    stats = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], -1).unsqueeze(1).contiguous()
+    mean, rstd, a, b = ops.in_finalize(stats, gamma.detach(), beta.detach(), drop, 1e-5, S * S)
+    z = ops.in_apply(y, a, b, 0.01)
+    yr = yf.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    del yf
+    zr = F.leaky_relu(F.instance_norm(yr, weight=gamma, bias=beta, eps=1e-5), 0.01) * drop[:, :, None, None]
+    assert O.rel_l2(z.float(), zr.detach().permute(0, 2, 3, 1)) <= 4e-3
+    dz, dz2 = _act((B, S, S, c), 3), _act((B, S, S, c), 4)
+    dy, dg, db = ops.in_backward(dz, dz2, y, a, b, mean, rstd, drop, gamma.detach(), 0.01)
+    zr.backward((dz.float() + dz2.float()).permute(0, 3, 1, 2))
+    assert O.rel_l2(dy.float(), yr.grad.permute(0, 2, 3, 1)) <= 6e-3
+    assert O.rel_l2(dg, gamma.grad) <= 1e-3 and O.rel_l2(db, beta.grad) <= 1e-3
+
+
+def test_full_size_upsample_and_head_against_torch_fp32():
+    """The 256^2 -> 512^2 upsample into the 96-channel concat buffer (with the producer's norm apply fused in) and the
+    1x1 head forward / backward with the fused apply ([32, 512, 512, 32] -> fp32 NCHW logits), against
+    F.interpolate / F.conv2d and autograd in fp32 on the same GPU."""
+    import torch.nn.functional as F
+
+    from unet_implementations_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # ---- upsample2x with (a, b, slope)
+    c, h = 64, S // 2
+    y = _act((B, h, h, c), 6, 1.5)
+    a = (torch.rand(B, c, device="cuda", generator=g) + 0.3) * (torch.rand(B, c, device="cuda", generator=g) > 0.2)
+    b = torch.randn(B, c, device="cuda", generator=g) * (a != 0)
+    cat = torch.full((B, S, S, c + 32), 5.0, dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x(y, cat[..., :c], norm=(a.contiguous(), b.contiguous(), 0.01))
+    zr = F.leaky_relu(y.float() * a[:, None, None, :] + b[:, None, None, :], 0.01).permute(0, 3, 1, 2).requires_grad_(True)
+    ur = F.interpolate(zr, size=(S, S), mode="bilinear", align_corners=False)
+    assert O.rel_l2(cat[..., :c].float(), ur.detach().permute(0, 2, 3, 1)) <= 4e-3
+    assert float((cat[..., c:].float() - 5.0).abs().max()) == 0.0     # the skip half of the concat buffer is untouched
+    dcat = _act((B, S, S, c + 32), 7)
+    dx = ops.upsample2x_backward(dcat[..., :c])
+    ur.backward(dcat[..., :c].float().permute(0, 3, 1, 2))
+    assert O.rel_l2(dx.float(), zr.grad.permute(0, 2, 3, 1)) <= 4e-3
+    del cat, dcat, ur, zr, dx
+    # ---- head with (a, b, slope)
+    c = 32
+    y = _act((B, S, S, c), 8, 1.5)
+    a = torch.rand(B, c, device="cuda", generator=g) + 0.3
+    b = torch.randn(B, c, device="cuda", generator=g)
+    wt = (torch.randn(3, c, 1, 1, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    bias = torch.randn(3, device="cuda", generator=g).requires_grad_(True)
+    zr = F.leaky_relu(y.float() * a[:, None, None, :] + b[:, None, None, :], 0.01).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # the checker must be real fp32: cuDNN's default TF32 conv is 2e-4 off
+    try:
+        lr = F.conv2d(zr, wt, bias)
+        logits = ops.head_forward(y, wt.detach(), bias.detach(), norm=(a, b, 0.01))
+        assert O.rel_l2(logits, lr.detach()) <= 1e-4
+        dl = torch.randn(B, 3, S, S, device="cuda", generator=g) * 1e-3
+        lr.backward(dl)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    dz, dw, db = ops.head_backward(dl, y, wt.detach(), norm=(a, b, 0.01))
+    assert O.rel_l2(dz.float(), zr.grad.permute(0, 2, 3, 1)) <= 4e-3
+    assert O.rel_l2(dw, wt.grad) <= 1e-3 and O.rel_l2(db, bias.grad) <= 1e-3
+
+
+def test_full_size_loss_against_the_restated_reference_loss():
+    """SimpleLoss forward / backward on [32, 3, 512, 512] logits + int64 targets with ignored pixels against the
+    restatement of losses.py:24-121 (oracle.simple_loss, itself pinned to the reference's committed values at small
+    sizes) evaluated in float64 on the same GPU."""
+    from unet_implementations_b200.models.losses import SimpleLoss
+    g = torch.Generator(device="cuda").manual_seed(9)
+    logits = (torch.randn(B, 3, S, S, device="cuda", generator=g) * 2.0).requires_grad_(True)
+    _, target = O.synthetic_batch(B, S, seed=3)
+    target = target.cuda()
+    loss = SimpleLoss()(logits, target)
+    loss.backward()
+    ref_in = logits.detach().double().requires_grad_(True)
+    w = O.class_weights(target).double()
+    ref = O.simple_loss(ref_in, target, weights=w, dynamic=False)
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    assert O.rel_l2(logits.grad.double(), ref_in.grad) <= 1e-4
