@@ -165,8 +165,8 @@ struct InBwdK {
 };
 
 // T1 = sum dz*m, T2 = sum dz*m*(y - mean) over the block's pixels, m = lrelu'(a*y+b).   grid (P, images)
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK<T> K, float* __restrict__ part, int P) {
+template <typename T, bool HAS2>
+__global__ void __launch_bounds__(kNormThreads, (HAS2 || sizeof(T) != 2) ? 2 : 3) in_bwd_reduce_kernel(InBwdK<T> K, float* __restrict__ part, int P) {
   using Acc = typename AccT<T>::type;
   extern __shared__ __align__(8) unsigned char red_raw[];
   Acc* red = reinterpret_cast<Acc*>(red_raw);  // [lanes][c8n][16]
@@ -188,17 +188,17 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK<T> K
   if (hi > K.HW) hi = K.HW;
   const T* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
   const T* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
-  const T* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  const T* d2b = HAS2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
   const int lanes = K.lanes;
   constexpr int U = 4;  // pixels in flight per thread: 8-12 independent 16-byte loads cover the HBM latency
   for (int64_t px = lo + lane; px < hi; px += U * lanes) {
-    Vec8<T> vy[U], vd[U], vd2[U];
+    Vec8<T> vy[U], vd[U], vd2[HAS2 ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
         vy[u] = Vec8<T>::ld_stream(yb + (px + u * lanes) * K.yp);
         vd[u] = Vec8<T>::ld_stream(db + (px + u * lanes) * K.dzp);
-        if (d2b) vd2[u] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
+        if (HAS2) vd2[HAS2 ? u : 0] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(kNormThreads) in_bwd_reduce_kernel(InBwdK<T> K
       float yv[8], d[8];
       vy[u].unpack(yv);
       vd[u].unpack(d);
-      if (d2b) {
+      if (HAS2) {
         float d2[8];
-        vd2[u].unpack(d2);
+        vd2[HAS2 ? u : 0].unpack(d2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] += d2[j];
       }
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) in_bwd_param_kernel(const float* __restri
 }
 
 // grid (blocks_per_image, images)
-template <typename T>
+template <typename T, bool HAS2>
 __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T> K, const float* __restrict__ coef,
                                                                         T* __restrict__ dy, int64_t dyp) {
   const int n = K.n0 + blockIdx.y;
@@ -346,18 +346,18 @@ __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T>
   if (hi > K.HW) hi = K.HW;
   const T* yb = K.y + static_cast<int64_t>(n) * K.HW * K.yp + c0;
   const T* db = K.dz + static_cast<int64_t>(n) * K.HW * K.dzp + c0;
-  const T* d2b = K.dz2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
+  const T* d2b = HAS2 ? K.dz2 + static_cast<int64_t>(n) * K.HW * K.dz2p + c0 : nullptr;
   T* ob = dy + static_cast<int64_t>(n) * K.HW * dyp + c0;
   const int lanes = K.lanes;
   constexpr int U = 4;
   for (int64_t px = lo + lane; px < hi; px += U * lanes) {
-    Vec8<T> vy[U], vd[U], vd2[U];
+    Vec8<T> vy[U], vd[U], vd2[HAS2 ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (px + u * lanes < hi) {
         vy[u] = Vec8<T>::ld_stream(yb + (px + u * lanes) * K.yp);
         vd[u] = Vec8<T>::ld_stream(db + (px + u * lanes) * K.dzp);
-        if (d2b) vd2[u] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
+        if (HAS2) vd2[HAS2 ? u : 0] = Vec8<T>::ld_stream(d2b + (px + u * lanes) * K.dz2p);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -365,9 +365,9 @@ __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T>
       float yv[8], d[8], o[8];
       vy[u].unpack(yv);
       vd[u].unpack(d);
-      if (d2b) {
+      if (HAS2) {
         float d2[8];
-        vd2[u].unpack(d2);
+        vd2[HAS2 ? u : 0].unpack(d2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] += d2[j];
       }
@@ -380,6 +380,153 @@ __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T>
       Vec8<T>::st(ob + (px + u * lanes) * dyp, o);
     }
   }
+}
+
+// Small levels (32^2 and 16^2: five of the 22 units) in ONE kernel: a CTA owns one image x CG channels, whose whole
+// (dz, [dz2], y) slab fits in shared memory -- 3 tensor passes over HBM instead of 5 and one launch instead of three.
+// GPU time (CUDA-graph replay, tools/norm_small_bench.py): 43.8 -> 35.9 us at 32^2 x 512, 21.0 -> 11.7 us at 16^2 x 512.  Phase 1
+// streams the slab into shared memory while accumulating T1, T2; the block reduces them in fixed order, 32/64 threads
+// evaluate the per-channel coefficients exactly as in_bwd_finalize_kernel does; phase 2 re-reads the slab from shared
+// memory and writes dy.  grid (C / CG, images), 256 threads, bf16 storage only.
+template <bool HAS2>
+__global__ void __launch_bounds__(256, 2) in_bwd_fused_kernel(InBwdK<__nv_bfloat16> K, const float* __restrict__ gamma,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ drop,
+                                                               __nv_bfloat16* __restrict__ dy, int64_t dyp,
+                                                               float* __restrict__ imgsum, int cg8, double inv_hw) {
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(16) unsigned char fz_raw[];
+  const int HW = static_cast<int>(K.HW);
+  uint4* ty = reinterpret_cast<uint4*>(fz_raw);               // [HW][cg8]
+  uint4* td = ty + static_cast<size_t>(HW) * cg8;
+  uint4* td2 = td + static_cast<size_t>(HW) * cg8;            // only with HAS2
+  float* red = reinterpret_cast<float*>(td + static_cast<size_t>(HW) * cg8 * (HAS2 ? 2 : 1));  // [256][16]
+  float* coef = red + 256 * 16;                                // [CG][4]: k1, k2, k3'
+  const int n = blockIdx.y;
+  const int CG = cg8 << 3;
+  const int cbase = blockIdx.x * CG;
+  const int c8 = threadIdx.x % cg8, lane = threadIdx.x / cg8, lanes = 256 / cg8;
+  const int c0 = cbase + (c8 << 3);
+  float ra[8], rb[8], rm[8];
+  ld8f(K.a + n * K.C + c0, ra);
+  ld8f(K.b + n * K.C + c0, rb);
+  ld8f(K.mean + n * K.C + c0, rm);
+  float t1[8], t2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t1[j] = t2[j] = 0.f;
+  const T* yb = K.y + static_cast<int64_t>(n) * HW * K.yp + c0;
+  const T* db = K.dz + static_cast<int64_t>(n) * HW * K.dzp + c0;
+  const T* d2b = HAS2 ? K.dz2 + static_cast<int64_t>(n) * HW * K.dz2p + c0 : nullptr;
+  constexpr int U = 4;
+  for (int px = lane; px < HW; px += U * lanes) {
+    Vec8<T> vy[U], vd[U], vd2[HAS2 ? U : 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (px + u * lanes < HW) {
+        vy[u] = Vec8<T>::ld_stream(yb + static_cast<int64_t>(px + u * lanes) * K.yp);
+        vd[u] = Vec8<T>::ld_stream(db + static_cast<int64_t>(px + u * lanes) * K.dzp);
+        if (HAS2) vd2[HAS2 ? u : 0] = Vec8<T>::ld_stream(d2b + static_cast<int64_t>(px + u * lanes) * K.dz2p);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = px + u * lanes;
+      if (q >= HW) break;
+      ty[q * cg8 + c8] = vy[u].r;
+      td[q * cg8 + c8] = vd[u].r;
+      float yv[8], d[8];
+      vy[u].unpack(yv);
+      vd[u].unpack(d);
+      if (HAS2) {
+        td2[q * cg8 + c8] = vd2[HAS2 ? u : 0].r;
+        float d2[8];
+        vd2[HAS2 ? u : 0].unpack(d2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += d2[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(ra[j], yv[j], rb[j]);
+        const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
+        t1[j] += gm;
+        t2[j] += gm * (yv[j] - rm[j]);
+      }
+    }
+  }
+  float* mine = red + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = t1[j];
+    mine[8 + j] = t2[j];
+  }
+  __syncthreads();
+  // thread t < CG: channel cbase + t -- sums over the pixel lanes in fixed order, then the coefficients of
+  // in_bwd_finalize_kernel (same expressions, double)
+  if (threadIdx.x < CG) {
+    const int cl = threadIdx.x, cc8 = cl >> 3, j = cl & 7;
+    float s1 = 0.f, s2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      s1 += red[(l * cg8 + cc8) * 16 + j];
+      s2 += red[(l * cg8 + cc8) * 16 + 8 + j];
+    }
+    const int c = cbase + cl;
+    const int i = n * K.C + c;
+    const double sc = drop ? static_cast<double>(drop[i]) : 1.0;
+    const double r = rstd[i];
+    const double S1 = sc * static_cast<double>(s1), S2 = sc * r * static_cast<double>(s2);
+    const double gr = static_cast<double>(gamma[c]) * r;
+    const float k1 = static_cast<float>(gr * sc);
+    const float k2 = static_cast<float>(gr * r * S2 * inv_hw);
+    const float k3 = static_cast<float>(gr * S1 * inv_hw);
+    coef[cl * 4 + 0] = k1;
+    coef[cl * 4 + 1] = k2;
+    coef[cl * 4 + 2] = fmaf(k2, K.mean[i], -k3);
+    imgsum[i * 2 + 0] = static_cast<float>(S1);
+    imgsum[i * 2 + 1] = static_cast<float>(S2);
+  }
+  __syncthreads();
+  float k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    k1[j] = coef[((c8 << 3) + j) * 4 + 0];
+    k2[j] = coef[((c8 << 3) + j) * 4 + 1];
+    k3[j] = coef[((c8 << 3) + j) * 4 + 2];
+  }
+  T* ob = dy + static_cast<int64_t>(n) * HW * dyp + c0;
+  for (int q = lane; q < HW; q += lanes) {  // this thread's own shared-memory entries
+    Vec8<T> vy, vd;
+    vy.r = ty[q * cg8 + c8];
+    vd.r = td[q * cg8 + c8];
+    float yv[8], d[8], o[8];
+    vy.unpack(yv);
+    vd.unpack(d);
+    if (HAS2) {
+      Vec8<T> v2;
+      v2.r = td2[q * cg8 + c8];
+      float d2[8];
+      v2.unpack(d2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += d2[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pre = fmaf(ra[j], yv[j], rb[j]);
+      const float gm = pre > 0.f ? d[j] : d[j] * K.slope;
+      o[j] = fmaf(k1[j], gm, fmaf(-k2[j], yv[j], k3[j]));
+    }
+    Vec8<T>::st(ob + static_cast<int64_t>(q) * dyp, o);
+  }
+}
+
+// channels per CTA of the fused form, 0 = not applicable (slab + 17 KB of scratch must fit 220 KB of shared memory)
+static int bwd_fused_group(int64_t HW, int C, bool has2) {
+  static const bool off = [] { const char* e = getenv("B200UNET_NO_NORM_FUSED"); return e && e[0] == '1'; }();  // A/B knob
+  if (off || HW > 4096) return 0;
+  if (has2 && HW > 256) return 0;  // measured at 32^2 x 512: 61.6 us fused against 50.0 us for the three kernels
+  const int64_t per_ch = HW * 2 * (has2 ? 3 : 2);
+  const int64_t budget = 96 * 1024;  // two CTAs per SM: the phases of one overlap the other's
+  for (int cg = 64; cg >= 16; cg >>= 1)
+    if (C % cg == 0 && per_ch * cg <= budget && HW >= 256 / (cg / 8)) return cg;
+  return 0;
 }
 
 static int check_nhwc(const char* what, int C, int64_t p0, int64_t p1, int64_t p2) {
@@ -490,17 +637,41 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
   K.chunk = chunk;
   const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(typename AccT<T>::type);
   const double inv_hw = 1.0 / static_cast<double>(HW);
+  if constexpr (sizeof(T) == 2) {
+    const int cg = bwd_fused_group(HW, C, has2);
+    if (cg) {
+      const size_t smem = static_cast<size_t>(HW) * cg * 2 * (has2 ? 3 : 2) + (256 * 16 + 64 * 4) * sizeof(float);
+      auto kern = has2 ? in_bwd_fused_kernel<true> : in_bwd_fused_kernel<false>;
+      static bool attr_set[2] = {false, false};
+      if (!attr_set[has2 ? 1 : 0]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set[has2 ? 1 : 0] = true;
+      }
+      K.n0 = 0;
+      kern<<<dim3(C / cg, N), 256, smem, st>>>(K, A->gamma, A->rstd, A->drop_scale, static_cast<T*>(A->dy), A->dy_pitch,
+                                              imgsum, cg / 8, inv_hw);
+      B200_LAUNCH_CHECK("in_bwd_fused_kernel");
+      in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+      B200_LAUNCH_CHECK("in_bwd_param_kernel");
+      return 0;
+    }
+  }
   for (int n0 = 0; n0 < N; n0 += ipc) {
     const int nn = (N - n0 < ipc) ? N - n0 : ipc;
     K.n0 = n0;
-    in_bwd_reduce_kernel<T><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+    if (has2) in_bwd_reduce_kernel<T, true><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+    else in_bwd_reduce_kernel<T, false><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
     B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
     in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
                                                                      imgsum, C, n0, inv_hw);
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
     K.chunk = chunk_apply;
-    in_bwd_apply_kernel<T><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
-        K, coef, static_cast<T*>(A->dy), A->dy_pitch);
+    if (has2)
+      in_bwd_apply_kernel<T, true><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+          K, coef, static_cast<T*>(A->dy), A->dy_pitch);
+    else
+      in_bwd_apply_kernel<T, false><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+          K, coef, static_cast<T*>(A->dy), A->dy_pitch);
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
