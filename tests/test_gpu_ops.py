@@ -268,3 +268,53 @@ def test_consumers_with_the_apply_pass_fused_in():
     dz, dw, db = ops.head_backward(dl.cuda(), y, wt.detach().cuda(), norm=(ad, bd, 0.01))
     assert O.rel_l2(dz.float(), zr.grad.permute(0, 2, 3, 1)) <= BF16_TOL
     assert O.rel_l2(dw, wt.grad) <= F32_TOL and O.rel_l2(db, bias.grad) <= F32_TOL
+
+
+def _guarded(shape, dtype=torch.bfloat16, guard=4096, fill=3.0):
+    """A tensor of `shape` carved out of the middle of a larger allocation whose margins hold a sentinel value."""
+    n = 1
+    for d in shape:
+        n *= d
+    buf = torch.full((n + 2 * guard,), fill, dtype=dtype, device="cuda")
+    return buf, buf[guard:guard + n].view(*shape)
+
+
+def _guards_intact(buf, guard=4096, fill=3.0):
+    return bool((buf[:guard].float() == fill).all()) and bool((buf[-guard:].float() == fill).all())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 9, 190, 32, 32), (1, 7, 70, 32, 32), (1, 13, 21, 64, 64), (1, 5, 130, 96, 32),
+                                            (1, 6, 9, 128, 256)])
+def test_conv_kernels_stay_inside_ragged_outputs(n, h, w, cin, cout):
+    """TMA stores clip at the tensor map's extents; the statistics and weight-gradient epilogues use plain stores.  Ragged
+    sizes (tiles hanging over every edge), outputs placed between sentinel margins: nothing outside may change."""
+    from unet_implementations_b200 import ops
+    x, _ = rand_act(n, h, w, cin, seed=31)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
+    wf, wd = ops.pack_conv_weights(wt)
+    ybuf, y = _guarded((n, h, w, cout))
+    ops.conv_fprop(x, wf, 1, out=y)
+    dy, _ = rand_act(n, h, w, cout, seed=32)
+    dbuf, dx = _guarded((n, h, w, cin))
+    ops.conv_dgrad(dy, wd, (h, w), 1, out=dx)
+    torch.cuda.synchronize()
+    assert _guards_intact(ybuf) and _guards_intact(dbuf)
+    assert torch.isfinite(y.float()).all() and torch.isfinite(dx.float()).all()
+    assert float((y.float() - 3.0).abs().max()) > 0  # the output itself was written
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 13, 10, 64), (1, 70, 66, 32), (1, 64, 8, 128), (3, 1, 1, 8)])
+def test_upsample_and_norm_kernels_stay_inside_ragged_outputs(n, h, w, c):
+    from unet_implementations_b200 import ops
+    x, _ = rand_act(n, h, w, c, seed=33)
+    a = torch.rand(n, c, device="cuda") + 0.5
+    b = torch.randn(n, c, device="cuda")
+    ubuf, up = _guarded((n, 2 * h, 2 * w, c))
+    ops.upsample2x(x, up, norm=(a, b, 0.01))
+    dbuf, dx = _guarded((n, h, w, c))
+    ops.upsample2x_backward(up, out=dx)
+    zbuf, z = _guarded((n, h, w, c))
+    ops.in_apply(x, a, b, 0.01, out=z)
+    torch.cuda.synchronize()
+    assert _guards_intact(ubuf) and _guards_intact(dbuf) and _guards_intact(zbuf)
+    assert torch.isfinite(up.float()).all() and torch.isfinite(dx.float()).all() and torch.isfinite(z.float()).all()
