@@ -168,8 +168,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Our_UNet fwd+loss+bwd, {args.size}x{args.size}, 3 classes, CPU fp32 (torch {torch.__version__})",
-                   "batch": batch, "note": "each step is a 4-image sample of the 32-image GPU step (images/s is per image)"},
+        "config": {"workload": f"Our_UNet training step (fwd + SimpleLoss + bwd), batch 32/GPU, {args.size}x{args.size} RGB, "
+                               "3-class masks, random-init weights (seed 1234)",
+                   "sample": f"each step is a {batch}-image sample of the 32-image step on the host CPU (images/s is per "
+                             f"image), fp32, torch {torch.__version__} CPU ops, {cores} threads",
+                   "batch": batch},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of batch {batch} after {warm} warm-up (oracle/unet_oracle.py, torch CPU ops)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
