@@ -19,6 +19,10 @@
 // weight tiles [3 kh][(co, j) x (parity, ci)] are built in shared memory by the epilogue warps at kernel start from
 // the ordinary packed weights (18 KB from L2 per CTA), so the C ABI and the packing are unchanged; the data gradient
 // only reads them flipped (kh -> 2 - kh, kw -> 2 - kw).
+// Roles (512 threads): warps 0..1 = TMA producers (one 24 KB patch per tile, 6 in flight), warp 2 = TMEM owner + the
+// MMA-issuing thread (12 MMAs per tile), warps 4..11 = two epilogue groups alternating tiles (tcgen05.ld, shuffle,
+// bf16 staging, TMA store), warps 12..15 = InstanceNorm partial sums of the staged tiles (forward only), handed over
+// through named barriers.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "conv_common.cuh"
