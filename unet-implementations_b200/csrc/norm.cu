@@ -78,10 +78,16 @@ __global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restric
   double s1 = 0.0, s2 = 0.0;
   if (c < C) {
     const float2* sp = reinterpret_cast<const float2*>(stats) + static_cast<int64_t>(n) * P * C + c;
-    for (int p = pg; p < P; p += 8) {
-      const float2 v = __ldg(sp + static_cast<int64_t>(p) * C);
-      s1 += v.x;
-      s2 += v.y;
+    for (int p = pg; p < P; p += 32) {  // four independent loads in flight: this kernel is pure latency
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (p + 8 * u < P) ? __ldg(sp + static_cast<int64_t>(p + 8 * u) * C) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1 += v[u].x;
+        s2 += v[u].y;
+      }
     }
   }
   red[pg][cl][0] = s1;
@@ -253,10 +259,16 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
   double t1 = 0.0, t2 = 0.0;
   if (c < C) {
     const float2* sp = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(n) * P * C + c;
-    for (int p = pg; p < P; p += 8) {
-      const float2 v = sp[static_cast<int64_t>(p) * C];
-      t1 += v.x;
-      t2 += v.y;
+    for (int p = pg; p < P; p += 32) {  // four independent loads in flight
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (p + 8 * u < P) ? sp[static_cast<int64_t>(p + 8 * u) * C] : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        t1 += v[u].x;
+        t2 += v[u].y;
+      }
     }
   }
   red[pg][cl][0] = t1;
