@@ -395,6 +395,23 @@ def main():
         ms_e2e = timed(e2e_region_step, args.steps)
         if not all(l == l and abs(l) < 1e6 for l in losses):
             raise SystemExit(f"bench.py: non-finite loss in the end-to-end region: {losses[-4:]}")
+    # ---- the same resident step followed by the trainer's optimizer step ("with and without SGD step"):
+    # SGD momentum 0.99, Nesterov, weight decay 1e-4 (train.py:445-451) through the fused multi-tensor kernel.  Last,
+    # because it changes the weights.
+    with_sgd = None
+    if not args.no_e2e:
+        from unet_implementations_b200.optim import FusedSGD
+        opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4)
+
+        def sgd_step():
+            step(image_d, mask_d)
+            opt.step()
+
+        for _ in range(3):
+            sgd_step()
+        ms_sgd = timed(sgd_step, args.steps) / args.steps
+        with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT,
+                    "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4), one multi-tensor launch"}
     clocks = sampler.stop() if sampler else None
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
     h2d = image_h.numel() * 4 + mask_h.numel() * 8
@@ -466,12 +483,13 @@ def main():
                                    f"batch {B}/GPU, {S}x{S} RGB, 3-class masks, random-init weights (seed 1234)",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "working set (>10 GB of activations per step) far exceeds the 126 MB L2; no flush needed",
-                       "optimizer_step": "not included (BASELINE.md: step = forward + loss + backward)",
+                       "optimizer_step": "not included in value / e2e (BASELINE.md: step = forward + loss + backward); measured beside them in with_optimizer_step",
                        "presteps": "30 untimed steps after the warm-up (power-cap steady state)",
                        "overlap": "weight-gradient kernels on a side stream beside the next layer's norm backward"
                                   if model.overlap_wgrad else "none (single stream)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
+            "with_optimizer_step": with_sgd,
             "gpu_launches": int(launches),
             "remeasured": remeasured,
             "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
