@@ -96,3 +96,33 @@ def test_weight_gradient_with_row_tap_on_x_and_column_tap_on_dy():
             dys = torch.roll(F.pad(dy[0], (1, 1)), shifts=kw - 1, dims=2)[:, :, 1:W + 1]
             dw[:, :, kh, kw] = torch.einsum("chw,ohw->oc", xp[:, kh:kh + H], dys)
     assert torch.allclose(dw, w.grad, atol=1e-12)
+
+
+def test_bilinear_2x_taps_and_gather_backward():
+    """csrc/resample.cu: out[2i] = .25 in[max(i-1,0)] + .75 in[i], out[2i+1] = .75 in[i] + .25 in[min(i+1,n-1)] per axis
+    (F.interpolate(mode='bilinear', align_corners=False) at an exact factor 2, unet.py:220-225); backward in gather form
+    din[i] = .75 (d[2i] + d[2i+1]) + .25 (d[2i-1] + d[2i+2]) where a tap that falls off the output did not exist --
+    its weight went to the edge sample instead: din[0] gets .25 d[0] more, din[n-1] gets .25 d[2n-1] more."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 2, 5, 6, generator=g, dtype=D).requires_grad_(True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+
+    def up_axis(t, dim):
+        n = t.shape[dim]
+        idx = torch.arange(n)
+        lo, hi = t.index_select(dim, (idx - 1).clamp(min=0)), t.index_select(dim, (idx + 1).clamp(max=n - 1))
+        even, odd = 0.25 * lo + 0.75 * t, 0.75 * t + 0.25 * hi
+        return torch.stack([even, odd], dim=dim + 1).flatten(dim, dim + 1)
+
+    assert torch.allclose(up_axis(up_axis(x.detach(), 3), 2), ref.detach(), atol=1e-12)   # along w first, then h
+    d = torch.randn_like(ref)
+    ref.backward(d)
+
+    def down_axis(t, dim):
+        m = t.shape[dim]
+        n = m // 2
+        i = torch.arange(n)
+        take = lambda j: t.index_select(dim, j.clamp(0, m - 1))  # noqa: E731  (clamped index = the edge sample)
+        return 0.75 * (take(2 * i) + take(2 * i + 1)) + 0.25 * (take(2 * i - 1) + take(2 * i + 2))
+
+    assert torch.allclose(down_axis(down_axis(d, 2), 3), x.grad, atol=1e-12)
