@@ -177,6 +177,15 @@ int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target, const flo
 int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target, const float* tables, const float* grad_out,
                       float weight_ce, float weight_dice, int ignore_index, float* dlogits_nchw, int N, int64_t HW,
                       void* stream);
+/* The same two passes with uint8 targets [N,H,W] in {0,1,2,255} -- the masks as the dataset stores them
+ * (train.py:300, :311 widens them to int64 only because nn.CrossEntropyLoss wants int64): 1 instead of 8 bytes per
+ * pixel across PCIe and through HBM. */
+int b200unet_loss_fwd_u8(const float* logits_nchw, const uint8_t* target, const float* class_weights, int dynamic,
+                         float weight_ce, float weight_dice, int ignore_index, float smooth, float* loss_out,
+                         float* tables, float* workspace, int64_t workspace_bytes, int N, int64_t HW, void* stream);
+int b200unet_loss_bwd_u8(const float* logits_nchw, const uint8_t* target, const float* tables, const float* grad_out,
+                         float weight_ce, float weight_dice, int ignore_index, float* dlogits_nchw, int N, int64_t HW,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout helpers used by the module-level (per-op) entry points and the tests.
@@ -261,10 +270,39 @@ int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int
  *   {0,1,2,255} int64 (other values become 0).  mean3/std3 are HOST pointers.  Either half may be NULL.  Bit-exact. */
 int b200unet_preprocess_u8(const void* image_u8_nhwc, const void* mask_u8, float* image_out_nchw, int64_t* mask_out,
                            const float* mean3, const float* std3, int N, int64_t HW, void* stream);
+/* preprocess_u8_nhwc32: the same image conversion written straight as the stem's tensor-core operand -- uint8 HWC
+ *   [N,H,W,3] -> (x / 255 - mean) / std (fp32, the reference's operations in its order) -> bf16 NHWC [N,H,W,32] with
+ *   channels 3..31 zero, in ONE kernel: bit-identical to preprocess_u8 followed by image_to_nhwc32_bf16, without the
+ *   12-byte/pixel fp32 round trip through HBM.  mean3/std3 are HOST pointers. */
+int b200unet_preprocess_u8_nhwc32(const void* image_u8_nhwc, void* dst_nhwc32, const float* mean3, const float* std3, int N,
+                                  int64_t HW, void* stream);
 int b200unet_sgd_max_tensors(void);
 int b200unet_sgd_nesterov_step(float* const* params, const float* const* grads, float* const* momentum_bufs,
                                const int64_t* numels, int count, float lr, float momentum, float weight_decay,
                                int nesterov, int first_step, void* stream);
+/* sgd_flat_step -- SURVEY.md 8f row 1 as written: the optimizer step of train.py:431-453 / :650 / :664 as ONE launch
+ *   over flat fp32 master / gradient / momentum buffers (all tensors at the same element offsets), which scales the
+ *   gradient (the mean of the gradient all-reduce, or a GradScaler's 1/scale), applies SGD + Nesterov momentum +
+ *   weight decay with the arithmetic of sgd_nesterov_step, and EMITS the bf16 packs the conv kernels read
+ *   ([Cout][3][3][Cin_pad], [Cin][3][3][Cout_pad], and the parity-stacked stride-2 dgrad pack) for every tensor whose
+ *   descriptor names them -- the per-step repack (pack_conv_weights) disappears.  `table_dev` is a DEVICE array of
+ *   `count` descriptors sorted by first_block; first_block = prefix sum of ceil(numel / sgd_flat_block_elems()).
+ *   flags bit 0: update this tensor; bit 1: first momentum step (buf = decayed gradient, as torch does). */
+typedef struct {
+  int64_t offset;      /* element offset of the tensor in the flat buffers */
+  int32_t numel;
+  int32_t flags;
+  int32_t first_block;
+  int32_t cout, cin, ksize; /* conv weight OIHW [cout][cin][ksize][ksize], ksize 3 or 1 (centre tap); unused without packs */
+  int32_t cout_pad, cin_pad; /* row lengths of the dgrad / fprop packs (zero padding is the caller's, written once) */
+  void* wf;            /* bf16 [cout][3][3][cin_pad] or NULL (no packs) */
+  void* wd;            /* bf16 [cin][3][3][cout_pad] or NULL */
+  void* ws;            /* bf16 [4*cin][4][cout] (b200unet_pack_s2_dgrad_weights layout) or NULL */
+} b200unet_flat_tensor;
+int b200unet_sgd_flat_block_elems(void);
+int b200unet_sgd_flat_step(const b200unet_flat_tensor* table_dev, int count, int total_blocks, float* master,
+                           const float* grad, float* momentum_buf, float lr, float momentum, float weight_decay,
+                           int nesterov, float grad_scale, void* stream);
 int b200unet_argmax_counts(const float* logits_nchw, const int64_t* target, int ignore_index, int64_t* pred_or_null,
                            int64_t* counts9, int N, int64_t HW, void* stream);
 

@@ -148,6 +148,41 @@ def test_full_size_tensor_core_convs_against_the_direct_kernels(name, cin, cout,
     assert O.rel_l2(ops.conv_wgrad(x, dy, stride), ops.conv_wgrad(x, dy, stride, simt=True)) <= 1e-3
 
 
+@pytest.mark.parametrize("name,cin,cout,stride,hw", FULL_LAYERS)
+def test_full_size_tensor_core_convs_against_torch_conv2d_on_the_gpu(name, cin, cout, stride, hw):
+    """The independent oracle at the benchmark's layer shapes (batch 32): the reference's own operator -- `F.conv2d`
+    and its autograd (Our_UNet/models/unet.py:106-115) -- in fp32 on the same GPU with TF32 off, fed the same
+    bf16-rounded operands.  Test infrastructure only; nothing on the product path calls torch's convolution."""
+    import torch.nn.functional as F
+    from unet_implementations_b200 import ops
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device="cuda").manual_seed(12)
+        x = torch.randn(B, hw, hw, cin, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5).bfloat16().float()
+        wf, wd = ops.pack_conv_weights(wt)
+        y, _ = ops.conv_fprop(x, wf, stride)
+        xn = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        wr = wt.clone().requires_grad_(True)
+        y_ref = F.conv2d(xn, wr, None, stride, 1)
+        assert O.rel_l2(y.float().permute(0, 3, 1, 2), y_ref.detach()) <= 4e-3
+        oh = y.shape[1]
+        dy = torch.randn(B, oh, oh, cout, device="cuda", generator=g).bfloat16()
+        y_ref.backward(dy.float().permute(0, 3, 1, 2))
+        del y_ref
+        if stride == 2 and cin <= 64:
+            dx = torch.empty((B, hw, hw, cin), dtype=torch.bfloat16, device="cuda")
+            ops.conv_dgrad_s2(dy, ops.pack_s2_dgrad_weights(wd), (hw, hw), out=dx)
+        else:
+            dx = ops.conv_dgrad(dy, wd, (hw, hw), stride)
+        assert O.rel_l2(dx.float().permute(0, 3, 1, 2), xn.grad) <= 4e-3
+        assert O.rel_l2(ops.conv_wgrad(x, dy, stride), wr.grad) <= 1e-3
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _act(shape, seed, scale=1.0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(*shape, device="cuda", generator=g) * scale).bfloat16()

@@ -47,6 +47,14 @@ class InBwdArgs(Structure):
     ]
 
 
+class FlatTensor(Structure):
+    """b200unet_flat_tensor (include/b200unet.h): one tensor of the flat optimizer step."""
+    _fields_ = [
+        ("offset", c_int64), ("numel", c_int), ("flags", c_int), ("first_block", c_int), ("cout", c_int), ("cin", c_int),
+        ("ksize", c_int), ("cout_pad", c_int), ("cin_pad", c_int), ("wf", c_void_p), ("wd", c_void_p), ("ws", c_void_p),
+    ]
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
 # name -> (restype, argtypes); restype c_int means "status code, raise on non-zero"
@@ -84,6 +92,8 @@ SIGNATURES = {
     "b200unet_loss_workspace": (c_int64, [_I, _L]),
     "b200unet_loss_fwd": (c_int, [_P, _P, _P, _I, _F, _F, _I, _F, _P, _P, _P, _L, _I, _L, _P]),
     "b200unet_loss_bwd": (c_int, [_P, _P, _P, _P, _F, _F, _I, _P, _I, _L, _P]),
+    "b200unet_loss_fwd_u8": (c_int, [_P, _P, _P, _I, _F, _F, _I, _F, _P, _P, _P, _L, _I, _L, _P]),
+    "b200unet_loss_bwd_u8": (c_int, [_P, _P, _P, _P, _F, _F, _I, _P, _I, _L, _P]),
     "b200unet_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, _L, _I, _I, _L, _P]),
     "b200unet_nhwc_bf16_to_nchw_f32": (c_int, [_P, _L, _P, _I, _I, _L, _P]),
     # fp32 verification mode: same signatures as the bf16 entry points
@@ -106,6 +116,9 @@ SIGNATURES = {
     "b200unet_head_norm_bwd": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_head_norm_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_preprocess_u8": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _P]),
+    "b200unet_preprocess_u8_nhwc32": (c_int, [_P, _P, _P, _P, _I, _L, _P]),
+    "b200unet_sgd_flat_block_elems": (c_int, []),
+    "b200unet_sgd_flat_step": (c_int, [_P, _I, _I, _P, _P, _P, _F, _F, _F, _I, _F, _P]),
     "b200unet_sgd_max_tensors": (c_int, []),
     "b200unet_sgd_nesterov_step": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _P]),
     "b200unet_argmax_counts": (c_int, [_P, _P, _I, _P, _P, _I, _L, _P]),
@@ -122,7 +135,7 @@ SIGNATURES = {
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_launch_count", "b200unet_conv_fprop_partials",
-    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_recon_head_bwd_workspace",
+    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_recon_head_bwd_workspace",
     "b200unet_conv_dgrad_s2_supported",
     "b200unet_mse_workspace",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",

@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, device check, TMA descriptor encoder.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace b200 {
@@ -67,12 +68,19 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return 0;
 }
 
+// SMs the grids of this library are sized for: the device's count minus B200UNET_RESERVED_SMS (data-parallel runs
+// keep a few SMs free for the NCCL kernels of the gradient all-reduce, so that a persistent one-CTA-per-SM conv kernel
+// never has a CTA waiting behind a communication kernel; ddp.init_process_group sets it).  Read once per process.
 int num_sms() {
   static int n = 0;
   if (n == 0) {
-    int dev = 0;
+    int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    const char* e = getenv("B200UNET_RESERVED_SMS");
+    const int r = e ? atoi(e) : 0;
+    if (r > 0 && r < v / 2) v -= r;
+    n = v;
   }
   return n;
 }

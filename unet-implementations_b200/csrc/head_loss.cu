@@ -32,44 +32,107 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return s;  // valid on thread 0
 }
 
-// grid (blocks_per_image, N)
+// Four consecutive pixels of one image per thread and step: three 16-byte logit loads (one per class plane) and one
+// 32-byte (int64) or 4-byte (uint8) target load.  `vec` = HW is a multiple of 4 (every plane and image then starts
+// 16-byte aligned); otherwise the same code runs on guarded scalar loads.
+template <typename TT>
+__device__ __forceinline__ void load_px4(const float* __restrict__ z0, const TT* __restrict__ tg, int64_t HW, int64_t px,
+                                         bool vec, float (&a)[3][4], int (&t)[4]) {
+  if (vec) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z0 + c * HW + px));
+      a[c][0] = v.x; a[c][1] = v.y; a[c][2] = v.z; a[c][3] = v.w;
+    }
+    if (sizeof(TT) == 8) {
+      const longlong2 u = __ldg(reinterpret_cast<const longlong2*>(tg + px));
+      const longlong2 w = __ldg(reinterpret_cast<const longlong2*>(tg + px) + 1);
+      // labels outside [0, 255] can match neither a class nor a (byte-sized) ignore index: map them to a value that
+      // matches nothing so that the 32-bit compare below equals the reference's 64-bit one
+      const long long q[4] = {u.x, u.y, w.x, w.y};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (q[j] < -(1ll << 30) || q[j] > (1ll << 30)) ? (1 << 30) + 1 : static_cast<int>(q[j]);
+    } else {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(tg + px));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = static_cast<int>((u >> (8 * j)) & 0xffu);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = px + j < HW;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[c][j] = in ? z0[c * HW + px + j] : 0.f;
+      long long q = in ? static_cast<long long>(tg[px + j]) : -1;
+      t[j] = (q < -(1ll << 30) || q > (1ll << 30)) ? (1 << 30) + 1 : static_cast<int>(q);
+      if (!in) t[j] = -2;  // outside the image: counted nowhere (handled by the caller through `in`)
+    }
+  }
+}
+
+// grid (blocks_per_image, N).  One pass; the twelve block sums are ONE round of warp shuffle trees + one fixed-order
+// sum over the eight warps (the first version ran twelve serial block reductions with two barriers each and scalar
+// 4-byte loads: 2.1 TB/s).
+template <typename TT>
 __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(const float* __restrict__ logits,
-                                                                 const int64_t* __restrict__ target, int ignore_index,
+                                                                 const TT* __restrict__ target, int ignore_index,
                                                                  float* __restrict__ part, int64_t HW) {
-  __shared__ float scratch[kLossThreads / 32];
+  __shared__ float scratch[kLossThreads / 32][kLossVals];
   const int n = blockIdx.y;
   const float* z0 = logits + static_cast<int64_t>(n) * kNC * HW;
-  const int64_t* tg = target + static_cast<int64_t>(n) * HW;
-  float cnt[kNC] = {0.f, 0.f, 0.f}, S[kNC] = {0.f, 0.f, 0.f}, I[kNC] = {0.f, 0.f, 0.f}, Pp[kNC] = {0.f, 0.f, 0.f};
+  const TT* tg = target + static_cast<int64_t>(n) * HW;
+  const bool vec = (HW & 3) == 0;
+  float acc[kLossVals];  // cnt[3], S[3], I[3], P[3]
+#pragma unroll
+  for (int i = 0; i < kLossVals; ++i) acc[i] = 0.f;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kLossThreads * kLossPxPerThread;
+  constexpr int kIters = kLossPxPerThread / 4;
+  float a[kIters][3][4];
+  int t[kIters][4];
+  bool live[kIters];
 #pragma unroll
-  for (int k = 0; k < kLossPxPerThread; ++k) {
-    const int64_t px = base + static_cast<int64_t>(k) * kLossThreads + threadIdx.x;
-    if (px >= HW) continue;
-    const int64_t t = tg[px];
-    if (t == ignore_index) continue;
-    const float a0 = z0[px], a1 = z0[HW + px], a2 = z0[2 * HW + px];
-    const float m = fmaxf(a0, fmaxf(a1, a2));
-    const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
-    const float se = e0 + e1 + e2;
-    const float inv = 1.f / se;
-    const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
-    const float lse = m + logf(se);
-    Pp[0] += p0;
-    Pp[1] += p1;
-    Pp[2] += p2;
-    if (t == 0) { cnt[0] += 1.f; S[0] += lse - a0; I[0] += p0; }
-    else if (t == 1) { cnt[1] += 1.f; S[1] += lse - a1; I[1] += p1; }
-    else if (t == 2) { cnt[2] += 1.f; S[2] += lse - a2; I[2] += p2; }
+  for (int k = 0; k < kIters; ++k) {
+    const int64_t px = base + (static_cast<int64_t>(k) * kLossThreads + threadIdx.x) * 4;
+    live[k] = px < HW;
+    if (live[k]) load_px4<TT>(z0, tg, HW, px, vec, a[k], t[k]);
   }
-  float* dst = part + (static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * kLossVals;
 #pragma unroll
-  for (int c = 0; c < kNC; ++c) {
-    float v;
-    v = block_sum(cnt[c], scratch); if (threadIdx.x == 0) dst[c] = v;
-    v = block_sum(S[c], scratch);   if (threadIdx.x == 0) dst[kNC + c] = v;
-    v = block_sum(I[c], scratch);   if (threadIdx.x == 0) dst[2 * kNC + c] = v;
-    v = block_sum(Pp[c], scratch);  if (threadIdx.x == 0) dst[3 * kNC + c] = v;
+  for (int k = 0; k < kIters; ++k) {
+    if (!live[k]) continue;
+    const int64_t px = base + (static_cast<int64_t>(k) * kLossThreads + threadIdx.x) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tj = t[k][j];
+      if (tj == ignore_index || (!vec && px + j >= HW)) continue;
+      const float a0 = a[k][0][j], a1 = a[k][1][j], a2 = a[k][2][j];
+      const float m = fmaxf(a0, fmaxf(a1, a2));
+      const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+      const float se = e0 + e1 + e2;
+      const float inv = 1.f / se;
+      const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+      const float lse = m + logf(se);
+      acc[9] += p0;
+      acc[10] += p1;
+      acc[11] += p2;
+      if (tj == 0) { acc[0] += 1.f; acc[3] += lse - a0; acc[6] += p0; }
+      else if (tj == 1) { acc[1] += 1.f; acc[4] += lse - a1; acc[7] += p1; }
+      else if (tj == 2) { acc[2] += 1.f; acc[5] += lse - a2; acc[8] += p2; }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kLossVals; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) scratch[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kLossVals) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) s += scratch[w][threadIdx.x];
+    part[(static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * kLossVals + threadIdx.x] = s;
   }
 }
 
@@ -143,8 +206,9 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks,
   loss_out[2] = static_cast<float>(dice_loss);
 }
 
+template <typename TT>
 __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const float* __restrict__ logits,
-                                                                 const int64_t* __restrict__ target,
+                                                                 const TT* __restrict__ target,
                                                                  const float* __restrict__ tables,
                                                                  const float* __restrict__ grad_out, float weight_ce,
                                                                  float weight_dice, int ignore_index,
@@ -156,31 +220,59 @@ __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const float* __r
   const float A0 = tb[0], A1 = tb[1], A2 = tb[2], B0 = tb[3], B1 = tb[4], B2 = tb[5];
   const float* z0 = logits + static_cast<int64_t>(n) * kNC * HW;
   float* d0 = dlogits + static_cast<int64_t>(n) * kNC * HW;
-  const int64_t* tg = target + static_cast<int64_t>(n) * HW;
+  const TT* tg = target + static_cast<int64_t>(n) * HW;
+  const bool vec = (HW & 3) == 0;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kLossThreads * kLossPxPerThread;
+  constexpr int kIters = kLossPxPerThread / 4;
+  float a[kIters][3][4];
+  int t[kIters][4];
+  bool live[kIters];
 #pragma unroll
-  for (int k = 0; k < kLossPxPerThread; ++k) {
-    const int64_t px = base + static_cast<int64_t>(k) * kLossThreads + threadIdx.x;
-    if (px >= HW) continue;
-    const int64_t t = tg[px];
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (t != ignore_index) {
-      const float a0 = z0[px], a1 = z0[HW + px], a2 = z0[2 * HW + px];
-      const float m = fmaxf(a0, fmaxf(a1, a2));
-      const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
-      const float inv = 1.f / (e0 + e1 + e2);
-      const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
-      const float wt = t == 0 ? wn0 : (t == 1 ? wn1 : (t == 2 ? wn2 : 0.f));
-      // dDice/dp_c
-      const float G0 = B0 + (t == 0 ? A0 : 0.f), G1 = B1 + (t == 1 ? A1 : 0.f), G2 = B2 + (t == 2 ? A2 : 0.f);
-      const float gp = G0 * p0 + G1 * p1 + G2 * p2;
-      g0 = weight_ce * wt * (p0 - (t == 0 ? 1.f : 0.f)) + weight_dice * p0 * (G0 - gp);
-      g1 = weight_ce * wt * (p1 - (t == 1 ? 1.f : 0.f)) + weight_dice * p1 * (G1 - gp);
-      g2 = weight_ce * wt * (p2 - (t == 2 ? 1.f : 0.f)) + weight_dice * p2 * (G2 - gp);
+  for (int k = 0; k < kIters; ++k) {
+    const int64_t px = base + (static_cast<int64_t>(k) * kLossThreads + threadIdx.x) * 4;
+    live[k] = px < HW;
+    if (live[k]) load_px4<TT>(z0, tg, HW, px, vec, a[k], t[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kIters; ++k) {
+    if (!live[k]) continue;
+    const int64_t px = base + (static_cast<int64_t>(k) * kLossThreads + threadIdx.x) * 4;
+    float g[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tj = t[k][j];
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      if (tj != ignore_index) {
+        const float a0 = a[k][0][j], a1 = a[k][1][j], a2 = a[k][2][j];
+        const float m = fmaxf(a0, fmaxf(a1, a2));
+        const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+        const float inv = 1.f / (e0 + e1 + e2);
+        const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+        const float wt = tj == 0 ? wn0 : (tj == 1 ? wn1 : (tj == 2 ? wn2 : 0.f));
+        // dDice/dp_c
+        const float G0 = B0 + (tj == 0 ? A0 : 0.f), G1 = B1 + (tj == 1 ? A1 : 0.f), G2 = B2 + (tj == 2 ? A2 : 0.f);
+        const float gp = G0 * p0 + G1 * p1 + G2 * p2;
+        g0 = weight_ce * wt * (p0 - (tj == 0 ? 1.f : 0.f)) + weight_dice * p0 * (G0 - gp);
+        g1 = weight_ce * wt * (p1 - (tj == 1 ? 1.f : 0.f)) + weight_dice * p1 * (G1 - gp);
+        g2 = weight_ce * wt * (p2 - (tj == 2 ? 1.f : 0.f)) + weight_dice * p2 * (G2 - gp);
+      }
+      g[0][j] = g0 * gs;
+      g[1][j] = g1 * gs;
+      g[2][j] = g2 * gs;
     }
-    d0[px] = g0 * gs;
-    d0[HW + px] = g1 * gs;
-    d0[2 * HW + px] = g2 * gs;
+    if (vec) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<float4*>(d0 + c * HW + px) = make_float4(g[c][0], g[c][1], g[c][2], g[c][3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (px + j < HW) {
+          d0[px + j] = g[0][j];
+          d0[HW + px + j] = g[1][j];
+          d0[2 * HW + px + j] = g[2][j];
+        }
+    }
   }
 }
 
@@ -447,16 +539,16 @@ extern "C" int64_t b200unet_loss_workspace(int N, int64_t HW) {
   return static_cast<int64_t>(N) * blocks * kLossVals * 4;
 }
 
-extern "C" int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target, const float* class_weights,
-                                 int dynamic, float weight_ce, float weight_dice, int ignore_index, float smooth,
-                                 float* loss_out, float* tables, float* workspace, int64_t workspace_bytes, int N,
-                                 int64_t HW, void* stream) {
+template <typename TT>
+static int loss_fwd_impl(const float* logits_nchw, const TT* target, const float* class_weights, int dynamic,
+                         float weight_ce, float weight_dice, int ignore_index, float smooth, float* loss_out,
+                         float* tables, float* workspace, int64_t workspace_bytes, int N, int64_t HW, void* stream) {
   B200_CHECK_ARG(logits_nchw && target && loss_out && tables && workspace, "loss_fwd: null pointer");
   B200_CHECK_ARG(N > 0 && HW > 0, "loss_fwd: empty batch");
   B200_CHECK_ARG(workspace_bytes >= b200unet_loss_workspace(N, HW), "loss_fwd: workspace too small");
   const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  loss_fwd_kernel<<<dim3(blocks, N), kLossThreads, 0, st>>>(logits_nchw, target, ignore_index, workspace, HW);
+  loss_fwd_kernel<TT><<<dim3(blocks, N), kLossThreads, 0, st>>>(logits_nchw, target, ignore_index, workspace, HW);
   B200_LAUNCH_CHECK("loss_fwd_kernel");
   const size_t smem = static_cast<size_t>(N) * kLossVals * sizeof(double);
   B200_CHECK_ARG(smem <= 48 * 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
@@ -466,15 +558,44 @@ extern "C" int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target
   return 0;
 }
 
-extern "C" int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target, const float* tables,
-                                 const float* grad_out, float weight_ce, float weight_dice, int ignore_index,
-                                 float* dlogits_nchw, int N, int64_t HW, void* stream) {
+template <typename TT>
+static int loss_bwd_impl(const float* logits_nchw, const TT* target, const float* tables, const float* grad_out,
+                         float weight_ce, float weight_dice, int ignore_index, float* dlogits_nchw, int N, int64_t HW,
+                         void* stream) {
   B200_CHECK_ARG(logits_nchw && target && tables && dlogits_nchw, "loss_bwd: null pointer");
   const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
-  loss_bwd_kernel<<<dim3(blocks, N), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  loss_bwd_kernel<TT><<<dim3(blocks, N), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       logits_nchw, target, tables, grad_out, weight_ce, weight_dice, ignore_index, dlogits_nchw, HW);
   B200_LAUNCH_CHECK("loss_bwd_kernel");
   return 0;
+}
+
+extern "C" int b200unet_loss_fwd(const float* logits_nchw, const int64_t* target, const float* class_weights,
+                                 int dynamic, float weight_ce, float weight_dice, int ignore_index, float smooth,
+                                 float* loss_out, float* tables, float* workspace, int64_t workspace_bytes, int N,
+                                 int64_t HW, void* stream) {
+  return loss_fwd_impl<int64_t>(logits_nchw, target, class_weights, dynamic, weight_ce, weight_dice, ignore_index, smooth,
+                                loss_out, tables, workspace, workspace_bytes, N, HW, stream);
+}
+extern "C" int b200unet_loss_fwd_u8(const float* logits_nchw, const uint8_t* target, const float* class_weights,
+                                    int dynamic, float weight_ce, float weight_dice, int ignore_index, float smooth,
+                                    float* loss_out, float* tables, float* workspace, int64_t workspace_bytes, int N,
+                                    int64_t HW, void* stream) {
+  return loss_fwd_impl<uint8_t>(logits_nchw, target, class_weights, dynamic, weight_ce, weight_dice, ignore_index, smooth,
+                                loss_out, tables, workspace, workspace_bytes, N, HW, stream);
+}
+
+extern "C" int b200unet_loss_bwd(const float* logits_nchw, const int64_t* target, const float* tables,
+                                 const float* grad_out, float weight_ce, float weight_dice, int ignore_index,
+                                 float* dlogits_nchw, int N, int64_t HW, void* stream) {
+  return loss_bwd_impl<int64_t>(logits_nchw, target, tables, grad_out, weight_ce, weight_dice, ignore_index, dlogits_nchw,
+                                N, HW, stream);
+}
+extern "C" int b200unet_loss_bwd_u8(const float* logits_nchw, const uint8_t* target, const float* tables,
+                                    const float* grad_out, float weight_ce, float weight_dice, int ignore_index,
+                                    float* dlogits_nchw, int N, int64_t HW, void* stream) {
+  return loss_bwd_impl<uint8_t>(logits_nchw, target, tables, grad_out, weight_ce, weight_dice, ignore_index, dlogits_nchw,
+                                N, HW, stream);
 }
 
 template <typename T>

@@ -56,6 +56,75 @@ __global__ void __launch_bounds__(kSgdThreads) sgd_nesterov_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ flat optimizer step
+// SURVEY.md 8f row 1 as written: ONE launch over the flat fp32 master / gradient / momentum buffers that (i) applies
+// the all-reduce epilogue scale to the gradient, (ii) does the SGD-Nesterov update of sgd_nesterov_kernel (same
+// operations in the same order: bit-exact with torch.optim.SGD for scale 1) and (iii) emits the bf16 operand packs
+// the conv kernels consume -- [Cout][3][3][Cin] (fprop), [Cin][3][3][Cout] (dgrad) and the parity-stacked stride-2
+// dgrad pack -- so that no repack kernel runs between the optimizer and the next forward and the packs can never be
+// stale.  Threads walk a tensor in OIHW order (the 20 B/parameter of fp32 traffic is coalesced); the two or three
+// 2-byte pack stores per parameter are scattered and merge in L2 (the packs are 80 MB, the L2 126 MB).
+constexpr int kFlatThreads = 256, kFlatPerThread = 4;
+
+__global__ void __launch_bounds__(kFlatThreads) sgd_flat_kernel(const b200unet_flat_tensor* __restrict__ T, int count,
+                                                                 float* __restrict__ master,
+                                                                 const float* __restrict__ grad,
+                                                                 float* __restrict__ mom, float lr, float momentum,
+                                                                 float wd, int nesterov, float grad_scale) {
+  int lo = 0, hi = count;
+  const int b = blockIdx.x;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&T[mid].first_block) <= b) lo = mid; else hi = mid;
+  }
+  const b200unet_flat_tensor D = T[lo];
+  if (!(D.flags & 1)) return;
+  const bool first = (D.flags & 2) != 0;
+  float* __restrict__ p = master + D.offset;
+  const float* __restrict__ g = grad + D.offset;
+  float* __restrict__ buf = mom ? mom + D.offset : nullptr;
+  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(D.wf);
+  __nv_bfloat16* wdp = static_cast<__nv_bfloat16*>(D.wd);
+  __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(D.ws);
+  const int kk = D.ksize * D.ksize;
+  const int per_o = D.cin * kk;
+  const int base = (b - D.first_block) * kFlatThreads * kFlatPerThread;
+#pragma unroll
+  for (int k = 0; k < kFlatPerThread; ++k) {
+    const int i = base + k * kFlatThreads + threadIdx.x;
+    if (i >= D.numel) break;
+    const float pv = p[i];
+    float gv = g[i];
+    if (grad_scale != 1.f) gv = __fmul_rn(gv, grad_scale);
+    if (wd != 0.f) gv = fmaf(wd, pv, gv);
+    float upd = gv;
+    if (momentum != 0.f) {
+      const float bv = first ? gv : __fadd_rn(__fmul_rn(buf[i], momentum), gv);
+      buf[i] = bv;
+      upd = nesterov ? fmaf(momentum, bv, gv) : bv;
+    }
+    const float pn = fmaf(-lr, upd, pv);
+    p[i] = pn;
+    if (wf) {
+      const int o = i / per_o;
+      const int r = i - o * per_o;
+      const int ci = r / kk;
+      const int tap = (kk == 9) ? (r - ci * 9) : 4;  // a 1x1 weight is the centre tap of a zero 3x3 kernel
+      const __nv_bfloat16 v = __float2bfloat16_rn(pn);
+      wf[(static_cast<int64_t>(o) * 9 + tap) * D.cin_pad + ci] = v;
+      if (wdp) wdp[(static_cast<int64_t>(ci) * 9 + tap) * D.cout_pad + o] = v;
+      if (ws) {
+        // parity-stacked stride-2 dgrad pack [4*Cin][4][Cout] (pack_s2_dgrad_weights_kernel): tap kh serves input-row
+        // parity ph with shift dh:  kh = 1 -> (0, 0),  kh = 2 -> (1, 0),  kh = 0 -> (1, 1); same along w
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const int ph = kh == 1 ? 0 : 1, dh = kh == 0 ? 1 : 0;
+        const int pw = kw == 1 ? 0 : 1, dw = kw == 0 ? 1 : 0;
+        ws[((static_cast<int64_t>(ph * 2 + pw) * D.cin + ci) * 4 + (dh * 2 + dw)) * D.cout + o] = v;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ validation
 constexpr int kEvalThreads = 256, kEvalPerThread = 8;
 
@@ -128,6 +197,45 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
   }
 }
 
+
+// uint8 HWC -> normalised bf16 NHWC zero-padded to 32 channels (the stem's operand): four pixels per thread (one
+// 12-byte read, four 64-byte rows written).
+__global__ void __launch_bounds__(256) preprocess_u8_nhwc32_kernel(const uint8_t* __restrict__ img, uint4* __restrict__ dst,
+                                                                    float m0, float m1, float m2, float s0, float s1,
+                                                                    float s2, int64_t total_px) {
+  const int64_t px0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (px0 >= total_px) return;
+  uint8_t v[12];
+  if (px0 + 4 <= total_px) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(img + px0 * 3);  // px0 % 4 == 0: 12-byte aligned groups
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = (w0 >> (8 * j)) & 0xff;
+      v[4 + j] = (w1 >> (8 * j)) & 0xff;
+      v[8 + j] = (w2 >> (8 * j)) & 0xff;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = (px0 * 3 + j < total_px * 3) ? img[px0 * 3 + j] : 0;
+  }
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (px0 + j >= total_px) break;
+    const float r = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[3 * j + 0]), 255.f), m0), s0);
+    const float g = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[3 * j + 1]), 255.f), m1), s1);
+    const float b = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[3 * j + 2]), 255.f), m2), s2);
+    const __nv_bfloat162 rg = __floats2bfloat162_rn(r, g);
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(b, 0.f);
+    uint4* o = dst + (px0 + j) * 4;
+    o[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&b0), 0u, 0u);
+    o[1] = z;
+    o[2] = z;
+    o[3] = z;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -163,6 +271,19 @@ extern "C" int b200unet_sgd_nesterov_step(float* const* params, const float* con
   return 0;
 }
 
+extern "C" int b200unet_sgd_flat_block_elems(void) { return kFlatThreads * kFlatPerThread; }
+
+extern "C" int b200unet_sgd_flat_step(const b200unet_flat_tensor* table_dev, int count, int total_blocks, float* master,
+                                      const float* grad, float* momentum_buf, float lr, float momentum,
+                                      float weight_decay, int nesterov, float grad_scale, void* stream) {
+  B200_CHECK_ARG(table_dev && master && grad && count > 0 && total_blocks > 0, "sgd_flat_step: null pointer or empty table");
+  B200_CHECK_ARG(momentum == 0.f || momentum_buf, "sgd_flat_step: momentum buffer required");
+  sgd_flat_kernel<<<total_blocks, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      table_dev, count, master, grad, momentum_buf, lr, momentum, weight_decay, nesterov, grad_scale);
+  B200_LAUNCH_CHECK("sgd_flat_kernel");
+  return 0;
+}
+
 extern "C" int b200unet_argmax_counts(const float* logits_nchw, const int64_t* target, int ignore_index,
                                       int64_t* pred_or_null, int64_t* counts9, int N, int64_t HW, void* stream) {
   B200_CHECK_ARG(logits_nchw && target && counts9, "argmax_counts: null pointer");
@@ -187,5 +308,19 @@ extern "C" int b200unet_preprocess_u8(const void* image_u8_nhwc, const void* mas
       static_cast<const uint8_t*>(image_u8_nhwc), static_cast<const uint8_t*>(mask_u8), image_out_nchw, mask_out, m[0], m[1],
       m[2], sd[0], sd[1], sd[2], HW);
   B200_LAUNCH_CHECK("preprocess_u8_kernel");
+  return 0;
+}
+
+extern "C" int b200unet_preprocess_u8_nhwc32(const void* image_u8_nhwc, void* dst_nhwc32, const float* mean3,
+                                             const float* std3, int N, int64_t HW, void* stream) {
+  B200_CHECK_ARG(image_u8_nhwc && dst_nhwc32 && mean3 && std3, "preprocess_u8_nhwc32: null pointer");
+  B200_CHECK_ARG(N > 0 && HW > 0, "preprocess_u8_nhwc32: bad sizes");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(image_u8_nhwc) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_nhwc32) & 15) == 0,
+                 "preprocess_u8_nhwc32: source must be 4-byte and destination 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(N) * HW;
+  preprocess_u8_nhwc32_kernel<<<(unsigned)ceil_div64(total, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(image_u8_nhwc), static_cast<uint4*>(dst_nhwc32), mean3[0], mean3[1], mean3[2], std3[0],
+      std3[1], std3[2], total);
+  B200_LAUNCH_CHECK("preprocess_u8_nhwc32_kernel");
   return 0;
 }

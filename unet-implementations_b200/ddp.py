@@ -6,105 +6,116 @@ so batch sharding needs no collective in the forward.  `SimpleLoss` normalises o
 (losses.py:44-60, :118), so the all-reduced gradient is the mean over ranks of the per-rank oracle gradients --
 exactly what stock DistributedDataParallel around the reference would compute.
 
-Mechanism: `UNet`'s fused backward hands every parameter gradient to `model._grad_sink(param, grad)` in the order
-it produces them (head, decoder 4..0, bottleneck, encoder 4..0).  The sink copies it into one flat fp32 buffer laid
-out in that order; when the last gradient of a bucket has arrived the bucket is all-reduced asynchronously
-(NCCL runs it on its own stream, ordered after the producing kernels) while backward keeps launching dgrad/wgrad
-kernels.  `finish()` -- called at the end of backward -- makes the compute stream wait for the outstanding buckets.
-The gradients autograd returns are views of the flat buffer.
+Mechanism: `UNet`'s fused backward has every gradient-producing kernel write straight into one flat fp32 buffer laid
+out in production order (flat.FlatGradSink: head, decoder 4..0, bottleneck, encoder 4..0 -- no per-gradient copy);
+when the last gradient of a bucket has been delivered the bucket is all-reduced asynchronously (NCCL runs it on its
+own stream, ordered after the producing kernels) while backward keeps launching dgrad/wgrad kernels.  `finish()` --
+called at the end of backward -- reduces whatever is left and makes the compute stream wait for the outstanding
+buckets.  The gradients autograd returns are views of the flat buffer.
+
+NCCL and the persistent conv kernels.  The tensor-core conv kernels run one CTA per SM with ~226 KB of shared memory;
+an NCCL kernel that lands on an SM delays that SM's CTA, and a persistent kernel is as slow as its slowest CTA
+(round 1: dgrad +11 %, wgrad +4 % at 8 GPUs).  The payload is tiny against NVLink (78.6 MB per 22 ms step), so the
+communicator is capped to a few CTAs (`nccl_options`, NCCL_MAX_CTAS) and the conv kernels leave that many SMs free
+while a reducer is attached (`B200UNET_RESERVED_SMS`, read by the library's grid sizing).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from .flat import FlatGradSink, backward_param_order  # noqa: F401  (re-exported)
 
-def backward_param_order(model) -> List[nn.Parameter]:
-    """Parameters in the order UNet's backward produces their gradients (models/unet.py:_backward_impl)."""
-    order: List[nn.Parameter] = []
-    head = model.segmentation_output
-    order += [head.weight] + ([head.bias] if head.bias is not None else [])
-    layers = model._layers()
-    fusion = model._fusion_unit() if hasattr(model, "_fusion_unit") else None
-    if fusion is not None:  # between the encoder and the decoder (models/clip_unet.py); needs the extra features every step
-        layers = [L for L in layers if L["kind"] == "enc"] + [dict(kind="fusion", unit=fusion)] + \
-                 [L for L in layers if L["kind"] == "dec"]
-    for L in reversed(layers):
-        conv, norm, _, _ = L["unit"]
-        order += [norm.weight, norm.bias]
-        if conv.bias is not None:
-            order.append(conv.bias)
-        order.append(conv.weight)
-    return order
+DEFAULT_NCCL_CTAS = 4
 
 
-class BucketedGradAllReduce:
+def nccl_options(max_ctas: int = DEFAULT_NCCL_CTAS):
+    """ProcessGroupNCCL options that cap the communicator at `max_ctas` CTAs (ncclConfig.maxCTAs)."""
+    opts = dist.ProcessGroupNCCL.Options()
+    try:
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+    except AttributeError:  # a torch build without ncclConfig plumbing: the environment variable does the same
+        pass
+    return opts
+
+
+def init_process_group(device: torch.device, max_ctas: Optional[int] = None, reserve_sms: Optional[int] = None):
+    """`dist.init_process_group("nccl")` for one process per GPU with the communicator capped to `max_ctas` CTAs and
+    as many SMs kept free by the persistent conv kernels.  Environment overrides: B200UNET_NCCL_CTAS,
+    B200UNET_RESERVED_SMS (0 disables)."""
+    ctas = int(os.environ.get("B200UNET_NCCL_CTAS", max_ctas if max_ctas is not None else DEFAULT_NCCL_CTAS))
+    os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+    os.environ.setdefault("NCCL_MIN_CTAS", "1")
+    if "B200UNET_RESERVED_SMS" not in os.environ:
+        os.environ["B200UNET_RESERVED_SMS"] = str(reserve_sms if reserve_sms is not None else ctas)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=device, pg_options=nccl_options(ctas))
+    return ctas
+
+
+class BucketedGradAllReduce(FlatGradSink):
     """Gradient sink: flat fp32 buffer + bucketed asynchronous all-reduce (mean) over `group`."""
 
     def __init__(self, model, group=None, bucket_bytes: int = 16 << 20, device: Optional[torch.device] = None):
+        super().__init__(model, device=device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
-        params = [p for p in backward_param_order(model) if p.requires_grad]
-        dev = device or params[0].device
-        self.offsets: Dict[int, int] = {}
-        self.bucket_of: Dict[int, int] = {}
         self.buckets: List[List[int]] = []  # [start, end) element ranges
-        off, start, last_ids = 0, 0, []
-        self.last_param_of_bucket: Dict[int, int] = {}
-        for p in params:
-            self.offsets[id(p)] = off
+        self.bucket_of: Dict[int, int] = {}
+        start = 0
+        for p in self.params:
+            end = self.offsets[id(p)] + (p.numel() + 3) // 4 * 4
             self.bucket_of[id(p)] = len(self.buckets)
-            off += (p.numel() + 3) // 4 * 4  # keep every gradient 16-byte aligned
-            last = id(p)
-            if (off - start) * 4 >= bucket_bytes:
-                self.buckets.append([start, off])
-                self.last_param_of_bucket[last] = len(self.buckets) - 1
-                start = off
-        if off > start:
-            self.buckets.append([start, off])
-            self.last_param_of_bucket[id(params[-1])] = len(self.buckets) - 1
-        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+            if (end - start) * 4 >= bucket_bytes:
+                self.buckets.append([start, end])
+                start = end
+        if self.numel > start:
+            self.buckets.append([start, self.numel])
         # gradients may arrive slightly out of production order (weight gradients run on a side stream and are
         # delivered one layer later): a bucket is reduced when ALL of its parameters have arrived
         self.bucket_size: List[int] = [0] * len(self.buckets)
-        for p in params:
-            b = 0
-            while not (self.buckets[b][0] <= self.offsets[id(p)] < self.buckets[b][1]):
-                b += 1
-            self.bucket_of[id(p)] = b
-            self.bucket_size[b] += 1
+        for p in self.params:
+            self.bucket_size[self.bucket_of[id(p)]] += 1
         self.arrived: List[int] = [0] * len(self.buckets)
+        self.reduced: List[bool] = [False] * len(self.buckets)
         self.works: list = []
-        self.numel = off
-        model._grad_sink = self
+        self.enabled = True  # False = accumulate locally (no_sync)
 
-    def __call__(self, p: nn.Parameter, g: torch.Tensor) -> torch.Tensor:
-        off = self.offsets[id(p)]
-        view = self.flat[off:off + p.numel()].view_as(p)
-        view.copy_(g)
+    def _reduce(self, b: int) -> None:
+        self.reduced[b] = True
+        if self.world <= 1 or not self.enabled:
+            return
+        lo, hi = self.buckets[b]
+        chunk = self.flat[lo:hi]
+        op = dist.ReduceOp.AVG if self.backend == "nccl" else dist.ReduceOp.SUM
+        self.works.append(dist.all_reduce(chunk, op=op, group=self.group, async_op=True))
+
+    def delivered(self, p: nn.Parameter) -> None:
         b = self.bucket_of[id(p)]
         self.arrived[b] += 1
-        if self.arrived[b] == self.bucket_size[b] and self.world > 1:
-            lo, hi = self.buckets[b]
-            chunk = self.flat[lo:hi]
-            if self.backend == "nccl":
-                self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
-            else:
-                self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        return view
+        if self.arrived[b] == self.bucket_size[b]:
+            self._reduce(b)
 
-    def finish(self):
-        """Block the current stream (not the host) until every outstanding bucket has been reduced."""
+    def finish(self) -> None:
+        """Reduce the buckets that did not fill up (a parameter without a gradient this step -- a frozen layer, an
+        unused fusion conv -- must not leave its bucket mates un-reduced), then block the current stream (not the
+        host) until every outstanding bucket has been reduced."""
+        for b in range(len(self.buckets)):
+            if not self.reduced[b] and self.arrived[b] > 0:
+                self._reduce(b)
         for w in self.works:
             w.wait()
         if self.works and self.backend != "nccl":
             self.flat.mul_(1.0 / self.world)
         self.works = []
         self.arrived = [0] * len(self.buckets)
+        self.reduced = [False] * len(self.buckets)
 
 
 def broadcast_parameters(model, src: int = 0, group=None):

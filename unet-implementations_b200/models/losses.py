@@ -27,7 +27,9 @@ class _SimpleLossFunction(torch.autograd.Function):
             if lg.dtype != torch.float32 or not lg.is_contiguous():
                 lg = lg.float().contiguous()  # the reference's CE/softmax run in fp32 under autocast
             tg = target.detach()
-            if tg.dtype != torch.int64 or not tg.is_contiguous():
+            if tg.dtype == torch.uint8:  # masks as the dataset stores them: read as they are
+                tg = tg.contiguous()
+            elif tg.dtype != torch.int64 or not tg.is_contiguous():
                 tg = tg.long().contiguous()
             out, tables = ops.loss_forward(lg, tg, class_weights, dynamic, weight_ce, weight_dice, ignore_index, smooth)
         ctx.save_for_backward(lg, tg, tables)

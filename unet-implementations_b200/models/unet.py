@@ -134,9 +134,11 @@ class UpBlock(nn.Module):
                                     spatial_dropout_rate=spatial_dropout_rate)
 
     def forward(self, x, skip):
-        raise NotImplementedError(
-            "b200unet: UpBlock runs only inside UNet.forward, where the upsample writes straight into the concat "
-            "buffer; there is no stand-alone NCHW path for it")
+        """Stand-alone use (NCHW fp32 in and out, unet.py:203-231): bilinear 2x upsample written into the concat buffer
+        next to the skip, then the ConvBlock.  `UNet.forward` does not go through here (it keeps everything NHWC)."""
+        if not (x.is_cuda and skip.is_cuda):
+            raise RuntimeError("b200unet: UpBlock needs CUDA tensors on an sm_100 device; there is no CPU path")
+        return self.conv_block(_UpsampleCatFunction.apply(x, skip))
 
 
 class UNet(nn.Module):
@@ -198,6 +200,8 @@ class UNet(nn.Module):
         self._mask_override: Optional[List[torch.Tensor]] = None  # inject dropout masks instead of drawing them
         self.last_dropout_masks: List[torch.Tensor] = []          # [N,C] scales used by the last training forward
         self._trace = None                                        # debug: list collecting (raw conv out, activation) per unit
+        self._trace_bwd = None                                    # debug: list collecting the backward tensors per unit
+        self._trace_fwd = None                                    # debug: forward tensors per unit WITHOUT changing the path
         self._grad_sink = None                                    # callable(param, grad) fired as backward produces grads
         # backward runs each weight-gradient kernel (tensor-bound) on a side stream, concurrently with the NEXT layer's
         # InstanceNorm backward (HBM-bound) on the main stream; B200UNET_OVERLAP=0 or this flag = False serialises
@@ -255,10 +259,24 @@ class UNet(nn.Module):
                 layers.append(dict(kind="dec", stage=j, idx=i, last=(i == len(us) - 1), unit=u))
         return layers
 
+    def _ext(self, w: nn.Parameter, dtype):
+        """The bf16 packs of weight `w` maintained by the fused optimizer step (optim.FusedSGD(model=...) emits them from
+        the updated master weights inside its one launch), if they were made from exactly the current values."""
+        packs = getattr(self, "_ext_packs", None)
+        if not packs or dtype != BF16:
+            return None
+        spec = packs.get(id(w))
+        if spec is None or spec["version"] != w._version or spec["wf"].device != w.device:
+            return None  # someone else wrote the weight since (load_state_dict, an in-place init): repack as usual
+        return spec
+
     def _packed(self, conv: nn.Conv2d, need_dgrad: bool, dtype=BF16):
         """Repacks of a conv weight for the conv kernels ([Cout,3,3,Cin] and [Cin,3,3,Cout], bf16 or fp32), cached on
         the parameter's version counter."""
         w = conv.weight
+        ext = self._ext(w, dtype)
+        if ext is not None and (ext["wd"] is not None or not need_dgrad):
+            return ext["wf"], ext["wd"]
         key = id(w)
         ver = w._version
         hit = self._pack_cache.get(key)
@@ -272,6 +290,9 @@ class UNet(nn.Module):
     def _packed_stem(self, conv: nn.Conv2d):
         """bf16 [Cout,3,3,32] pack of the stem weight (input channels zero-padded to 32), cached like _packed."""
         w = conv.weight
+        ext = self._ext(w, BF16)
+        if ext is not None and ext["key"] == "stem":
+            return ext["wf"]
         key = ("stem", id(w))
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr():
@@ -283,6 +304,9 @@ class UNet(nn.Module):
     def _packed_s2(self, conv: nn.Conv2d, wd: torch.Tensor):
         """Parity-stacked dgrad pack of a stride-2 conv with Cin in {32, 64} (ops.pack_s2_dgrad_weights), cached on the
         identity of the ordinary dgrad pack it is derived from; None when the path does not apply."""
+        ext = self._ext(conv.weight, BF16)
+        if ext is not None and ext["wd"] is wd:
+            return ext["ws"]
         key = ("s2", id(conv.weight))
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] is wd:
@@ -295,6 +319,9 @@ class UNet(nn.Module):
         """A 1x1 conv on the 3x3 conv kernels: its weight as the centre tap of a zero 3x3 kernel (the fusion layer is
         2.4 GFLOP per image this way, 0.6 % of the step), packed and cached like _packed."""
         w = conv.weight
+        ext = self._ext(w, dtype)
+        if ext is not None and ext["key"] == "k1":
+            return ext["wf"], ext["wd"]
         key = ("k1", id(w))
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr() \
@@ -310,6 +337,9 @@ class UNet(nn.Module):
         """Packs of a 3x3 head conv whose OUTPUT channels are zero-padded (32 for the bf16 tensor-core kernels, 8 for
         the fp32 direct kernels), cached like _packed."""
         w = conv.weight
+        ext = self._ext(w, dtype)
+        if ext is not None and ext["key"] == "head":
+            return ext["wf"], ext["wd"]
         key = ("head", id(w))
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr() \
@@ -322,11 +352,23 @@ class UNet(nn.Module):
         self._pack_cache[key] = (w._version, wf, wd, w.data_ptr())
         return wf, wd
 
+    # normalisation applied to uint8 HWC input batches (the dataset's, train.py:303-308)
+    input_mean = (0.485, 0.456, 0.406)
+    input_std = (0.229, 0.224, 0.225)
+
     def forward(self, x):
-        if x.dim() != 4 or x.size(1) != self.in_channels:
+        """x: fp32 NCHW [B,C,H,W] as the trainer feeds it (train.py:630), or -- SURVEY.md 8f row 2 -- the batch as the
+        dataset stores it: uint8 HWC [B,H,W,3], normalised on the device inside the stem's layout kernel."""
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or x.size(3) != self.in_channels or self.in_channels != 3:
+                raise ValueError(f"UNet.forward expects uint8 [B,H,W,3] images, got {tuple(x.shape)}")
+        elif x.dim() != 4 or x.size(1) != self.in_channels:
             raise ValueError(f"UNet.forward expects [B,{self.in_channels},H,W], got {tuple(x.shape)}")
         if not x.is_cuda:
             raise RuntimeError("b200unet: UNet.forward needs a CUDA tensor on an sm_100 device; there is no CPU path")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("b200unet: the gradient with respect to the input image is not computed by the fused "
+                                      "backward (the stem's data gradient is skipped, SURVEY.md A.1); detach the input")
         params = [p for p in self.parameters()]
         return _UNetFunction.apply(self, x, *params)
 
@@ -394,9 +436,22 @@ class _UNetFunction(torch.autograd.Function):
 
 def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     x = x.detach()
-    if x.dtype != torch.float32 or not x.is_contiguous():
-        x = x.float().contiguous()
-    B, _, H, W = x.shape
+    x_u8 = None
+    if x.dtype == torch.uint8:
+        x_u8 = x.contiguous()
+        B, H, W, _ = x_u8.shape
+        x = None  # the fp32 NCHW image is only materialised for the paths that need it (_image())
+    else:
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        B, _, H, W = x.shape
+
+    def _image():
+        nonlocal x
+        if x is None:
+            from ..data import preprocess_batch
+            x = preprocess_batch(x_u8, None, model.input_mean, model.input_std)[0]
+        return x
     n = model.n_stages
     feats = list(model.features_per_stage)
     layers = model._layers()
@@ -405,7 +460,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         raise ValueError(f"b200unet: precision must be 'bf16' or 'fp32', got {model.precision!r}")
     adt = torch.float32 if model.precision == "fp32" else BF16  # activation storage type of the arena
     need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside Function.forward; this is the autograd truth
-    dev = x.device
+    dev = x_u8.device if x_u8 is not None else x.device
 
     # spatial size per encoder level
     sizes = []
@@ -425,6 +480,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
            for d in range(n - 1)]
 
     # dropout scales, drawn in the reference's order with the reference's call
+    _f32_like = x if x is not None else torch.empty(0, dtype=torch.float32, device=dev)
     override = list(model._mask_override) if model._mask_override is not None else None
     used_masks = []
 
@@ -434,7 +490,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         if override is not None:
             m = override.pop(0).to(device=dev, dtype=torch.float32)
         else:
-            m = drop.draw(x, B, c)
+            m = drop.draw(_f32_like, B, c)
         m = m.reshape(B, c).contiguous()
         used_masks.append(m)
         return m
@@ -467,6 +523,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             d = n - 2 - L["stage"]
             c_low = feats[d + 1]
             ops.upsample2x(cur, cat[d][..., :c_low], norm=cur_norm)
+            if model._trace_fwd is not None:
+                model._trace_fwd.append(dict(kind="up", src=cur, norm=cur_norm, out=cat[d][..., :c_low]))
             rec["low"] = cur  # only its shape matters in backward
             cur = cat[d]
             cur_norm = None
@@ -474,16 +532,20 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         if first:
             if cin <= 8 and cout == 32 and stride == 1 and adt == BF16 and W >= 64:
                 # stem on the tensor-core path: image -> bf16 NHWC zero-padded to 32 channels (64 B per pixel), then
-                # the narrow-output 32 -> 32 kernels; the padded copy is also the X operand of the weight gradient
-                xin32 = ops.image_to_nhwc32(x)
+                # the narrow-output 32 -> 32 kernels; the padded copy is also the X operand of the weight gradient.
+                # A uint8 HWC batch is normalised inside that one layout kernel (no fp32 image in HBM at all).
+                if x_u8 is not None:
+                    xin32 = ops.preprocess_u8_nhwc32(x_u8, model.input_mean, model.input_std)
+                else:
+                    xin32 = ops.image_to_nhwc32(x)
                 y, stats = ops.conv_fprop(xin32, model._packed_stem(conv), 1, want_stats=True)
                 rec["stem"] = True
                 rec["xin32"] = xin32 if need_grad else None
             elif cin == 3 and cout == 32 and stride == 1 and adt == BF16:
-                y, stats = ops.stem_fprop(x, conv.weight)
+                y, stats = ops.stem_fprop(_image(), conv.weight)
                 rec["stem"] = True
             else:
-                xin = ops.nchw_to_nhwc(x, out=_padded_nhwc(B, H, W, cin, dev, adt))
+                xin = ops.nchw_to_nhwc(_image(), out=_padded_nhwc(B, H, W, cin, dev, adt))
                 wf, wd = model._packed(conv, False, adt)
                 y, stats = _conv_fwd(xin, wf, stride)
                 rec["xin"] = xin
@@ -500,7 +562,7 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
             rec["xin"] = cur
             rec["wd"] = wd
         if conv._forward_hooks:
-            _fire_forward_hooks(conv, x if first else cur, y, first)
+            _fire_forward_hooks(conv, _image() if first else cur, y, first)
         scale = draw(drop, cout)
         oh, ow = y.shape[1], y.shape[2]
         mean, rstd, a, b = ops.in_finalize(stats, norm.weight, norm.bias, scale, norm.eps, oh * ow)
@@ -519,6 +581,11 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         else:
             z, cur_norm = ops.in_apply(y, a, b, act.negative_slope, out=dst), None
         rec.update(y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale, slope=act.negative_slope, conv=conv, norm=norm)
+        if model._trace_fwd is not None:
+            model._trace_fwd.append(dict(kind="unit", li=li_f, L=L, conv=conv, norm=norm, stride=stride, slope=act.negative_slope,
+                                         xin=rec.get("xin32") if rec.get("xin32") is not None else rec.get("xin"),
+                                         y=y, mean=mean, rstd=rstd, a=a, b=b, scale=scale,
+                                         z=None if fuse_into_consumer else z))
         saved.append(rec)
         cur = z
         if model._trace is not None:
@@ -528,6 +595,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
         if head.in_channels != 32 or head.out_channels != 3 or head.bias is None:
             raise NotImplementedError("b200unet: the head kernel is built for Conv2d(32 -> 3, 1x1, bias) (unet.py:374-381)")
         logits = ops.head_forward(cur, head.weight, head.bias, norm=cur_norm)
+        if model._trace_fwd is not None:
+            model._trace_fwd.append(dict(kind="head", z=cur, norm=cur_norm, logits=logits))
         if need_grad:
             ctx.head_norm = cur_norm
     else:
@@ -545,7 +614,8 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     if need_grad:
         ctx.model = model
         ctx.saved = saved
-        ctx.image = x
+        ctx.image = x  # None for a uint8 batch on the tensor-core stem (its weight gradient reads the padded bf16 copy)
+        ctx.image_u8 = x_u8
         ctx.z_last = cur
         ctx.cat = cat
         ctx.sizes = sizes
@@ -575,17 +645,43 @@ def _backward_impl(ctx, dlogits):
     req = ctx.param_req
     sink = model._grad_sink
 
+    def wants(p: Optional[nn.Parameter]) -> bool:
+        return p is not None and req[ids[id(p)]]
+
+    def dest(p: Optional[nn.Parameter]):
+        """Slot of p's gradient in the sink's flat buffer (the producing kernel writes there), or None."""
+        if sink is None or not wants(p) or not hasattr(sink, "dest"):
+            return None
+        return sink.dest(p)
+
     def put(p: Optional[nn.Parameter], g_fn):
         """Store the gradient of parameter p (computed lazily, only if it requires grad)."""
-        if p is None:
-            return
-        i = ids[id(p)]
-        if not req[i]:
+        if not wants(p):
             return
         g = g_fn()
         if sink is not None:
             g = sink(p, g)
-        grads[i] = g
+        grads[ids[id(p)]] = g
+
+    # the 22 conv biases that feed an InstanceNorm have an exactly-zero gradient (SURVEY.md 8a).  With a flat sink their
+    # slots were zeroed at construction and are never written; otherwise ONE zero buffer per backward is sliced
+    # (each bias its own memory: autograd may adopt the slice as .grad) instead of one zeros_like launch per layer
+    dead_bias = [rec["conv"].bias for rec in saved if wants(rec["conv"].bias)]
+    zero_pool, zero_off = None, [0]
+    if dead_bias and (sink is None or not hasattr(sink, "dest")):
+        zero_pool = torch.zeros(sum((b.numel() + 3) // 4 * 4 for b in dead_bias), dtype=torch.float32, device=dlogits.device)
+
+    def zero_grad_of(b: nn.Parameter):
+        d = dest(b)
+        if d is not None:
+            return d
+        if zero_pool is None:
+            return torch.zeros_like(b)
+        v = zero_pool[zero_off[0]:zero_off[0] + b.numel()].view(b.shape)
+        zero_off[0] += (b.numel() + 3) // 4 * 4
+        return v
+
+    btrace = model._trace_bwd  # debug/test: per-layer backward tensors (tests/test_gpu_layerwise.py)
 
     # the earliest layer (forward order) that still has a trainable parameter: backward stops there
     first_needed = len(saved)
@@ -599,7 +695,8 @@ def _backward_impl(ctx, dlogits):
     if dlogits.dtype != torch.float32:
         dlogits = dlogits.float()
     if model.head_kind == "seg1x1":
-        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm)
+        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm, out_dw=dest(head.weight),
+                                         out_db=dest(head.bias))
     else:
         z_last, wdh = ctx.z_last, ctx.head_wd
         cpad = wdh.shape[3]
@@ -608,6 +705,8 @@ def _backward_impl(ctx, dlogits):
         dz = ops.conv_dgrad(dpre, wdh, (z_last.shape[1], z_last.shape[2]), 1, simt=simt_h)
         dwh = ops.conv_wgrad(z_last, dpre, 1, simt=simt_h)[:head.out_channels].contiguous()
         ctx.head_out = None
+    if btrace is not None:
+        btrace.append(dict(kind="head", dlogits=dlogits, dz=dz, dw=dwh, db=dbh))
     put(head.weight, lambda: dwh)
     put(head.bias, lambda: dbh)
 
@@ -634,19 +733,24 @@ def _backward_impl(ctx, dlogits):
             # has been ordered behind the side-stream work: no record_stream on the big activations, whose deferred
             # reuse made the caching allocator grow and stall now and then (100 ms steps in bench.py)
 
-    def wgrad_async(p: Optional[nn.Parameter], fn, inputs):
+    def wgrad_async(p: Optional[nn.Parameter], fn, inputs, trec=None):
         """Run fn() (a weight-gradient launch) for parameter p: on the side stream after everything enqueued on the
         main stream so far, or inline when overlap is off."""
-        if p is None or not req[ids[id(p)]]:
+        if not wants(p):
             return
         if not overlap:
-            put(p, fn)
+            g = fn()
+            if trec is not None:
+                trec["dw"] = g
+            put(p, lambda: g)
             return
         side.wait_stream(main)
         with torch.cuda.stream(side):
             g = fn()
             ev = torch.cuda.Event()
             ev.record(side)
+        if trec is not None:
+            trec["dw"] = g
         pending.append((p, g, ev, list(inputs)))
 
     dskip: Dict[int, torch.Tensor] = {}  # encoder level -> gradient view of the skip half of dcat
@@ -661,14 +765,22 @@ def _backward_impl(ctx, dlogits):
             dz2 = dskip.pop(L["stage"])
         else:
             dz2 = None
+        dgd, dbd = dest(norm.weight), dest(norm.bias)
+        if dgd is None or dbd is None:
+            dgd = dbd = None
         dy, dgamma, dbeta = ops.in_backward(dz, dz2, rec["y"], rec["a"], rec["b"], rec["mean"], rec["rstd"], rec["scale"],
-                                            norm.weight, rec["slope"])
+                                            norm.weight, rec["slope"], out_dgamma=dgd, out_dbeta=dbd)
+        trec = None
+        if btrace is not None:
+            trec = dict(kind="unit", li=li, dz=dz, dz2=dz2, y=rec["y"], dy=dy, dgamma=dgamma, dbeta=dbeta, xin=rec.get("xin"),
+                        xin32=rec.get("xin32"))
+            btrace.append(trec)
         rec["y"] = None
         collect()  # the previous layer's weight gradient ran beside this norm backward
         put(norm.weight, lambda: dgamma)
         put(norm.bias, lambda: dbeta)
         # the conv bias feeds an InstanceNorm: its exact gradient is zero
-        put(conv.bias, lambda: torch.zeros_like(conv.bias))
+        put(conv.bias, lambda: zero_grad_of(conv.bias))
         stride = rec["stride"]
         cin, cout = conv.in_channels, conv.out_channels
         simt = not _use_tc(cin, cout)
@@ -676,7 +788,11 @@ def _backward_impl(ctx, dlogits):
             if conv._backward_hooks:
                 _fire_backward_hooks(conv, None, dy)
             xin32 = rec.get("xin32")
-            wgrad_async(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, xin32), [ctx.image, dy, xin32])
+            if xin32 is None and ctx.image is None:  # uint8 batch on the narrow-image stem path
+                from ..data import preprocess_batch
+                ctx.image = preprocess_batch(ctx.image_u8, None, model.input_mean, model.input_std)[0]
+            wgrad_async(conv.weight, lambda: ops.stem_wgrad_tc(ctx.image, dy, xin32, out=dest(conv.weight), channels=cin),
+                        [ctx.image, dy, xin32], trec)
             break
         xin = rec["xin"]
         last = li == first_needed or rec.get("stem") is False
@@ -689,9 +805,12 @@ def _backward_impl(ctx, dlogits):
             else:
                 dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         if L["kind"] == "fusion":  # 1x1 weight = centre tap of the 3x3 gradient
-            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2].contiguous(), [xin, dy])
+            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2].contiguous(), [xin, dy],
+                        trec)
         else:
-            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt), [xin, dy])
+            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt, out=dest(conv.weight)), [xin, dy], trec)
+        if trec is not None:
+            trec["dx"] = dx
         if conv._backward_hooks:
             _fire_backward_hooks(conv, dx, dy)
         if last:
@@ -702,6 +821,8 @@ def _backward_impl(ctx, dlogits):
             c_low = feats[d + 1]
             dskip[d] = dx[..., c_low:]
             dz = ops.upsample2x_backward(dx[..., :c_low])
+            if btrace is not None:
+                btrace.append(dict(kind="up", d=d, dout=dx[..., :c_low], dx=dz))
         elif L["kind"] == "fusion":
             dz = dx[..., :feats[-1]]  # the extra features are inputs: their half of the gradient is dropped
         else:
@@ -765,6 +886,38 @@ class _BlockFunction(torch.autograd.Function):
                 dz = ops.conv_dgrad(dy, r["wd"], (xin.shape[1], xin.shape[2]), conv.stride[0], out=dxp, simt=simt)
         dx = ops.nhwc_to_nchw(dz) if ctx.x_needs else None
         return (None, dx) + tuple(pg.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+class _UpsampleCatFunction(torch.autograd.Function):
+    """cat([bilinear_2x(x), skip], 1) on NCHW fp32 tensors through the NHWC kernels (stand-alone UpBlock only)."""
+
+    @staticmethod
+    def forward(ctx, x, skip):
+        ops.require_device()
+        B, c_low, h, w = x.shape
+        c_skip = skip.shape[1]
+        if tuple(skip.shape[2:]) != (2 * h, 2 * w):
+            raise NotImplementedError("b200unet: UpBlock implements the exact 2x case of F.interpolate (unet.py:220-225); "
+                                      f"got {tuple(x.shape[2:])} -> {tuple(skip.shape[2:])}")
+        if c_low % 8 or c_skip % 8:
+            raise NotImplementedError("b200unet: UpBlock needs channel counts that are multiples of 8")
+        with torch.cuda.device(x.device):
+            cat = torch.empty((B, 2 * h, 2 * w, c_low + c_skip), dtype=BF16, device=x.device)
+            xl = ops.nchw_to_nhwc(x.detach().float().contiguous())
+            ops.upsample2x(xl, cat[..., :c_low])
+            ops.nchw_to_nhwc(skip.detach().float().contiguous(), out=cat[..., c_low:])
+            out = ops.nhwc_to_nchw(cat)
+        ctx.c_low = c_low
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c_low = ctx.c_low
+        with torch.cuda.device(dout.device):
+            d = ops.nchw_to_nhwc(dout.float().contiguous())
+            dx = ops.nhwc_to_nchw(ops.upsample2x_backward(d[..., :c_low])) if ctx.needs_input_grad[0] else None
+            dskip = dout[:, c_low:].float().contiguous() if ctx.needs_input_grad[1] else None
+        return dx, dskip
 
 
 def _run_block_standalone(block: ConvBlock, x: torch.Tensor):

@@ -138,12 +138,16 @@ def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
     return dx
 
 
-def conv_wgrad(x, dy, stride=1, simt=False):
-    """Weight gradient in the nn.Conv2d layout: fp32 [Cout,Cin,3,3]."""
+def conv_wgrad(x, dy, stride=1, simt=False, out=None):
+    """Weight gradient in the nn.Conv2d layout: fp32 [Cout,Cin,3,3] (written into `out` when given)."""
     n, h, w, cin = x.shape
     _, oh, ow, cout = dy.shape
     assert conv_out_hw(h, w, stride) == (oh, ow)
-    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    if out is not None:
+        assert tuple(out.shape) == (cout, cin, 3, 3) and out.dtype == torch.float32 and out.is_contiguous()
+        dw = out
+    else:
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
     assert x.dtype == dy.dtype
     if simt or x.dtype == F32:
         a = ConvWgradArgs(_p(x), pitch_of(x), _p(dy), pitch_of(dy), _p(dw), None, 0, n, h, w, cin, cout, stride)
@@ -184,6 +188,19 @@ def image_to_nhwc32(img_nchw):
     return xp
 
 
+def preprocess_u8_nhwc32(images_u8, mean, std):
+    """uint8 HWC batch [N,H,W,3] -> (x / 255 - mean) / std -> bf16 NHWC [N,H,W,32] (channels 3..31 zero) in one kernel:
+    the dataset's tensor conversion (train.py:303-308) and the stem's layout change fused."""
+    assert images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.size(3) == 3 and images_u8.is_cuda
+    x = images_u8.contiguous()
+    n, h, w, _ = x.shape
+    xp = torch.empty((n, h, w, 32), dtype=BF16, device=x.device)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.call("b200unet_preprocess_u8_nhwc32", _p(x), _p(xp), m3, s3, n, h * w, _stream())
+    return xp
+
+
 def pack_stem_weights(w_oihw):
     """[Cout, C<=8, 3, 3] fp32 -> bf16 [Cout,3,3,32] with the input channels zero-padded to 32."""
     cout, c = w_oihw.shape[0], w_oihw.shape[1]
@@ -192,14 +209,18 @@ def pack_stem_weights(w_oihw):
     return pack_conv_weights(w32, need_dgrad=False)[0]
 
 
-def stem_wgrad_tc(img_nchw, dy, xp=None):
+def stem_wgrad_tc(img_nchw, dy, xp=None, out=None, channels=None):
     """Stem weight gradient on the tensor-core path: the narrow-output wgrad kernel (Cin = 32 -> Cout = 32) runs on the
     zero-padded bf16 image and the 29 zero rows are dropped.  2.5x faster than the CUDA-core kernel at 512^2 x 32."""
-    c = img_nchw.shape[1]
+    c = channels if channels is not None else img_nchw.shape[1]
     assert dy.dtype == BF16
     if xp is None:
         xp = image_to_nhwc32(img_nchw)
-    return conv_wgrad(xp, dy, 1)[:, :c].contiguous()
+    full = conv_wgrad(xp, dy, 1)
+    if out is not None:
+        out.copy_(full[:, :c])
+        return out
+    return full[:, :c].contiguous()
 
 
 def stem_wgrad(img_nchw, dy):
@@ -232,14 +253,18 @@ def in_apply(y, a, b, slope, out=None):
     return z
 
 
-def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope):
+def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgamma=None, out_dbeta=None):
     """Backward of z = lrelu(IN(y))*drop.  dz2 (optional) is a second gradient contribution added to dz.
-    Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C])."""
+    Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C]); the parameter gradients go to out_dgamma / out_dbeta if given."""
     n, h, w, c = y.shape
     hw = h * w
     nbytes = _lib.call("b200unet_in_backward_workspace", n, hw, c)
     ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=y.device)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
+    if out_dgamma is not None and out_dbeta is not None:
+        assert out_dgamma.numel() == c and out_dbeta.numel() == c and out_dgamma.dtype == torch.float32
+        dgb = (out_dgamma, out_dbeta)
+    else:
+        dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
     dy = torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
     assert dz.dtype == y.dtype and (dz2 is None or dz2.dtype == y.dtype)
     args = InBwdArgs(_p(dz), pitch_of(dz), _p(dz2), pitch_of(dz2) if dz2 is not None else 0, _p(y), pitch_of(y), _p(a),
@@ -307,7 +332,7 @@ def head_forward(z, weight, bias, norm=None):
     return logits
 
 
-def head_backward(dlogits, z, weight, norm=None):
+def head_backward(dlogits, z, weight, norm=None, out_dw=None, out_db=None):
     """Returns (dz NHWC, dW [K,C,1,1], db [K]).  norm as in head_forward (z recomputed from the raw conv output)."""
     n, h, w, c = z.shape
     k = weight.shape[0]
@@ -315,8 +340,9 @@ def head_backward(dlogits, z, weight, norm=None):
     nbytes = _lib.call("b200unet_head_bwd_workspace", n, h * w, c, k)
     ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=z.device)
     dz = torch.empty((n, h, w, c), dtype=z.dtype, device=z.device)
-    dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=z.device)
-    db = torch.empty((k,), dtype=torch.float32, device=z.device)
+    dw = out_dw if out_dw is not None else torch.empty((k, c, 1, 1), dtype=torch.float32, device=z.device)
+    db = out_db if out_db is not None else torch.empty((k,), dtype=torch.float32, device=z.device)
+    assert dw.numel() == k * c and db.numel() == k and dw.is_contiguous() and db.is_contiguous()
     if norm is None:
         _lib.call("b200unet_head_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
                   pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
@@ -333,7 +359,7 @@ def loss_forward(logits, target, class_weights, dynamic, weight_ce, weight_dice,
     lg = _f32(logits)
     n, k, h, w = lg.shape
     assert k == 3, "SimpleLoss kernels are built for 3 classes (losses.py:40)"
-    assert target.dtype == torch.int64 and target.is_cuda and target.is_contiguous()
+    assert target.dtype in (torch.int64, torch.uint8) and target.is_cuda and target.is_contiguous()
     assert tuple(target.shape) == (n, h, w)
     hw = h * w
     nbytes = _lib.call("b200unet_loss_workspace", n, hw)
@@ -341,7 +367,8 @@ def loss_forward(logits, target, class_weights, dynamic, weight_ce, weight_dice,
     out = torch.empty((3,), dtype=torch.float32, device=lg.device)
     tables = torch.empty((3 + 6 * n,), dtype=torch.float32, device=lg.device)
     cw = _f32(class_weights) if class_weights is not None else None
-    _lib.call("b200unet_loss_fwd", _p(lg), _p(target), _p(cw), int(bool(dynamic)), float(weight_ce),
+    _lib.call("b200unet_loss_fwd" + ("_u8" if target.dtype == torch.uint8 else ""), _p(lg), _p(target), _p(cw),
+              int(bool(dynamic)), float(weight_ce),
               float(weight_dice), int(ignore_index), float(smooth), _p(out), _p(tables), _p(ws), nbytes, n, hw,
               _stream())
     return out, tables
@@ -352,7 +379,8 @@ def loss_backward(logits, target, tables, grad_out, weight_ce, weight_dice, igno
     n, k, h, w = lg.shape
     dl = torch.empty_like(lg)
     go = _f32(grad_out.reshape(1).contiguous()) if grad_out is not None else None
-    _lib.call("b200unet_loss_bwd", _p(lg), _p(target), _p(tables), _p(go), float(weight_ce), float(weight_dice),
+    _lib.call("b200unet_loss_bwd" + ("_u8" if target.dtype == torch.uint8 else ""), _p(lg), _p(target), _p(tables), _p(go),
+              float(weight_ce), float(weight_dice),
               int(ignore_index), _p(dl), n, h * w, _stream())
     return dl
 
