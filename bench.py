@@ -2,7 +2,7 @@
 """Headline benchmark: Our_UNet 512x512 training step (forward + Dice/weighted-CE loss + backward, gradient
 all-reduce for N > 1), images/s, on N B200s of one box (BASELINE.json: metric / configs[1], configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload unet|ae|clip] [--impl b200|reference|torch_gpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -12,7 +12,10 @@ copy of image+mask and a device->host read of the loss inside the timed region, 
 `roofline` is for the dominant kernel family (the tcgen05 implicit-GEMM convs): algorithmic conv FLOPs of the step
 divided by the CUDA-event time spent inside those entry points, measured live during the timed steps.
 `--impl reference` times the CPU port of the reference's step (oracle/unet_oracle.py: the reference is a pure-Python
-torch project whose tree is not on the GPU box) on the host cores.
+torch project whose tree is not on the GPU box) on the host cores; `--impl torch_gpu` times the same op sequence on
+stock PyTorch + cuDNN kernels ON the B200 (bf16 autocast) -- the same-box competitor of SURVEY.md 8(d).
+`--workload ae` = BASELINE.json configs[3] (autoencoder reconstruction step, batch 64), `--workload clip` = configs[4]
+(CLIP-conditioned UNet, batch 32 per GPU, random [B,512,16,16] features standing in for the frozen ViT's output).
 """
 import argparse
 import json
@@ -28,6 +31,28 @@ sys.path.insert(0, ROOT)
 METRIC = "our_unet_512_train_images_per_sec"
 UNIT = "img/s"
 FEATS = [32, 64, 128, 256, 512, 512]
+
+
+WORKLOADS = {
+    # name: (metric, default batch per GPU, description)
+    "unet": ("our_unet_512_train_images_per_sec", 32, "Our_UNet training step (fwd + SimpleLoss + bwd{ar})"),
+    "ae": ("ae_reconstruction_512_train_images_per_sec", 64,
+           "AE_pretrained reconstruction step (Autoencoder fwd + MSELoss + bwd{ar})"),
+    "clip": ("clip_unet_512_train_images_per_sec", 32,
+             "CLIP_UNet training step (fwd with [B,512,16,16] patch features + SimpleLoss + bwd{ar}; frozen ViT out of scope)"),
+}
+
+
+def extra_flops_per_image(workload, size=512):
+    """Algorithmic conv FLOPs the variants add to conv_flops_per_image: (fwd, fwd+bwd)."""
+    if workload == "ae":      # Conv2d(32 -> 3, 3x3) head instead of the 1x1 head (autoencoder.py:377-387)
+        f = 2.0 * 3 * size * size * 32 * 9 - 2.0 * 3 * size * size * 32
+        return f, 3 * f
+    if workload == "clip":    # clip_fusion_conv: Conv2d(1024 -> 512, 1x1) at the bottleneck (CLIP_UNet/models/unet.py:356-364)
+        hb = size >> 5
+        f = 2.0 * 512 * hb * hb * 1024
+        return f, 3 * f
+    return 0.0, 0.0
 
 
 def conv_flops_per_image(size=512):
@@ -129,28 +154,68 @@ class ClockSampler:
                 "source": "NVML, 10 ms period, during the timed regions", "reasons": sorted(reasons)}
 
 
-def cpu_port_step_time(batch, size, steps, warmup, threads):
-    """Time the CPU port of the reference step (oracle) -- fp32, `threads` host threads.  Returns s/step."""
+def build_model(workload):
+    """The module of the workload with the trainer's constructor arguments, seed 1234 (random init, as the trainers do)."""
+    import torch
+    torch.manual_seed(1234)
+    if workload == "ae":
+        from unet_implementations_b200.models.autoencoder import Autoencoder
+        # AE_pretrained/reconstruction/src/train.py:351-370: dropout [0,0,.05,.1,.15,.15] / [.15,.1,.1,.05,0]
+        return Autoencoder(encoder_dropout_rates=[0.0, 0.0, 0.05, 0.1, 0.15, 0.15],
+                           decoder_dropout_rates=[0.15, 0.1, 0.1, 0.05, 0.0])
+    if workload == "clip":
+        from unet_implementations_b200.models.clip_unet import UNet as ClipUNet
+        return ClipUNet()
+    from unet_implementations_b200.models.unet import UNet
+    return UNet()
+
+
+def oracle_step_fn(workload, batch, size, device="cpu", autocast=False):
+    """step() -> loss of the reference's op sequence (oracle/unet_oracle.py: plain torch functional ops) for the
+    workload, on `device`.  Used by the CPU baseline legs and by --impl torch_gpu; never by the product path."""
     import torch
 
     from oracle import unet_oracle as O
-    from unet_implementations_b200.models.unet import UNet
-    torch.set_num_threads(threads)
-    torch.manual_seed(1234)
-    model = UNet()  # construction only: weights identical to the reference's for this seed; never called on CPU
+    model = build_model(workload)  # construction only: weights identical to the reference's for this seed
     cfg = O.config_of(model)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = {k: v.detach().clone().to(device) for k, v in model.state_dict().items()}
     x, target = O.synthetic_batch(batch, size, seed=0)
+    x, target = x.to(device), target.to(device)
+    g = torch.Generator().manual_seed(5)
+    clip = torch.randn(batch, 512, size >> 5, size >> 5, generator=g).to(device) if workload == "clip" else None
+    recon_target = torch.rand(batch, 3, size, size, generator=g).to(device) if workload == "ae" else None
+
+    def step():
+        torch.manual_seed(99)
+        masks = O.draw_dropout_masks(cfg, batch, x)
+        ctx = torch.autocast(device if isinstance(device, str) else device.type, dtype=torch.bfloat16, enabled=autocast)
+        with ctx:
+            if workload == "ae":
+                return O.autoencoder_training_step(sd, x, recon_target, cfg, masks)["loss"]
+            return O.training_step(sd, x, target, cfg, masks, clip_features=clip)["loss"]
+
+    return step
+
+
+def cpu_port_step_time(batch, size, steps, warmup, threads, workload="unet"):
+    """Time the CPU port of the reference step (oracle) -- fp32, `threads` host threads.  Returns s/step."""
+    import torch
+    torch.set_num_threads(threads)
+    step = oracle_step_fn(workload, batch, size)
     times = []
     for i in range(warmup + steps):
-        torch.manual_seed(99)
         t0 = time.perf_counter()
-        masks = O.draw_dropout_masks(cfg, batch, x)
-        O.training_step(sd, x, target, cfg, masks)
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     return sum(times) / len(times)
+
+
+def workload_text(workload, world, B, S):
+    ar = " + grad all-reduce" if world > 1 else ""
+    return (WORKLOADS[workload][2].format(ar=ar) + f", batch {B}/GPU, {S}x{S} RGB, "
+            + ("3-class masks, " if workload != "ae" else "") + "random-init weights (seed 1234)")
 
 
 def run_reference(args, rank, world):
@@ -158,19 +223,17 @@ def run_reference(args, rank, world):
         return
     import torch
     cores = os.cpu_count() or 1
-    batch = 4  # BASELINE.json configs[0]: the reference's CPU-runnable case; a bounded sample of the 32-image step
+    batch = 4  # BASELINE.json configs[0]: the reference's CPU-runnable case; a bounded sample of the per-GPU step
     steps = max(1, min(args.steps, 3))
     warm = 1
-    s_per_step = cpu_port_step_time(batch, args.size, steps, warm, cores)
+    s_per_step = cpu_port_step_time(batch, args.size, steps, warm, cores, args.workload)
     v = batch / s_per_step
-    fwd, fb, _ = conv_flops_per_image(args.size)
     out = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": WORKLOADS[args.workload][0], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Our_UNet training step (fwd + SimpleLoss + bwd), batch 32/GPU, {args.size}x{args.size} RGB, "
-                               "3-class masks, random-init weights (seed 1234)",
-                   "sample": f"each step is a {batch}-image sample of the 32-image step on the host CPU (images/s is per "
+        "config": {"workload": workload_text(args.workload, 1, args.batch, args.size),
+                   "sample": f"each step is a {batch}-image sample of the {args.batch}-image step on the host CPU (images/s is per "
                              f"image), fp32, torch {torch.__version__} CPU ops, {cores} threads",
                    "batch": batch},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -181,23 +244,124 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_torch_gpu(args, rank, world):
+    """The same-box competitor: the reference's op sequence on stock
+    PyTorch + cuDNN kernels on ONE B200, torch.autocast(bf16), same batch and inputs.  None of this repo's kernels run."""
+    if rank != 0:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "torch_gpu", "unavailable": "no CUDA device"}), flush=True)
+        return
+    torch.cuda.set_device(0)
+    torch.backends.cudnn.benchmark = True
+    B, S = args.batch, args.size
+    step = oracle_step_fn(args.workload, B, S, device="cuda", autocast=True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    k = max(1, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    v = B / (ms * 1e-3)
+    out = {"impl": "torch_gpu", "metric": WORKLOADS[args.workload][0], "value": v, "unit": UNIT, "n_gpus": 1, "steps": k,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": workload_text(args.workload, 1, B, S),
+                      "how": f"oracle/unet_oracle.py functional ops (F.conv2d / F.instance_norm / F.interpolate / SimpleLoss "
+                             f"restatement) under torch.autocast(bf16), torch {torch.__version__}, cuDNN "
+                             f"{torch.backends.cudnn.version()}, cudnn.benchmark on"},
+           "loss": float(loss), "peak_memory_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+class Workload:
+    """Model + loss + synthetic batches of one BASELINE.json configuration, behind the modules' public API."""
+
+    def __init__(self, name, B, S, dev, rank):
+        import torch
+
+        from unet_implementations_b200 import data
+        from unet_implementations_b200.models.losses import MSELoss, SimpleLoss
+        self.name, self.B, self.S, self.dev = name, B, S, dev
+        self.model = build_model(name).to(dev).train()
+        self.loss_fn = MSELoss() if name == "ae" else SimpleLoss(weight_dice=1.0, weight_ce=1.0, ignore_index=255, smooth=1e-5,
+                                                                 class_weights=None, dynamic_weights=True)
+        self.data = data
+        # BASELINE.md section 3 inputs, data seed 0 + rank: what the trainer hands the model (fp32 NCHW image, int64 mask)
+        g = torch.Generator().manual_seed(rank)
+        image = torch.randn(B, 3, S, S, generator=g)
+        mask = torch.randint(0, 3, (B, S, S), generator=g)
+        mask[torch.rand(B, S, S, generator=g) < 0.1] = 255
+        self.resident = {"image": image.to(dev)}
+        if name == "ae":   # the autoencoder's target is the un-normalised [0,1] image (AE .. src/train.py:257, :262-267)
+            self.resident["target"] = torch.rand(B, 3, S, S, generator=g).to(dev)
+        else:
+            self.resident["mask"] = mask.to(dev)
+        if name == "clip":  # stands in for ClipPatchExtractor's output (CLIP_UNet/models/unet.py:581-617); no gradient
+            self.resident["clip"] = torch.randn(B, 512, S >> 5, S >> 5, generator=g).to(dev)
+        # the batch as the dataset stores it (train.py:299-311 before the float conversion): uint8 HWC image, uint8 mask
+        self.host = {"image": torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()}
+        if name != "ae":
+            m8 = mask.to(torch.uint8)
+            self.host["mask"] = m8.pin_memory()
+        if name == "clip":
+            self.host["clip"] = torch.randn(B, 512, S >> 5, S >> 5, generator=g).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
+
+    def zero_grad(self):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def step(self, batch):
+        """forward + loss + backward through the public module API; batch = dict of device tensors (either form)."""
+        self.zero_grad()
+        img = batch["image"]
+        if self.name == "clip":
+            out = self.model(img, batch["clip"])
+        else:
+            out = self.model(img)
+        if self.name == "ae":
+            tgt = batch.get("target")
+            if tgt is None:  # uint8 batch: the reconstruction target is the image / 255 (one kernel, no normalisation)
+                tgt = self.data.preprocess_batch(img, None, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0))[0]
+            loss = self.loss_fn(out, tgt)
+        else:
+            loss = self.loss_fn(out, batch["mask"])
+        loss.backward()
+        return loss
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE.json configs[1]: 32)")
+    ap.add_argument("--workload", default="unet", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the BASELINE.json configuration's)")
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-entry-point CUDA-event timing")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used for ncu captures)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer, optimizer and graph legs (ncu captures)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = WORKLOADS[args.workload][1]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "torch_gpu":
+        run_torch_gpu(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -205,50 +369,34 @@ def main():
     import torch.distributed as dist
 
     from unet_implementations_b200 import _lib, ddp
-    from unet_implementations_b200.models.losses import SimpleLoss
-    from unet_implementations_b200.models.unet import UNet
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    nccl_ctas = None
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        nccl_ctas = ddp.init_process_group(dev)  # NCCL capped to a few CTAs, as many SMs left free by the conv grids
 
     def barrier():
         if world > 1:
             dist.barrier()
 
     B, S = args.batch, args.size
-    torch.manual_seed(1234)
-    model = UNet().to(dev).train()
-    loss_fn = SimpleLoss(weight_dice=1.0, weight_ce=1.0, ignore_index=255, smooth=1e-5, class_weights=None,
-                         dynamic_weights=True)
+    wl = Workload(args.workload, B, S, dev, rank)
+    model = wl.model
     reducer = None
     if world > 1:
         ddp.broadcast_parameters(model)
         reducer = ddp.BucketedGradAllReduce(model, bucket_bytes=16 << 20)
-    # BASELINE.md section 3 inputs, data seed 0 + rank
-    g = torch.Generator().manual_seed(rank)
-    image_h = torch.randn(B, 3, S, S, generator=g).pin_memory()
-    mask_h = torch.randint(0, 3, (B, S, S), generator=g)
-    mask_h[torch.rand(B, S, S, generator=g) < 0.1] = 255
-    mask_h = mask_h.pin_memory()
-    image_d = image_h.to(dev)
-    mask_d = mask_h.to(dev)
     torch.manual_seed(99 + rank)
+    resident = wl.resident
 
-    def step(img, msk):
-        for p in model.parameters():
-            p.grad = None
-        logits = model(img)
-        loss = loss_fn(logits, msk)
-        loss.backward()
-        return loss
+    def step():
+        return wl.step(resident)
 
     for _ in range(args.warmup):
-        step(image_d, mask_d)
+        step()
     torch.cuda.synchronize()
     # clock / power sampling starts before the untimed pre-steps (NVML's first queries are slow and share driver locks
     # with kernel launches) and runs through all timed regions
@@ -256,10 +404,10 @@ def main():
     if sampler:
         sampler.start()
     # untimed pre-steps: the step runs at the 1 kW power cap and the SM clock it sustains drifts for the first second;
-    # all three timed regions below then see the same steady state (these steps are not counted in `warmup`)
+    # all timed regions below then see the same steady state (these steps are not counted in `warmup`)
     presteps = 30
     for _ in range(presteps):
-        step(image_d, mask_d)
+        step()
     torch.cuda.synchronize()
 
     def timed(fn, k):
@@ -285,7 +433,7 @@ def main():
 
     timed.per_rank_ms = None
 
-    # ---- resident-input throughput (+ live per-entry-point timing for the roofline)
+    # ---- resident-input throughput
     # per-step events inside the region expose a one-off stall (another tenant's driver call, a host hiccup): a region
     # whose slowest step is > 1.5x its median step is measured once more and the fact is recorded in the JSON line
     remeasured = None
@@ -296,7 +444,7 @@ def main():
         def marked_step():
             if counter[0] == 0:
                 marks[0].record()
-            step(image_d, mask_d)
+            step()
             counter[0] += 1
             marks[counter[0]].record()
 
@@ -326,19 +474,31 @@ def main():
         prof = _lib.EventProfiler()
         was = model.overlap_wgrad
         model.overlap_wgrad = False
-        step(image_d, mask_d)
+        step()
         torch.cuda.synchronize()
         _lib.PROFILER = prof
-        ms_serial = timed(lambda: step(image_d, mask_d), prof_steps) / prof_steps
+        ms_serial = timed(step, prof_steps) / prof_steps
         _lib.PROFILER = None
         model.overlap_wgrad = was
 
-    # ---- end to end through the public API with host buffers: every step copies ITS batch (image + int64 mask) from
-    # pinned host memory and reads its loss back to the host.  The copies run on a side stream one step ahead of the
-    # compute stream (what a pinned-memory DataLoader with non_blocking copies does), so they overlap the previous
-    # step's kernels; each of the K timed steps still issues and waits for its own H2D copy and D2H read.
+    # ---- the gradient all-reduce alone (N > 1): the same buckets, nothing else on the GPU
+    allreduce_only_ms = None
+    if reducer is not None:
+        def ar_only():
+            for b in range(len(reducer.buckets)):
+                reducer._reduce(b)
+            reducer.finish()
+        ar_only()
+        allreduce_only_ms = timed(ar_only, 10) / 10
+
+    # ---- end to end through the public API with host buffers: every step copies ITS batch from
+    # pinned host memory AS THE DATASET STORES IT -- uint8 HWC image, uint8 mask (train.py:299-311 before the float
+    # conversion) -- and reads its loss back to the host.  The model normalises the uint8 image inside the stem's layout
+    # kernel and the loss kernels read uint8 masks.  The copies run on a side stream one step ahead of the compute stream
+    # (what a pinned-memory DataLoader with non_blocking copies does); each of the K timed steps still issues and waits
+    # for its own H2D copy and D2H read.
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(image_d), torch.empty_like(mask_d)) for _ in range(2)]
+    bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in wl.host.items()} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     state = {"i": 0}
@@ -346,8 +506,8 @@ def main():
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])  # the step that last used this slot has finished with it
-            bufs[slot][0].copy_(image_h, non_blocking=True)
-            bufs[slot][1].copy_(mask_h, non_blocking=True)
+            for k, v in wl.host.items():
+                bufs[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
 
     for sl in range(2):
@@ -367,7 +527,7 @@ def main():
             prefetch(0)
         prefetch(slot ^ 1)  # next step's batch, overlapping this step's compute
         torch.cuda.current_stream().wait_event(ready[slot])
-        loss = step(bufs[slot][0], bufs[slot][1])
+        loss = wl.step(bufs[slot])
         consumed[slot].record()
         if i >= 2:
             loss_ev[slot].synchronize()
@@ -395,28 +555,55 @@ def main():
         ms_e2e = timed(e2e_region_step, args.steps)
         if not all(l == l and abs(l) < 1e6 for l in losses):
             raise SystemExit(f"bench.py: non-finite loss in the end-to-end region: {losses[-4:]}")
+
+    # ---- CUDA-graph replay of the resident step (SURVEY.md 8d timing method): forward + loss + backward captured once,
+    # replayed K times -- what the launch overhead of the eager step costs (N = 1 only: one graph per process)
+    graph_leg = None
+    if not args.no_e2e and not args.no_graph and world == 1:
+        try:
+            from unet_implementations_b200.graph import GraphedStep
+            gs = GraphedStep(step, warmup=2)
+            for _ in range(3):
+                gs.replay()
+            ms_graph = timed(gs.replay, args.steps) / args.steps
+            graph_leg = {"ms_per_step": ms_graph, "value": world * B / (ms_graph * 1e-3), "unit": UNIT,
+                         "graph_nodes": gs.num_nodes, "loss": float(gs.loss)}
+            del gs
+        except Exception as e:  # noqa: BLE001 -- the eager numbers above stand on their own
+            graph_leg = {"error": repr(e)[:300]}
+            torch.cuda.synchronize()
+
     # ---- the same resident step followed by the trainer's optimizer step ("with and without SGD step"):
-    # SGD momentum 0.99, Nesterov, weight decay 1e-4 (train.py:445-451) through the fused multi-tensor kernel.  Last,
-    # because it changes the weights.
+    # SGD momentum 0.99, Nesterov, weight decay 1e-4 (train.py:445-451) as ONE launch over the flat master / gradient /
+    # momentum buffers that also emits the bf16 conv operand packs (no repack kernels).  Last: it changes the weights.
     with_sgd = None
     if not args.no_e2e:
         from unet_implementations_b200.optim import FusedSGD
-        opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4)
+        opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4, model=model)
 
         def sgd_step():
-            step(image_d, mask_d)
+            step()
             opt.step()
 
         for _ in range(3):
             sgd_step()
+        l0 = _lib.call("b200unet_launch_count")
         ms_sgd = timed(sgd_step, args.steps) / args.steps
         with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT,
-                    "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4), one multi-tensor launch"}
+                    "gpu_launches_per_step": (_lib.call("b200unet_launch_count") - l0) / args.steps,
+                    "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4, model=model): one launch over the "
+                                 "flat master/grad/momentum buffers, emits the bf16 weight packs (weights change every step; "
+                                 "no pack kernel runs)"}
     clocks = sampler.stop() if sampler else None
     e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
-    h2d = image_h.numel() * 4 + mask_h.numel() * 8
 
     fwd, fb, tc = conv_flops_per_image(S)
+    xf, xfb = extra_flops_per_image(args.workload, S)
+    if args.workload == "ae":  # the 3x3 reconstruction head runs on the tensor-core conv kernels; there is no 1x1 head
+        tc += xfb + 3 * 2.0 * 3 * S * S * 32
+    elif args.workload == "clip":
+        tc += xfb
+    fb += xfb
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -428,10 +615,15 @@ def main():
     roofline_hbm = None
     breakdown = None
     traffic = {}
-    try:  # DRAM bytes per step and kernel family from the committed ncu launch list (tools/traffic_json.py)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-    except Exception:
-        pass
+    traffic_file = None
+    for cand in ("r2_traffic.json", "r1_traffic.json"):  # DRAM bytes per step and kernel family from the committed ncu
+        try:                                             # launch list (tools/traffic_json.py)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            traffic_file = cand
+            break
+        except Exception:
+            continue
+    std_cfg = args.workload == "unet" and B == 32 and S == 512
     if prof is not None:
         tot = prof.totals_ms()
         conv_names = ("b200unet_conv_fprop", "b200unet_conv_dgrad", "b200unet_conv_dgrad_s2", "b200unet_conv_wgrad",
@@ -440,11 +632,11 @@ def main():
         conv_ms_step = conv_ms / prof_steps
         achieved = tc * B / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
         tconv = traffic.get("conv")
-        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (gconv/nconv/pconv fprop+dgrad, wgrad/wgradn + finalize), all 22 3x3 convs",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (gconv/nconv/pconv fprop+dgrad, wgrad/wgradn + finalize), every 3x3 conv of the step",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": (tconv["dram_read_bytes"] + tconv["dram_write_bytes"]) if tconv and B == 32 and S == 512 else None,
+                    "traffic": (tconv["dram_read_bytes"] + tconv["dram_write_bytes"]) if tconv and std_cfg else None,
                     "traffic_note": "DRAM bytes of the family per step (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                    "profiles/r1_step_launches.md); algorithmic conv FLOPs per step = %.3e" % (tc * B),
+                                    "profiles/%s); algorithmic conv FLOPs per step = %.3e" % (traffic_file, tc * B),
                     "peak_source": peak_src, "conv_ms_per_step": conv_ms_step,
                     "conv_share_of_step": conv_ms_step / ms_serial, "serial_ms_per_step": ms_serial,
                     "whole_step_tflops": fb * B / (ms_per_step * 1e-3) / 1e12}
@@ -459,7 +651,7 @@ def main():
             tn = traffic.get("norm")
             roofline_hbm = {"bound": "hbm", "kernel": "in_apply + in_backward (InstanceNorm/LeakyReLU/dropout fwd + bwd)",
                             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                            "traffic": (tn["dram_read_bytes"] + tn["dram_write_bytes"]) if tn and B == 32 and S == 512 else None,
+                            "traffic": (tn["dram_read_bytes"] + tn["dram_write_bytes"]) if tn and std_cfg else None,
                             "algorithmic_bytes_per_step": elems * 10.0, "ms_per_step": norm_ms,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"}
         breakdown = {k.replace("b200unet_", ""): {"ms_per_step": v[0] / prof_steps, "calls_per_step": v[1] / prof_steps}
@@ -470,30 +662,38 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        s_per = cpu_port_step_time(4, S, 2, 1, cores)
+        s_per = cpu_port_step_time(4, S, 2, 1, cores, args.workload)
         cpu = {"value": 4 / s_per, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "2 steps of batch 4 after 1 warm-up (oracle/unet_oracle.py, fp32 torch CPU ops)"}
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": WORKLOADS[args.workload][0], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"Our_UNet training step (fwd + SimpleLoss + bwd{' + grad all-reduce' if world > 1 else ''}), "
-                                   f"batch {B}/GPU, {S}x{S} RGB, 3-class masks, random-init weights (seed 1234)",
+            "config": {"workload": workload_text(args.workload, world, B, S),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "working set (>10 GB of activations per step) far exceeds the 126 MB L2; no flush needed",
-                       "optimizer_step": "not included in value / e2e (BASELINE.md: step = forward + loss + backward); measured beside them in with_optimizer_step",
+                       "inputs": "value: fp32 NCHW image + int64 mask resident in HBM (the trainer's types, train.py:630-631); "
+                                 "e2e: uint8 HWC image + uint8 mask copied from pinned host memory every step "
+                                 "(the dataset's storage types, train.py:299-311), normalised on the device",
+                       "optimizer_step": "not included in value / e2e (BASELINE.md: step = forward + loss + backward); measured "
+                                         "beside them in with_optimizer_step; weights are constant in the value / e2e regions, so "
+                                         "their cached bf16 packs are reused (no per-step repack there)",
                        "presteps": "30 untimed steps after the warm-up (power-cap steady state)",
                        "overlap": "weight-gradient kernels on a side stream beside the next layer's norm backward"
-                                  if model.overlap_wgrad else "none (single stream)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                                  if model.overlap_wgrad else "none (single stream)",
+                       "nccl": (f"communicator capped to {nccl_ctas} CTAs; conv grids sized for "
+                                f"{os.environ.get('B200UNET_RESERVED_SMS', '0')} fewer SMs") if world > 1 else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "with_optimizer_step": with_sgd,
+            "graph_replay": graph_leg,
             "gpu_launches": int(launches),
             "remeasured": remeasured,
             "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "per_rank_ms_per_step": per_rank_resident,
+            "allreduce_only_ms": allreduce_only_ms,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
