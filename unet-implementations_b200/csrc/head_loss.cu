@@ -467,7 +467,9 @@ __global__ void __launch_bounds__(256) recon_head_fwd_kernel(const T* __restrict
   }
 }
 
-// grid (blocks, N); every block writes one partial row [K] of db
+// grid (blocks, N); every block writes one partial row [K] of db.  One thread per pixel: K coalesced 4-byte reads per
+// operand, and the Cpad-channel NHWC row (K real values, then zeros) written as 16-byte stores (the first version stored
+// the row one element at a time: 32 two-byte stores per pixel, 4.4 ms at batch 64 against 0.3 ms of traffic).
 template <typename T>
 __global__ void __launch_bounds__(256) recon_head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                               T* __restrict__ dpre, int64_t dp, int Cpad,
@@ -475,18 +477,25 @@ __global__ void __launch_bounds__(256) recon_head_bwd_kernel(const float* __rest
   __shared__ float scratch[8];
   const int n = blockIdx.y;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int vecs = Cpad * static_cast<int>(sizeof(T)) / 16;  // 16-byte stores per row (Cpad % 8 == 0)
   for (int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; px < HW; px += static_cast<int64_t>(gridDim.x) * 256) {
-    T* dst = dpre + (static_cast<int64_t>(n) * HW + px) * dp;
-    for (int k = 0; k < Cpad; ++k) {
-      float g = 0.f;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
       if (k < K) {
         const int64_t i = (static_cast<int64_t>(n) * K + k) * HW + px;
-        const float o = out[i];
-        g = dout[i] * o * (1.f - o);
-        if (k < 4) acc[k] += g;
+        const float o = __ldg(out + i);
+        g[k] = __ldg(dout + i) * o * (1.f - o);
+        acc[k] += g[k];
       }
-      dst[k] = from_f32<T>(g);
+    uint4* dst = reinterpret_cast<uint4*>(dpre + (static_cast<int64_t>(n) * HW + px) * dp);
+    if (sizeof(T) == 2) {
+      dst[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), 0u, 0u);
+    } else {
+      dst[0] = make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]), __float_as_uint(g[3]));
     }
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int v = 1; v < vecs; ++v) dst[v] = z;
   }
   for (int k = 0; k < K && k < 4; ++k) {
     const float v = block_sum(acc[k], scratch);
@@ -693,6 +702,8 @@ static int recon_head_bwd_impl(const float* dout_nchw, const float* out_nchw, vo
                                void* stream) {
   B200_CHECK_ARG(dout_nchw && out_nchw && dpre && db && workspace, "recon_head_bwd: null pointer");
   B200_CHECK_ARG(K >= 1 && K <= 4 && Cpad >= K && dpre_pitch >= Cpad && N <= 65535, "recon_head_bwd: bad channel counts");
+  B200_CHECK_ARG(Cpad % 8 == 0 && dpre_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(dpre) & 15) == 0,
+                 "recon_head_bwd: Cpad and the pitch must be multiples of 8, dpre 16-byte aligned");
   B200_CHECK_ARG(workspace_bytes >= b200unet_recon_head_bwd_workspace(N, HW), "recon_head_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = recon_blocks(HW, N);
