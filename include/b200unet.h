@@ -35,6 +35,11 @@ const char* b200unet_last_error(void);
 long long b200unet_launch_count(void);
 /* 1 if the current device is compute capability 10.x, else 0 (negative on error). */
 int b200unet_device_ok(void);
+/* Size every grid launched from now on for (device SMs - n) SMs; returns the previous value.  The data-parallel
+ * reducer (ddp.py) brackets backward with it so that the NCCL all-reduce kernels overlapping backward always find a
+ * free SM instead of delaying one CTA of a persistent one-CTA-per-SM conv kernel.  No reference counterpart (the
+ * reference has no distributed code). */
+int b200unet_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolution, pad 1, stride 1 or 2 -- replaces nn.Conv2d in ConvBlock (Our_UNet/models/unet.py:106-115)

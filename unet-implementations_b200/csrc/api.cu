@@ -68,21 +68,34 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return 0;
 }
 
-// SMs the grids of this library are sized for: the device's count minus B200UNET_RESERVED_SMS (data-parallel runs
-// keep a few SMs free for the NCCL kernels of the gradient all-reduce, so that a persistent one-CTA-per-SM conv kernel
-// never has a CTA waiting behind a communication kernel; ddp.init_process_group sets it).  Read once per process.
-int num_sms() {
+// SMs the grids of this library are sized for: the device's count minus the reserved ones.  Data-parallel runs keep
+// a few SMs free for the NCCL kernels of the gradient all-reduce WHILE BACKWARD RUNS (b200unet_set_reserved_sms, called
+// by the fused backward when a reducer is attached), so that a persistent one-CTA-per-SM conv kernel never has a CTA
+// waiting behind a communication kernel; forward kernels keep the whole device.  B200UNET_RESERVED_SMS_DEFAULT sets a
+// process-wide default (developer knob).
+static int g_reserved_sms = -1;  // -1: not initialised
+
+static int device_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    const char* e = getenv("B200UNET_RESERVED_SMS");
-    const int r = e ? atoi(e) : 0;
-    if (r > 0 && r < v / 2) v -= r;
     n = v;
   }
   return n;
+}
+
+int num_sms() {
+  int r = __atomic_load_n(&g_reserved_sms, __ATOMIC_RELAXED);
+  if (r < 0) {
+    const char* e = getenv("B200UNET_RESERVED_SMS_DEFAULT");
+    r = e ? atoi(e) : 0;
+    if (r < 0) r = 0;
+    __atomic_store_n(&g_reserved_sms, r, __ATOMIC_RELAXED);
+  }
+  const int v = device_sms();
+  return (r > 0 && r < v / 2) ? v - r : v;
 }
 
 }  // namespace b200
@@ -96,6 +109,12 @@ long long b200unet_launch_count(void) {
 }
 
 const char* b200unet_last_error(void) { return b200::g_err; }
+
+int b200unet_set_reserved_sms(int n) {
+  const int v = b200::num_sms();  // forces initialisation
+  (void)v;
+  return __atomic_exchange_n(&b200::g_reserved_sms, n < 0 ? 0 : n, __ATOMIC_RELAXED);
+}
 
 int b200unet_device_ok(void) {
   int dev = 0;

@@ -16,8 +16,10 @@ buckets.  The gradients autograd returns are views of the flat buffer.
 NCCL and the persistent conv kernels.  The tensor-core conv kernels run one CTA per SM with ~226 KB of shared memory;
 an NCCL kernel that lands on an SM delays that SM's CTA, and a persistent kernel is as slow as its slowest CTA
 (round 1: dgrad +11 %, wgrad +4 % at 8 GPUs).  The payload is tiny against NVLink (78.6 MB per 22 ms step), so the
-communicator is capped to a few CTAs (`nccl_options`, NCCL_MAX_CTAS) and the conv kernels leave that many SMs free
-while a reducer is attached (`B200UNET_RESERVED_SMS`, read by the library's grid sizing).
+communicator is capped to a few CTAs (`nccl_options`, NCCL_MAX_CTAS) and the conv grids of BACKWARD -- the only phase
+in which an all-reduce is in flight -- are sized for that many fewer SMs (`reserve_sms`, b200unet_set_reserved_sms;
+forward keeps the whole device).  The last bucket, whose all-reduce cannot overlap anything, holds only the small
+gradients produced last (`tail_bytes`).
 """
 from __future__ import annotations
 
@@ -61,18 +63,28 @@ def init_process_group(device: torch.device, max_ctas: Optional[int] = None, res
 class BucketedGradAllReduce(FlatGradSink):
     """Gradient sink: flat fp32 buffer + bucketed asynchronous all-reduce (mean) over `group`."""
 
-    def __init__(self, model, group=None, bucket_bytes: int = 16 << 20, device: Optional[torch.device] = None):
+    def __init__(self, model, group=None, bucket_bytes: int = 16 << 20, device: Optional[torch.device] = None,
+                 tail_bytes: int = 2 << 20):
         super().__init__(model, device=device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        # SMs the backward's conv grids leave free for the NCCL kernels (read by models/unet.py:_UNetFunction.backward)
+        self.reserve_sms = int(os.environ.get("B200UNET_RESERVED_SMS", "0")) if (self.world > 1 and self.backend == "nccl") else 0
+        # The LAST bucket cannot start before backward ends, so its all-reduce is exposed: it is kept small (the
+        # gradients produced last are the small ones -- encoder stages 2..0, 0.3 M of the 19.7 M elements), everything
+        # before it goes in buckets of `bucket_bytes`.
+        ends = [self.offsets[id(p)] + (p.numel() + 3) // 4 * 4 for p in self.params]
+        tail_start_idx = len(self.params)
+        while tail_start_idx > 1 and (self.numel - ends[tail_start_idx - 2]) * 4 <= tail_bytes:
+            tail_start_idx -= 1
         self.buckets: List[List[int]] = []  # [start, end) element ranges
         self.bucket_of: Dict[int, int] = {}
         start = 0
-        for p in self.params:
-            end = self.offsets[id(p)] + (p.numel() + 3) // 4 * 4
+        for i, p in enumerate(self.params):
+            end = ends[i]
             self.bucket_of[id(p)] = len(self.buckets)
-            if (end - start) * 4 >= bucket_bytes:
+            if (end - start) * 4 >= bucket_bytes or i == tail_start_idx - 1:
                 self.buckets.append([start, end])
                 start = end
         if self.numel > start:

@@ -33,6 +33,10 @@ except ImportError:  # imported as top-level `models.unet` through the drop-in s
 BF16 = torch.bfloat16
 
 
+def _lib_call(name, *args):
+    return ops._lib.call(name, *args)
+
+
 class SpatialDropout2d(nn.Module):
     """Channel dropout of the reference (unet.py:13-35): one Bernoulli(1-p) draw per (sample, channel), kept
     channels scaled by 1/(1-p).  Inside `UNet.forward` the draw below is made with the reference's exact call
@@ -429,8 +433,16 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        with torch.cuda.device(dlogits.device):
-            grads = _backward_impl(ctx, dlogits)
+        # a data-parallel reducer asks the conv grids of backward to leave a few SMs to its NCCL kernels (ddp.py)
+        sink = getattr(getattr(ctx, "model", None), "_grad_sink", None)
+        reserve = int(getattr(sink, "reserve_sms", 0) or 0)
+        prev = _lib_call("b200unet_set_reserved_sms", reserve) if reserve else 0
+        try:
+            with torch.cuda.device(dlogits.device):
+                grads = _backward_impl(ctx, dlogits)
+        finally:
+            if reserve:
+                _lib_call("b200unet_set_reserved_sms", prev)
         return (None, None) + tuple(grads)
 
 
