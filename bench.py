@@ -410,6 +410,24 @@ def main():
         step()
     torch.cuda.synchronize()
 
+    # ---- the production form of the step: forward + loss + backward captured ONCE into a CUDA graph and replayed
+    # (unet_implementations_b200.graph.GraphedStep; SURVEY.md 8d "CUDA events around a CUDA-graph-replayed step").  The
+    # eager form (one Python-enqueued launch per kernel) is timed beside it.  N > 1 replays the graph too when
+    # B200UNET_GRAPH_DDP=1 (NCCL all-reduces inside the capture); otherwise data-parallel runs stay eager.
+    gs = None
+    graph_err = None
+    if not args.no_graph and (world == 1 or os.environ.get("B200UNET_GRAPH_DDP", "0") == "1"):
+        try:
+            from unet_implementations_b200.graph import GraphedStep
+            gs = GraphedStep(step, warmup=2)
+            for _ in range(3):
+                gs.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001 -- the eager path stands on its own
+            gs, graph_err = None, repr(e)[:300]
+            torch.cuda.synchronize()
+    run_step = gs.replay if gs is not None else step
+
     def timed(fn, k):
         barrier()
         torch.cuda.synchronize()
@@ -444,16 +462,14 @@ def main():
         def marked_step():
             if counter[0] == 0:
                 marks[0].record()
-            step()
+            run_step()
             counter[0] += 1
             marks[counter[0]].record()
 
         if sampler and attempt == 0:
             sampler.samples.clear()  # keep only what was sampled during the timed regions
-        l0 = _lib.call("b200unet_launch_count")
         ms = timed(marked_step, args.steps)
         per_rank_resident = timed.per_rank_ms
-        launches = _lib.call("b200unet_launch_count") - l0
         per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
         worst, med = per[-1], per[len(per) // 2]
         flag = torch.tensor([1.0 if worst > 1.5 * med else 0.0], device=dev)
@@ -464,6 +480,15 @@ def main():
         remeasured = f"first attempt had a {worst:.1f} ms step against a median of {med:.1f} ms ({ms / args.steps:.2f} ms/step); measured again"
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    # the eager form of the same step (also the launch count: a graph replay launches the same kernels as graph nodes)
+    l0 = _lib.call("b200unet_launch_count")
+    step()
+    launches_per_step = _lib.call("b200unet_launch_count") - l0
+    launches = launches_per_step * args.steps
+    eager_leg = None
+    if gs is not None:
+        ms_eager = timed(step, args.steps) / args.steps
+        eager_leg = {"ms_per_step": ms_eager, "value": world * B / (ms_eager * 1e-3), "unit": UNIT}
 
     # ---- per-kernel-family timing for the roofline: a second timed region of the SAME step with the weight-gradient
     # kernels serialised on the main stream (in the headline region above they run on a side stream beside the next
@@ -520,6 +545,19 @@ def main():
     loss_ev = [torch.cuda.Event() for _ in range(2)]
     losses = []
 
+    # one captured step per input slot (a graph is bound to the addresses of its inputs)
+    slot_graphs = None
+    if gs is not None and not args.no_e2e and world == 1:
+        try:
+            for sl in range(2):
+                for k, v in wl.host.items():
+                    bufs[sl][k].copy_(v)
+            from unet_implementations_b200.graph import GraphedStep
+            slot_graphs = [GraphedStep(lambda sl=sl: wl.step(bufs[sl]), warmup=1) for sl in range(2)]
+        except Exception as e:  # noqa: BLE001
+            slot_graphs, graph_err = None, repr(e)[:300]
+            torch.cuda.synchronize()
+
     def e2e_step():
         i = state["i"]
         slot = i & 1
@@ -527,7 +565,7 @@ def main():
             prefetch(0)
         prefetch(slot ^ 1)  # next step's batch, overlapping this step's compute
         torch.cuda.current_stream().wait_event(ready[slot])
-        loss = wl.step(bufs[slot])
+        loss = slot_graphs[slot].replay() if slot_graphs is not None else wl.step(bufs[slot])
         consumed[slot].record()
         if i >= 2:
             loss_ev[slot].synchronize()
@@ -541,6 +579,7 @@ def main():
             loss_ev[sl].synchronize()
             losses.append(float(loss_h[sl]))
 
+    e2e_graphed = slot_graphs is not None
     if args.no_e2e:
         ms_e2e = float("nan")
     else:
@@ -556,27 +595,13 @@ def main():
         if not all(l == l and abs(l) < 1e6 for l in losses):
             raise SystemExit(f"bench.py: non-finite loss in the end-to-end region: {losses[-4:]}")
 
-    # ---- CUDA-graph replay of the resident step (SURVEY.md 8d timing method): forward + loss + backward captured once,
-    # replayed K times -- what the launch overhead of the eager step costs (N = 1 only: one graph per process)
-    graph_leg = None
-    if not args.no_e2e and not args.no_graph and world == 1:
-        try:
-            from unet_implementations_b200.graph import GraphedStep
-            gs = GraphedStep(step, warmup=2)
-            for _ in range(3):
-                gs.replay()
-            ms_graph = timed(gs.replay, args.steps) / args.steps
-            graph_leg = {"ms_per_step": ms_graph, "value": world * B / (ms_graph * 1e-3), "unit": UNIT,
-                         "graph_nodes": gs.num_nodes, "loss": float(gs.loss)}
-            del gs
-        except Exception as e:  # noqa: BLE001 -- the eager numbers above stand on their own
-            graph_leg = {"error": repr(e)[:300]}
-            torch.cuda.synchronize()
-
     # ---- the same resident step followed by the trainer's optimizer step ("with and without SGD step"):
     # SGD momentum 0.99, Nesterov, weight decay 1e-4 (train.py:445-451) as ONE launch over the flat master / gradient /
     # momentum buffers that also emits the bf16 conv operand packs (no repack kernels).  Last: it changes the weights.
     with_sgd = None
+    gs = None
+    slot_graphs = None
+    run_step = step
     if not args.no_e2e:
         from unet_implementations_b200.optim import FusedSGD
         opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4, model=model)
@@ -589,7 +614,7 @@ def main():
             sgd_step()
         l0 = _lib.call("b200unet_launch_count")
         ms_sgd = timed(sgd_step, args.steps) / args.steps
-        with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT,
+        with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT, "step_form": "eager",
                     "gpu_launches_per_step": (_lib.call("b200unet_launch_count") - l0) / args.steps,
                     "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4, model=model): one launch over the "
                                  "flat master/grad/momentum buffers, emits the bf16 weight packs (weights change every step; "
@@ -680,6 +705,8 @@ def main():
                        "optimizer_step": "not included in value / e2e (BASELINE.md: step = forward + loss + backward); measured "
                                          "beside them in with_optimizer_step; weights are constant in the value / e2e regions, so "
                                          "their cached bf16 packs are reused (no per-step repack there)",
+                       "step_form": ("value: CUDA-graph replay of forward + loss + backward (graph.GraphedStep), eager form in "
+                                     "`eager`" if eager_leg is not None else "eager (one host-enqueued launch per kernel)"),
                        "presteps": "30 untimed steps after the warm-up (power-cap steady state)",
                        "overlap": "weight-gradient kernels on a side stream beside the next layer's norm backward"
                                   if model.overlap_wgrad else "none (single stream)",
@@ -688,7 +715,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "with_optimizer_step": with_sgd,
-            "graph_replay": graph_leg,
+            "eager": eager_leg,
+            "graph": {"value_is_graph_replay": eager_leg is not None, "e2e_is_graph_replay": e2e_graphed,
+                      "error": graph_err},
             "gpu_launches": int(launches),
             "remeasured": remeasured,
             "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),

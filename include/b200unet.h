@@ -144,6 +144,14 @@ typedef struct {
   int N;
   int64_t HW;
   int C;
+  /* Producer-side sums (optional): the kernel that WROTE dz -- a data-gradient epilogue, the head backward -- may already
+   * have reduced, per image over its own P blocks, T1 = sum gm and T2raw = sum gm * y with
+   * gm = dz_stored * (a*y+b > 0 ? 1 : slope): fp32 [N][ext_P][C][2].  With ext_part (and ext_part2 for dz2 when dz2 is
+   * given) the reduction pass over (dz, y) is skipped: 3 tensor passes instead of 5.  NULL = reduce here. */
+  const float* ext_part;
+  int ext_P;
+  const float* ext_part2;
+  int ext_P2;
 } b200unet_in_bwd_args;
 int64_t b200unet_in_backward_workspace(int N, int64_t HW, int C);
 int b200unet_in_backward(const b200unet_in_bwd_args* a, void* stream);
@@ -219,6 +227,17 @@ int b200unet_head_norm_fwd(const void* y, int64_t y_pitch, const float* a, const
 int b200unet_head_norm_bwd(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a, const float* b,
                            float slope, const float* w, void* dz, int64_t dz_pitch, float* dw, float* db,
                            float* workspace, int64_t workspace_bytes, int N, int64_t HW, int C, int K, void* stream);
+/* head_norm_bwd that also emits the norm-backward partial sums of the unit whose raw output y it reads (see
+ * b200unet_in_bwd_args.ext_part): bwd_part = fp32 [N][P][C][2], P = b200unet_head_bwd_stat_slots(N, HW). */
+int b200unet_head_bwd_stat_slots(int N, int64_t HW);
+int b200unet_head_norm_bwd_stats(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a, const float* b,
+                                 float slope, const float* w, void* dz, int64_t dz_pitch, float* dw, float* db,
+                                 float* workspace, int64_t workspace_bytes, float* bwd_part, int N, int64_t HW, int C, int K,
+                                 void* stream);
+int b200unet_head_norm_bwd_stats_f32(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
+                                     const float* b, float slope, const float* w, void* dz, int64_t dz_pitch, float* dw,
+                                     float* db, float* workspace, int64_t workspace_bytes, float* bwd_part, int N,
+                                     int64_t HW, int C, int K, void* stream);
 int b200unet_upsample2x_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,
                                      void* out, int64_t out_pitch, int N, int H, int W, int C, void* stream);
 int b200unet_head_norm_fwd_f32(const void* y, int64_t y_pitch, const float* a, const float* b, float slope,

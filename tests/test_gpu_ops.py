@@ -270,6 +270,39 @@ def test_consumers_with_the_apply_pass_fused_in():
     assert O.rel_l2(dw, wt.grad) <= F32_TOL and O.rel_l2(db, bias.grad) <= F32_TOL
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 12, 20), (3, 64, 96), (1, 7, 5)])
+def test_head_backward_reduces_the_producing_units_norm_backward_sums(n, h, w):
+    """Producer-side sums (b200unet_in_bwd_args.ext_part): the head backward, which reads the last unit's raw output
+    anyway, also emits sum gm and sum gm * y per image; the norm backward fed with them (no reduction pass) must give
+    what the self-reducing norm backward gives (unet.py:118-127 backward)."""
+    from unet_implementations_b200 import ops
+    c = 32
+    y, y_ref = rand_act(n, h, w, c, seed=31, scale=1.5)
+    g = torch.Generator().manual_seed(32)
+    gamma = (torch.rand(c, generator=g) + 0.5).cuda()
+    beta = (torch.randn(c, generator=g) * 0.3).cuda()
+    drop = torch.where(torch.rand(n, c, generator=g) < 0.25, 0.0, 1.25).cuda()
+    stats = torch.stack([y.float().sum((1, 2)), (y.float() ** 2).sum((1, 2))], -1).reshape(n, 1, c, 2).contiguous()
+    mean, rstd, a, b = ops.in_finalize(stats, gamma, beta, drop, 1e-5, h * w)
+    wt = torch.randn(3, c, 1, 1, generator=g).cuda()
+    dl = torch.randn(n, 3, h, w, generator=g).cuda()
+    dz0, dw0, db0 = ops.head_backward(dl, y, wt, norm=(a, b, 0.01))
+    dz, dw, db, part = ops.head_backward(dl, y, wt, norm=(a, b, 0.01), want_bwd_part=True)
+    assert torch.equal(dz, dz0) and O.rel_l2(dw, dw0) <= 1e-6 and O.rel_l2(db, db0) <= 1e-6
+    # the sums themselves, against fp64 torch math on the stored dz
+    pre = y.double() * a[:, None, None, :].double() + b[:, None, None, :].double()
+    gm = dz.double() * torch.where(pre > 0, 1.0, 0.01)
+    t1, t2 = gm.sum((1, 2)), (gm * y.double()).sum((1, 2))
+    got = part.double().sum(1)
+    scale = gm.abs().sum((1, 2)).clamp_min(1e-30)
+    assert float(((got[..., 0] - t1).abs() / scale).max()) <= 1e-5
+    assert float(((got[..., 1] - t2).abs() / (gm * y.double()).abs().sum((1, 2)).clamp_min(1e-30)).max()) <= 1e-5
+    dy0, dg0, dbt0 = ops.in_backward(dz, None, y, a, b, mean, rstd, drop, gamma, 0.01)
+    dy1, dg1, dbt1 = ops.in_backward(dz, None, y, a, b, mean, rstd, drop, gamma, 0.01, ext_part=part)
+    assert O.rel_l2(dy1.float(), dy0.float()) <= 2e-3   # bf16 outputs of the same value up to fp32 summation order
+    assert O.rel_l2(dg1, dg0) <= 1e-4 and O.rel_l2(dbt1, dbt0) <= 1e-4
+
+
 def _guarded(shape, dtype=torch.bfloat16, guard=4096, fill=3.0):
     """A tensor of `shape` carved out of the middle of a larger allocation whose margins hold a sentinel value."""
     n = 1

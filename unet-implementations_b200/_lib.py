@@ -44,6 +44,7 @@ class InBwdArgs(Structure):
         ("drop_scale", c_void_p), ("gamma", c_void_p), ("slope", c_float), ("dy", c_void_p), ("dy_pitch", c_int64),
         ("dgamma", c_void_p), ("dbeta", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("N", c_int), ("HW", c_int64), ("C", c_int),
+        ("ext_part", c_void_p), ("ext_P", c_int), ("ext_part2", c_void_p), ("ext_P2", c_int),
     ]
 
 
@@ -116,6 +117,9 @@ SIGNATURES = {
     "b200unet_head_norm_fwd_f32": (c_int, [_P, _L, _P, _P, _F, _P, _P, _P, _I, _L, _I, _I, _P]),
     "b200unet_head_norm_bwd": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
     "b200unet_head_norm_bwd_f32": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _I, _L, _I, _I, _P]),
+    "b200unet_head_bwd_stat_slots": (c_int, [_I, _L]),
+    "b200unet_head_norm_bwd_stats": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _P, _I, _L, _I, _I, _P]),
+    "b200unet_head_norm_bwd_stats_f32": (c_int, [_P, _P, _L, _P, _P, _F, _P, _P, _L, _P, _P, _P, _L, _P, _I, _L, _I, _I, _P]),
     "b200unet_preprocess_u8": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _P]),
     "b200unet_preprocess_u8_nhwc32": (c_int, [_P, _P, _P, _P, _I, _L, _P]),
     "b200unet_sgd_flat_block_elems": (c_int, []),
@@ -136,7 +140,7 @@ SIGNATURES = {
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_set_reserved_sms", "b200unet_launch_count", "b200unet_conv_fprop_partials",
-    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_recon_head_bwd_workspace",
+    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_head_bwd_stat_slots", "b200unet_recon_head_bwd_workspace",
     "b200unet_conv_dgrad_s2_supported",
     "b200unet_mse_workspace",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",

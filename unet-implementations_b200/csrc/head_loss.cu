@@ -326,81 +326,95 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, 
   for (int k = 0; k < K; ++k) logits[(static_cast<int64_t>(n) * K + k) * HW + px] = acc[k];
 }
 
-// grid-stride over (pixel, channel octet): thread (px, c8) computes dz for 8 channels and accumulates its 8 columns
-// of dW[K][C] (+ db on the c8 == 0 thread) -- 27 accumulators instead of K*C = 96 per thread (the one-thread-per-pixel
-// version needed 254 registers: 12 % occupancy, 2.4 TB/s).  Block reduction: butterfly over the pixel lanes of a
-// warp, then the 8 warps in fixed order; one partial row per block (deterministic).
-template <typename T, int C, int K>
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ z,
+// grid (blocks per image, N): thread (px, c8) computes dz for 8 channels of its pixels of image n and accumulates its 8
+// columns of dW[K][C] (+ db on the c8 == 0 thread) -- 27 accumulators instead of K*C = 96 per thread (the
+// one-thread-per-pixel version needed 254 registers: 12 % occupancy, 2.4 TB/s).  Block reduction: butterfly over the
+// pixel lanes of a warp, then the 8 warps in fixed order; one partial row per block (deterministic).
+// STATS (only with the fused producer na/nb): the block also emits the InstanceNorm-backward partial sums of the unit
+// whose raw output y it is reading -- T1 = sum gm, T2raw = sum gm * y with gm = dz_stored * lrelu'(na*y+nb) -- so that
+// that unit's norm backward needs no reduction pass over (dz, y) (b200unet_in_bwd_args.ext_part).
+template <typename T, int C, int K, bool STATS>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ z,
                                                         int64_t zp, const float* __restrict__ w,
                                                         T* __restrict__ dz, int64_t dzp,
-                                                        float* __restrict__ partial, int N, int64_t HW,
+                                                        float* __restrict__ partial, int64_t HW,
                                                         const float* __restrict__ na, const float* __restrict__ nb,
-                                                        float slope) {
+                                                        float slope, float* __restrict__ tpart) {
   constexpr int C8N = C / 8;
+  constexpr int L = 256 / C8N;  // pixel lanes of a block
   static_assert(C8N >= 1 && C8N <= 32 && (C8N & (C8N - 1)) == 0, "C/8 must be a power of two <= 32");
-  __shared__ float red[8][K * C + K];
+  __shared__ float red[8][K * C + K + (STATS ? 2 * C : 0)];
+  const int n = blockIdx.y;
   const int c8 = threadIdx.x % C8N, c0 = c8 * 8;
   float wr[K][8];
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) wr[k][i] = w[k * C + c0 + i];
-  float aw[K][8], ab[K];
+  float av[8], bv[8];
+  if (na) {  // per-image affine of the fused producer: z = leaky_relu(na * y + nb)
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0)), a1 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0)), b1 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0) + 1);
+    av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+  float aw[K][8], ab[K], t1[STATS ? 8 : 1], t2[STATS ? 8 : 1];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     ab[k] = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) aw[k][i] = 0.f;
   }
-  const int64_t total = static_cast<int64_t>(N) * HW;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * (256 / C8N);
-  constexpr int U = 4;  // pixels in flight per thread
-  for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * (256 / C8N) + threadIdx.x / C8N; g0 < total; g0 += U * stride) {
+#pragma unroll
+  for (int i = 0; i < (STATS ? 8 : 1); ++i) t1[i] = t2[i] = 0.f;
+  const float* dln = dl + static_cast<int64_t>(n) * K * HW;
+  const T* zn = z + static_cast<int64_t>(n) * HW * zp + c0;
+  T* dzn = dz + static_cast<int64_t>(n) * HW * dzp + c0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * L;
+  constexpr int U = STATS ? 3 : 4;  // pixels in flight per thread (the sums cost 16 registers)
+  for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * L + threadIdx.x / C8N; g0 < HW; g0 += U * stride) {
     float d[U][K];
     Vec8<T> zv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t g = g0 + u * stride;
-      if (g < total) {
-        const int n = static_cast<int>(g / HW);
-        const int64_t px = g - static_cast<int64_t>(n) * HW;
+      const int64_t px = g0 + u * stride;
+      if (px < HW) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) d[u][k] = __ldg(dl + (static_cast<int64_t>(n) * K + k) * HW + px);
-        zv[u] = Vec8<T>::ld_stream(z + g * zp + c0);
+        for (int k = 0; k < K; ++k) d[u][k] = __ldg(dln + k * HW + px);
+        zv[u] = Vec8<T>::ld_stream(zn + px * zp);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t g = g0 + u * stride;
-      if (g >= total) break;
+      const int64_t px = g0 + u * stride;
+      if (px >= HW) break;
       float zf[8], o[8];
       zv[u].unpack(zf);
-      if (na) {  // z = leaky_relu(na * y + nb), recomputed from the raw conv output (per-image affine: L1-resident)
-        const int n = static_cast<int>(g / HW);
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0)), a1 = __ldg(reinterpret_cast<const float4*>(na + n * C + c0) + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0)), b1 = __ldg(reinterpret_cast<const float4*>(nb + n * C + c0) + 1);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = fmaf(av[i], zf[i], bv[i]);
-          zf[i] = t > 0.f ? t : t * slope;
-        }
-      }
 #pragma unroll
       for (int k = 0; k < K; ++k) ab[k] += d[u][k];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        const float yraw = zf[i];
+        float zact = yraw, sl = 1.f;
+        if (na) {
+          const float t = fmaf(av[i], yraw, bv[i]);
+          sl = t > 0.f ? 1.f : slope;
+          zact = t * sl;
+        }
         float sacc = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           sacc = fmaf(wr[k][i], d[u][k], sacc);
-          aw[k][i] = fmaf(d[u][k], zf[i], aw[k][i]);
+          aw[k][i] = fmaf(d[u][k], zact, aw[k][i]);
         }
         o[i] = sacc;
+        if (STATS) {
+          const float gm = to_f32(from_f32<T>(sacc)) * sl;  // the value the norm backward will read back
+          t1[i] += gm;
+          t2[i] = fmaf(gm, yraw, t2[i]);
+        }
       }
-      Vec8<T>::st(dz + g * dzp + c0, o);
+      Vec8<T>::st(dzn + px * dzp, o);
     }
   }
   // pixel lanes of a warp that share a channel octet: butterfly over the lane bits above log2(C8N)
@@ -413,6 +427,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       for (int i = 0; i < 8; ++i) aw[k][i] += __shfl_xor_sync(0xffffffffu, aw[k][i], m);
       ab[k] += __shfl_xor_sync(0xffffffffu, ab[k], m);
     }
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        t1[i] += __shfl_xor_sync(0xffffffffu, t1[i], m);
+        t2[i] += __shfl_xor_sync(0xffffffffu, t2[i], m);
+      }
+    }
   }
   if (lane < C8N) {
 #pragma unroll
@@ -421,13 +442,22 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       for (int i = 0; i < 8; ++i) red[warp][k * C + c0 + i] = aw[k][i];
       if (c8 == 0) red[warp][K * C + k] = ab[k];
     }
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        red[warp][K * C + K + 2 * (c0 + i)] = t1[i];
+        red[warp][K * C + K + 2 * (c0 + i) + 1] = t2[i];
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * C + K; i += 256) {
+  const int64_t row = static_cast<int64_t>(n) * gridDim.x + blockIdx.x;
+  for (int i = threadIdx.x; i < K * C + K + (STATS ? 2 * C : 0); i += 256) {
     float sacc = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) sacc += red[wv][i];
-    partial[static_cast<int64_t>(blockIdx.x) * (K * C + K) + i] = sacc;
+    if (i < K * C + K) partial[row * (K * C + K) + i] = sacc;
+    else tpart[row * (2 * C) + (i - (K * C + K))] = sacc;  // [N][P][C][2]
   }
 }
 
@@ -537,7 +567,7 @@ __global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ 
     da[i] = g * (a[i] - b[i]);
 }
 
-static int head_bwd_blocks() { return num_sms() * 4; }
+
 
 }  // namespace b200
 
@@ -629,26 +659,42 @@ extern "C" int b200unet_head_fwd_f32(const void* z, int64_t z_pitch, const float
   return head_fwd_impl<float>(z, z_pitch, w, bias, logits_nchw, N, HW, C, K, stream);
 }
 
+// blocks per image of the head backward = partial-sum slots per image of its norm-backward sums ([N][P][C][2])
+extern "C" int b200unet_head_bwd_stat_slots(int N, int64_t HW) {
+  if (N <= 0 || HW <= 0) return 0;
+  int64_t per = ceil_div64(static_cast<int64_t>(num_sms()) * 4, N);
+  const int64_t mx = ceil_div64(HW, 64);  // at least one sweep of 64 pixel lanes per block
+  if (per > mx) per = mx;
+  return static_cast<int>(per < 1 ? 1 : per);
+}
+
 extern "C" int64_t b200unet_head_bwd_workspace(int N, int64_t HW, int C, int K) {
-  (void)N; (void)HW;
-  return static_cast<int64_t>(head_bwd_blocks()) * (K * C + K) * 4;
+  return static_cast<int64_t>(b200unet_head_bwd_stat_slots(N, HW)) * N * (K * C + K) * 4;
 }
 
 template <typename T>
 static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pitch, const float* w, void* dz,
                          int64_t dz_pitch, float* dw, float* db, float* workspace, int64_t workspace_bytes, int N,
                          int64_t HW, int C, int K, void* stream, const float* na = nullptr, const float* nb = nullptr,
-                         float slope = 0.f) {
+                         float slope = 0.f, float* tpart = nullptr) {
   B200_CHECK_ARG(dlogits_nchw && z && w && dz && dw && db && workspace, "head_bwd: null pointer");
   B200_CHECK_ARG(z_pitch % 8 == 0 && dz_pitch % 8 == 0, "head_bwd: pitches must be multiples of 8");
+  B200_CHECK_ARG(N > 0 && N <= 65535, "head_bwd: batch must fit the grid");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_bwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
-  const int blocks = head_bwd_blocks();
+  B200_CHECK_ARG(!tpart || (na && nb), "head_bwd: the norm-backward partial sums need the fused producer (a, b)");
+  const int bpi = b200unet_head_bwd_stat_slots(N, HW);
   B200_CHECK_ARG(workspace_bytes >= b200unet_head_bwd_workspace(N, HW, C, K), "head_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  head_bwd_kernel<T, 32, 3><<<blocks, 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
-                                                    static_cast<T*>(dz), dz_pitch, workspace, N, HW, na, nb, slope);
+  if (tpart)
+    head_bwd_kernel<T, 32, 3, true><<<dim3(bpi, N), 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
+                                                                  static_cast<T*>(dz), dz_pitch, workspace, HW, na, nb,
+                                                                  slope, tpart);
+  else
+    head_bwd_kernel<T, 32, 3, false><<<dim3(bpi, N), 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
+                                                                   static_cast<T*>(dz), dz_pitch, workspace, HW, na, nb,
+                                                                   slope, nullptr);
   B200_LAUNCH_CHECK("head_bwd_kernel");
-  head_bwd_finalize_kernel<<<1, 1024, 0, st>>>(workspace, blocks, K * C, K, dw, db);
+  head_bwd_finalize_kernel<<<1, 1024, 0, st>>>(workspace, bpi * N, K * C, K, dw, db);
   B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
   return 0;
 }
@@ -777,6 +823,22 @@ extern "C" int b200unet_head_norm_bwd(const float* dlogits_nchw, const void* y, 
   B200_CHECK_ARG(a && b, "head_norm_bwd: null affine");
   return head_bwd_impl<__nv_bfloat16>(dlogits_nchw, y, y_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N,
                                       HW, C, K, stream, a, b, slope);
+}
+extern "C" int b200unet_head_norm_bwd_stats(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
+                                            const float* b, float slope, const float* w, void* dz, int64_t dz_pitch,
+                                            float* dw, float* db, float* workspace, int64_t workspace_bytes,
+                                            float* bwd_part, int N, int64_t HW, int C, int K, void* stream) {
+  B200_CHECK_ARG(a && b && bwd_part, "head_norm_bwd_stats: null affine or partial buffer");
+  return head_bwd_impl<__nv_bfloat16>(dlogits_nchw, y, y_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N,
+                                      HW, C, K, stream, a, b, slope, bwd_part);
+}
+extern "C" int b200unet_head_norm_bwd_stats_f32(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
+                                                const float* b, float slope, const float* w, void* dz, int64_t dz_pitch,
+                                                float* dw, float* db, float* workspace, int64_t workspace_bytes,
+                                                float* bwd_part, int N, int64_t HW, int C, int K, void* stream) {
+  B200_CHECK_ARG(a && b && bwd_part, "head_norm_bwd_stats: null affine or partial buffer");
+  return head_bwd_impl<float>(dlogits_nchw, y, y_pitch, w, dz, dz_pitch, dw, db, workspace, workspace_bytes, N, HW, C, K,
+                              stream, a, b, slope, bwd_part);
 }
 extern "C" int b200unet_head_norm_bwd_f32(const float* dlogits_nchw, const void* y, int64_t y_pitch, const float* a,
                                           const float* b, float slope, const float* w, void* dz, int64_t dz_pitch,

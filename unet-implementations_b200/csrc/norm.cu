@@ -246,7 +246,12 @@ __global__ void __launch_bounds__(kNormThreads, (HAS2 || sizeof(T) != 2) ? 2 : 3
 
 // per (n, c):  S1 = s*T1 = sum g,  S2 = s*rstd*T2 = sum g*xh;  dy = A1*m*dz - A2*(y - mean) - A3 with
 //   A1 = gamma*rstd*s,  A2 = gamma*rstd*rstd*S2/HW,  A3 = gamma*rstd*S1/HW.    grid (images, C/32), 256 threads
+// `part2` (optional): a second set of partials (the skip-connection operand reduced by its own producer).  `raw_mean`
+// (optional): the partials hold T2raw = sum gm * y instead of sum gm * (y - mean) (producer-side sums,
+// b200unet_in_bwd_args.ext_part): T2 = T2raw - mean * T1, in double.
 __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __restrict__ part, int P,
+                                                               const float* __restrict__ part2, int P2,
+                                                               const float* __restrict__ raw_mean,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ rstd,
                                                                const float* __restrict__ drop,
@@ -258,16 +263,21 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
   const int c = blockIdx.y * 32 + cl;
   double t1 = 0.0, t2 = 0.0;
   if (c < C) {
-    const float2* sp = reinterpret_cast<const float2*>(part) + static_cast<int64_t>(n) * P * C + c;
-    for (int p = pg; p < P; p += 32) {  // four independent loads in flight
-      float2 v[4];
+    for (int set = 0; set < 2; ++set) {
+      const float* pp = set ? part2 : part;
+      const int PP = set ? P2 : P;
+      if (!pp) continue;
+      const float2* sp = reinterpret_cast<const float2*>(pp) + static_cast<int64_t>(n) * PP * C + c;
+      for (int p = pg; p < PP; p += 32) {  // four independent loads in flight
+        float2 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        v[u] = (p + 8 * u < P) ? sp[static_cast<int64_t>(p + 8 * u) * C] : make_float2(0.f, 0.f);
+        for (int u = 0; u < 4; ++u)
+          v[u] = (p + 8 * u < PP) ? sp[static_cast<int64_t>(p + 8 * u) * C] : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        t1 += v[u].x;
-        t2 += v[u].y;
+        for (int u = 0; u < 4; ++u) {
+          t1 += v[u].x;
+          t2 += v[u].y;
+        }
       }
     }
   }
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
     t2 += red[k][cl][1];
   }
   const int i = n * C + c;
+  if (raw_mean) t2 -= static_cast<double>(raw_mean[i]) * t1;
   const double s = drop ? static_cast<double>(drop[i]) : 1.0;
   const double r = rstd[i];
   const double S1 = s * t1, S2 = s * r * t2;
@@ -650,7 +661,8 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
   const size_t red_bytes = static_cast<size_t>(m.threads) * 16 * sizeof(typename AccT<T>::type);
   const double inv_hw = 1.0 / static_cast<double>(HW);
   if constexpr (sizeof(T) == 2) {
-    const int cg = bwd_fused_group(HW, C, has2);
+    const bool ext_given = A->ext_part != nullptr && (!has2 || A->ext_part2 != nullptr);
+    const int cg = ext_given ? 0 : bwd_fused_group(HW, C, has2);
     if (cg) {
       const size_t smem = static_cast<size_t>(HW) * cg * 2 * (has2 ? 3 : 2) + (256 * 16 + 64 * 4) * sizeof(float);
       auto kern = has2 ? in_bwd_fused_kernel<true> : in_bwd_fused_kernel<false>;
@@ -668,14 +680,23 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
       return 0;
     }
   }
+  // producer-side sums: the kernel(s) that wrote dz (and dz2) already reduced gm and gm * y per image over their own
+  // blocks -- no pass over (dz, y) is needed before the apply pass
+  const bool ext = A->ext_part != nullptr && (!has2 || A->ext_part2 != nullptr);
   for (int n0 = 0; n0 < N; n0 += ipc) {
     const int nn = (N - n0 < ipc) ? N - n0 : ipc;
     K.n0 = n0;
-    if (has2) in_bwd_reduce_kernel<T, true><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
-    else in_bwd_reduce_kernel<T, false><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
-    B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
-    in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, A->gamma, A->rstd, A->drop_scale, coef,
-                                                                     imgsum, C, n0, inv_hw);
+    if (ext) {
+      in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(A->ext_part, A->ext_P, has2 ? A->ext_part2 : nullptr,
+                                                                       A->ext_P2, A->mean, A->gamma, A->rstd, A->drop_scale,
+                                                                       coef, imgsum, C, n0, inv_hw);
+    } else {
+      if (has2) in_bwd_reduce_kernel<T, true><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+      else in_bwd_reduce_kernel<T, false><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+      B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
+      in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, nullptr, 0, nullptr, A->gamma, A->rstd,
+                                                                       A->drop_scale, coef, imgsum, C, n0, inv_hw);
+    }
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
     K.chunk = chunk_apply;
     if (has2)

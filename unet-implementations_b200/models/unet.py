@@ -210,6 +210,8 @@ class UNet(nn.Module):
         # backward runs each weight-gradient kernel (tensor-bound) on a side stream, concurrently with the NEXT layer's
         # InstanceNorm backward (HBM-bound) on the main stream; B200UNET_OVERLAP=0 or this flag = False serialises
         self.overlap_wgrad = os.environ.get("B200UNET_OVERLAP", "1") != "0"
+        # kernels that write a gradient dz also reduce the norm-backward sums of the unit that consumes it (A/B knob)
+        self.producer_sums = os.environ.get("B200UNET_PRODUCER_SUMS", "1") != "0"
         self._side_streams: Dict[int, torch.cuda.Stream] = {}
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
         # "bf16": production path (tcgen05 convs, NHWC bf16 arena).  "fp32": verification mode -- the same fused
@@ -714,9 +716,16 @@ def _backward_impl(ctx, dlogits):
     head = model._head_conv()
     if dlogits.dtype != torch.float32:
         dlogits = dlogits.float()
+    ext_part = None  # norm-backward partial sums of the NEXT unit to process, produced by the kernel that wrote its dz
     if model.head_kind == "seg1x1":
-        dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm, out_dw=dest(head.weight),
-                                         out_db=dest(head.bias))
+        if ctx.head_norm is not None and model.producer_sums:
+            # the head backward reads the last unit's raw output anyway (it recomputes z for dW): it also reduces that
+            # unit's norm-backward sums, whose own reduction pass over (dz, y) -- 1.07 GB at 512^2 x 32 -- disappears
+            dz, dwh, dbh, ext_part = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm,
+                                                       out_dw=dest(head.weight), out_db=dest(head.bias), want_bwd_part=True)
+        else:
+            dz, dwh, dbh = ops.head_backward(dlogits, ctx.z_last, head.weight, norm=ctx.head_norm, out_dw=dest(head.weight),
+                                             out_db=dest(head.bias))
     else:
         z_last, wdh = ctx.z_last, ctx.head_wd
         cpad = wdh.shape[3]
@@ -789,7 +798,9 @@ def _backward_impl(ctx, dlogits):
         if dgd is None or dbd is None:
             dgd = dbd = None
         dy, dgamma, dbeta = ops.in_backward(dz, dz2, rec["y"], rec["a"], rec["b"], rec["mean"], rec["rstd"], rec["scale"],
-                                            norm.weight, rec["slope"], out_dgamma=dgd, out_dbeta=dbd)
+                                            norm.weight, rec["slope"], out_dgamma=dgd, out_dbeta=dbd,
+                                            ext_part=ext_part if dz2 is None else None)
+        ext_part = None
         trec = None
         if btrace is not None:
             trec = dict(kind="unit", li=li, dz=dz, dz2=dz2, y=rec["y"], dy=dy, dgamma=dgamma, dbeta=dbeta, xin=rec.get("xin"),

@@ -253,9 +253,12 @@ def in_apply(y, a, b, slope, out=None):
     return z
 
 
-def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgamma=None, out_dbeta=None):
+def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgamma=None, out_dbeta=None,
+                ext_part=None, ext_part2=None):
     """Backward of z = lrelu(IN(y))*drop.  dz2 (optional) is a second gradient contribution added to dz.
-    Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C]); the parameter gradients go to out_dgamma / out_dbeta if given."""
+    Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C]); the parameter gradients go to out_dgamma / out_dbeta if given.
+    ext_part / ext_part2: fp32 [N,P,C,2] partial sums (sum gm, sum gm*y) already produced by the kernel that wrote dz /
+    dz2 -- the reduction pass over (dz, y) is then skipped."""
     n, h, w, c = y.shape
     hw = h * w
     nbytes = _lib.call("b200unet_in_backward_workspace", n, hw, c)
@@ -267,9 +270,15 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgam
         dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
     dy = torch.empty((n, h, w, c), dtype=y.dtype, device=y.device)
     assert dz.dtype == y.dtype and (dz2 is None or dz2.dtype == y.dtype)
+    ep, ep2 = ext_part, ext_part2
+    if ep is not None:
+        assert ep.dtype == torch.float32 and ep.is_contiguous() and ep.shape[0] == n and tuple(ep.shape[2:]) == (c, 2)
+    if ep2 is not None:
+        assert ep2.dtype == torch.float32 and ep2.is_contiguous() and ep2.shape[0] == n and tuple(ep2.shape[2:]) == (c, 2)
     args = InBwdArgs(_p(dz), pitch_of(dz), _p(dz2), pitch_of(dz2) if dz2 is not None else 0, _p(y), pitch_of(y), _p(a),
                      _p(b), _p(mean), _p(rstd), _p(drop_scale), _p(_f32(gamma.detach())), float(slope), _p(dy),
-                     pitch_of(dy), _p(dgb[0]), _p(dgb[1]), _p(ws), nbytes, n, hw, c)
+                     pitch_of(dy), _p(dgb[0]), _p(dgb[1]), _p(ws), nbytes, n, hw, c,
+                     _p(ep), ep.shape[1] if ep is not None else 0, _p(ep2), ep2.shape[1] if ep2 is not None else 0)
     _lib.call("b200unet_in_backward" + _sfx(y), ctypes.byref(args), _stream())
     return dy, dgb[0], dgb[1]
 
@@ -332,8 +341,9 @@ def head_forward(z, weight, bias, norm=None):
     return logits
 
 
-def head_backward(dlogits, z, weight, norm=None, out_dw=None, out_db=None):
-    """Returns (dz NHWC, dW [K,C,1,1], db [K]).  norm as in head_forward (z recomputed from the raw conv output)."""
+def head_backward(dlogits, z, weight, norm=None, out_dw=None, out_db=None, want_bwd_part=False):
+    """Returns (dz NHWC, dW [K,C,1,1], db [K]).  norm as in head_forward (z recomputed from the raw conv output).
+    want_bwd_part (with norm): also returns the producing unit's norm-backward partial sums [N,P,C,2] as a 4th value."""
     n, h, w, c = z.shape
     k = weight.shape[0]
     dl = _f32(dlogits.contiguous())
@@ -346,6 +356,14 @@ def head_backward(dlogits, z, weight, norm=None, out_dw=None, out_db=None):
     if norm is None:
         _lib.call("b200unet_head_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(_f32(weight.detach().reshape(k, c))), _p(dz),
                   pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, n, h * w, c, k, _stream())
+    elif want_bwd_part:
+        a, b, slope = norm
+        slots = _lib.call("b200unet_head_bwd_stat_slots", n, h * w)
+        part = torch.empty((n, slots, c, 2), dtype=torch.float32, device=z.device)
+        _lib.call("b200unet_head_norm_bwd_stats" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(a), _p(b), float(slope),
+                  _p(_f32(weight.detach().reshape(k, c))), _p(dz), pitch_of(dz), _p(dw), _p(db), _p(ws), nbytes, _p(part),
+                  n, h * w, c, k, _stream())
+        return dz, dw, db, part
     else:
         a, b, slope = norm
         _lib.call("b200unet_head_norm_bwd" + _sfx(z), _p(dl), _p(z), pitch_of(z), _p(a), _p(b), float(slope),
