@@ -67,8 +67,20 @@ typedef struct {
   void* dx;           /* bf16 NHWC gradient wrt conv input [N,H,W,Cin], pitch dx_pitch */
   int64_t dx_pitch;
   int N, H, W, Cin, Cout, stride; /* H,W = conv INPUT size */
+  /* Optional producer-side InstanceNorm-backward sums (b200unet_in_bwd_args.ext_part).  dx is the gradient dz of the
+   * unit whose output feeds this conv; with bs_part != NULL the epilogue also reads that unit's raw output bs_y
+   * ([N,H,W,Cin] bf16) and reduces, per image over its own tiles, T1 = sum gm and T2raw = sum gm * y with
+   * gm = dx_stored * (bs_a*y + bs_b > 0 ? 1 : bs_slope), so that unit's norm backward needs no reduction pass.
+   * bs_part = fp32 [N][P][Cin][2], P = b200unet_conv_dgrad_bwd_slots(...) > 0 (0 = this shape does not support it). */
+  const void* bs_y;
+  int64_t bs_y_pitch;
+  const float* bs_a;   /* fp32 [N,Cin] */
+  const float* bs_b;
+  float bs_slope;
+  float* bs_part;
 } b200unet_conv_dgrad_args;
 int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream);
+int b200unet_conv_dgrad_bwd_slots(int N, int H, int W, int Cin, int Cout, int stride);
 
 typedef struct {
   const void* x;      /* bf16 NHWC conv input [N,H,W,Cin], pitch x_pitch */

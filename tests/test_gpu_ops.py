@@ -303,6 +303,38 @@ def test_head_backward_reduces_the_producing_units_norm_backward_sums(n, h, w):
     assert O.rel_l2(dg1, dg0) <= 1e-4 and O.rel_l2(dbt1, dbt0) <= 1e-4
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 40, 190, 32), (1, 9, 128, 32), (2, 21, 70, 64), (1, 64, 256, 64), (1, 7, 131, 32)])
+def test_data_gradient_epilogue_reduces_the_consuming_units_norm_backward_sums(n, h, w, c):
+    """Producer-side sums in the narrow-output data-gradient kernels (pair rows for dense 32 -> 32 tensors at W >= 128,
+    column-stacked otherwise): dx must be unchanged, the partial sums must equal fp64 sums over the STORED dx, and the
+    norm backward fed with them must agree with the self-reducing one."""
+    from unet_implementations_b200 import ops
+    g = torch.Generator().manual_seed(41)
+    dy, _ = rand_act(n, h, w, c, seed=42)
+    wt = torch.randn(c, c, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5
+    _, wd = ops.pack_conv_weights(wt.cuda())
+    y, _ = rand_act(n, h, w, c, seed=43, scale=1.5)
+    gamma = (torch.rand(c, generator=g) + 0.5).cuda()
+    beta = (torch.randn(c, generator=g) * 0.3).cuda()
+    drop = torch.where(torch.rand(n, c, generator=g) < 0.25, 0.0, 1.25).cuda()
+    stats = torch.stack([y.float().sum((1, 2)), (y.float() ** 2).sum((1, 2))], -1).reshape(n, 1, c, 2).contiguous()
+    mean, rstd, a, b = ops.in_finalize(stats, gamma, beta, drop, 1e-5, h * w)
+    dx0 = ops.conv_dgrad(dy, wd, (h, w), 1)
+    dx, part = ops.conv_dgrad(dy, wd, (h, w), 1, bwd_sums=(y, a, b, 0.01))
+    assert part is not None, "this shape is expected on the narrow-output kernels"
+    assert torch.equal(dx, dx0)
+    pre = y.double() * a[:, None, None, :].double() + b[:, None, None, :].double()
+    gm = dx.double() * torch.where(pre > 0, 1.0, 0.01)
+    got = part.double().sum(1)
+    t1, t2 = gm.sum((1, 2)), (gm * y.double()).sum((1, 2))
+    assert float(((got[..., 0] - t1).abs() / gm.abs().sum((1, 2)).clamp_min(1e-30)).max()) <= 1e-5
+    assert float(((got[..., 1] - t2).abs() / (gm * y.double()).abs().sum((1, 2)).clamp_min(1e-30)).max()) <= 1e-5
+    dy0, dg0, db0 = ops.in_backward(dx, None, y, a, b, mean, rstd, drop, gamma, 0.01)
+    dy1, dg1, db1 = ops.in_backward(dx, None, y, a, b, mean, rstd, drop, gamma, 0.01, ext_part=part)
+    assert O.rel_l2(dy1.float(), dy0.float()) <= 2e-3
+    assert O.rel_l2(dg1, dg0) <= 1e-4 and O.rel_l2(db1, db0) <= 1e-4
+
+
 def _guarded(shape, dtype=torch.bfloat16, guard=4096, fill=3.0):
     """A tensor of `shape` carved out of the middle of a larger allocation whose margins hold a sentinel value."""
     n = 1

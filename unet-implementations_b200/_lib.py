@@ -26,6 +26,8 @@ class ConvDgradArgs(Structure):
     _fields_ = [
         ("dy", c_void_p), ("dy_pitch", c_int64), ("wt", c_void_p), ("dx", c_void_p), ("dx_pitch", c_int64),
         ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("stride", c_int),
+        ("bs_y", c_void_p), ("bs_y_pitch", c_int64), ("bs_a", c_void_p), ("bs_b", c_void_p), ("bs_slope", c_float),
+        ("bs_part", c_void_p),
     ]
 
 
@@ -68,6 +70,7 @@ SIGNATURES = {
     "b200unet_conv_fprop_partials": (c_int, [_I, _I, _I, _I]),
     "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
     "b200unet_conv_dgrad": (c_int, [POINTER(ConvDgradArgs), _P]),
+    "b200unet_conv_dgrad_bwd_slots": (c_int, [_I, _I, _I, _I, _I, _I]),
     "b200unet_conv_dgrad_s2_supported": (c_int, [_I, _I]),
     "b200unet_pack_s2_dgrad_weights": (c_int, [_P, _P, _I, _I, _P]),
     "b200unet_conv_dgrad_s2": (c_int, [POINTER(ConvDgradArgs), _P]),
@@ -140,7 +143,7 @@ SIGNATURES = {
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
     "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_set_reserved_sms", "b200unet_launch_count", "b200unet_conv_fprop_partials",
-    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_head_bwd_stat_slots", "b200unet_recon_head_bwd_workspace",
+    "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_head_bwd_stat_slots", "b200unet_conv_dgrad_bwd_slots", "b200unet_recon_head_bwd_workspace",
     "b200unet_conv_dgrad_s2_supported",
     "b200unet_mse_workspace",
     "b200unet_conv_wgrad_workspace", "b200unet_stem_partials", "b200unet_stem_wgrad_workspace",

@@ -68,18 +68,31 @@ static inline int pick_bk(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 :
 // fp32 split-K partials [S][9][cin][cout] -> OIHW gradient (conv_tc.cu)
 int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st);
 
+// Producer-side InstanceNorm-backward sums of a data-gradient kernel (b200unet_conv_dgrad_args.bs_*): the epilogue reads
+// the consuming unit's raw output y next to the gradient tile it has just staged and accumulates, per image,
+// T1 = sum gm, T2raw = sum gm * y with gm = dx_stored * lrelu'(a*y + b) into `part` ([N][P][C][2], the layout of the
+// forward statistics).
+struct BwdSums {
+  const __nv_bfloat16* y;
+  int64_t y_pitch;
+  const float* a;
+  const float* b;
+  float slope;
+};
+
 // Narrow-output forward / data gradient with the column taps stacked on N (conv_narrow.cu): stride 1, N-side
 // channels in {32, 64}, weights resident in shared memory, image at least 64 pixels wide.
 bool nconv_supported(int k_channels, int n_channels, int stride, int W);
 int nconv_stat_slots(int N, int H, int W);
 int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
-                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st);
+                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st,
+                 const BwdSums* bs = nullptr);
 // 32 -> 32 channels on dense tensors with pixel pairs as 128-byte operand rows (conv_pair.cu); taken by nconv_launch
 // when it applies.
 bool pconv_supported(int k_channels, int n_channels, int stride, int W, int64_t src_pitch, int64_t out_pitch);
 int pconv_stat_slots(int N, int H, int W);
 int pconv_launch(const void* src, const void* wpack, void* out, float* stats, int N, int H, int W, int rev, int stat_slots,
-                 cudaStream_t st);
+                 cudaStream_t st, const BwdSums* bs = nullptr);
 // Partial-sum slots per image of the fprop statistics buffer [N][P][Cout][2]: one value for both fprop kernels
 // (conv_fprop_dgrad.cu), so that the caller can size the buffer without knowing which kernel will run.
 int conv_stat_slots(int N, int OH, int OW, int Cout);

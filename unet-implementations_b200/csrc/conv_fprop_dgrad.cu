@@ -708,6 +708,14 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
   return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
 }
 
+// Partial-sum slots per image of the producer-side norm-backward sums, 0 when the kernel that runs this data gradient
+// does not compute them (today: the narrow-output stride-1 kernels of the 512^2 and 256^2 levels, where the reduction
+// passes they replace are largest).
+extern "C" int b200unet_conv_dgrad_bwd_slots(int N, int H, int W, int Cin, int Cout, int stride) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return nconv_supported(Cout, Cin, stride, W) ? nconv_stat_slots(N, H, W) : 0;
+}
+
 extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream) {
   B200_CHECK_ARG(a && a->dy && a->wt && a->dx, "conv_dgrad: null pointer");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_dgrad: stride %d unsupported", a->stride);
@@ -716,9 +724,17 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
   if (!BK || !BN)
     return set_error(kErrUnsupported, "conv_dgrad: Cin=%d Cout=%d outside the tensor-core envelope", a->Cin, a->Cout);
   B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad: pitches must be multiples of 8 elements");
-  if (nconv_supported(a->Cout, a->Cin, a->stride, a->W))
+  if (nconv_supported(a->Cout, a->Cin, a->stride, a->W)) {
+    if (a->bs_part) {
+      B200_CHECK_ARG(a->bs_y && a->bs_a && a->bs_b, "conv_dgrad: norm-backward sums need y, a and b");
+      BwdSums bs{static_cast<const __nv_bfloat16*>(a->bs_y), a->bs_y_pitch, a->bs_a, a->bs_b, a->bs_slope};
+      return nconv_launch(a->dy, a->dy_pitch, a->wt, a->dx, a->dx_pitch, a->bs_part, a->N, a->H, a->W, a->Cout, a->Cin, 1,
+                          nconv_stat_slots(a->N, a->H, a->W), static_cast<cudaStream_t>(stream), &bs);
+    }
     return nconv_launch(a->dy, a->dy_pitch, a->wt, a->dx, a->dx_pitch, nullptr, a->N, a->H, a->W, a->Cout, a->Cin, 1, 0,
                         static_cast<cudaStream_t>(stream));
+  }
+  B200_CHECK_ARG(!a->bs_part, "conv_dgrad: this shape does not produce norm-backward sums (b200unet_conv_dgrad_bwd_slots == 0)");
   const int s = a->stride;
   const int OH = (a->H - 1) / s + 1, OW = (a->W - 1) / s + 1;
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(a->dy);

@@ -38,6 +38,7 @@ struct NConvParams {
   int stat_slots;
   float* stats;
   long long* debug;  // optional [gridDim.x][8] cycle counters (developer instrumentation; NULL in production)
+  BwdSums bs;        // data gradient only: bs.y != NULL makes the statistics pass the norm-backward reduction
 };
 
 struct NConvMaps {
@@ -218,6 +219,15 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
     uint8_t* stg = staging + g * Cfg::kStageBufBytes;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * Cfg::kNeff;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};       // [s1 c0, s2 c0, s1 c1, s2 c1] of this lane's channel pair
+    // data gradient with p.bs.y: the statistics pass becomes the norm-backward reduction of the consuming unit -- the
+    // staged values are dz, the matching words of that unit's raw output y are loaded from global memory at the START of
+    // the tile (kYSteps loads in flight per lane, consumed after the TMA store has been issued) and the sums are
+    // (sum gm, sum gm * y) with gm = dz * lrelu'(a*y + b)
+    const bool bwd = REV && p.bs.y != nullptr;
+    constexpr int kYSteps = (CO == 64) ? kNcValidW : kNcValidW / 2;
+    const uint32_t ycp = (CO == 64) ? static_cast<uint32_t>(lane) : (static_cast<uint32_t>(lane) & 15);  // channel pair
+    const uint32_t ypar = (CO == 64) ? 0u : (static_cast<uint32_t>(lane) >> 4);
+    float pa0 = 0.f, pa1 = 0.f, pb0 = 0.f, pb1 = 0.f;
     int acc_img = -1;
     auto flush = [&](int img) {
       const int first_tile = img * tiles_per_img;
@@ -248,6 +258,23 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
       if (do_stats && n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
+        if (bwd) {
+          const float2 a2 = __ldg(reinterpret_cast<const float2*>(p.bs.a + n_img * CO) + ycp);
+          const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bs.b + n_img * CO) + ycp);
+          pa0 = a2.x; pa1 = a2.y; pb0 = b2.x; pb1 = b2.y;
+        }
+      }
+      uint32_t yw[REV ? kYSteps : 1];
+      if (REV && bwd) {
+        const bool row_ok = (h0 + q) < p.H;
+        const __nv_bfloat16* yrow = p.bs.y + (static_cast<int64_t>(n_img) * p.H + (h0 + q)) * p.W * p.bs.y_pitch + 2 * ycp;
+#pragma unroll
+        for (int i = 0; i < kYSteps; ++i) {
+          const int col = (CO == 64) ? i : (2 * i + static_cast<int>(ypar));
+          yw[REV ? i : 0] = 0u;
+          if (row_ok && w0 + col < p.W)
+            yw[REV ? i : 0] = __ldg(reinterpret_cast<const uint32_t*>(yrow + static_cast<int64_t>(w0 + col) * p.bs.y_pitch));
+        }
       }
       const long long t0 = (kInstr && p.debug) ? clock64() : 0;
       mbar_wait(&tmem_full_bar[g], ph);
@@ -332,10 +359,21 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
             const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
-            s1a += x0;
-            s2a = fmaf(x0, x0, s2a);
-            s1b += x1;
-            s2b = fmaf(x1, x1, s2b);
+            if (REV && bwd) {
+              const uint32_t yy = yw[REV ? (i0 + i) : 0];
+              const float y0 = __uint_as_float(yy << 16), y1 = __uint_as_float(yy & 0xffff0000u);
+              const float g0 = fmaf(pa0, y0, pb0) > 0.f ? x0 : x0 * p.bs.slope;
+              const float g1 = fmaf(pa1, y1, pb1) > 0.f ? x1 : x1 * p.bs.slope;
+              s1a += g0;
+              s2a = fmaf(g0, y0, s2a);
+              s1b += g1;
+              s2b = fmaf(g1, y1, s2b);
+            } else {
+              s1a += x0;
+              s2a = fmaf(x0, x0, s2a);
+              s1b += x1;
+              s2b = fmaf(x1, x1, s2b);
+            }
           }
         }
         acc[0] += s1a;
@@ -451,9 +489,9 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
 // src: [N,H,W,K-side channels] (x for fprop, dy for dgrad); wpack: [N-side channels][3][3][K-side channels];
 // out: [N,H,W,n_channels] (y / dx); rev = 0 fprop, 1 dgrad
 int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* out, int64_t out_pitch, float* stats, int N,
-                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st) {
-  if (pconv_supported(k_channels, n_channels, 1, W, src_pitch, out_pitch))
-    return pconv_launch(src, wpack, out, stats, N, H, W, rev, stat_slots, st);
+                 int H, int W, int k_channels, int n_channels, int rev, int stat_slots, cudaStream_t st, const BwdSums* bs) {
+  if (pconv_supported(k_channels, n_channels, 1, W, src_pitch, out_pitch) && (!bs || bs->y_pitch == n_channels))
+    return pconv_launch(src, wpack, out, stats, N, H, W, rev, stat_slots, st, bs);
   const int BK = nconv_bk(k_channels);
   const NConvGrid g = nconv_grid(N, H, W);
   NConvParams p{};
@@ -467,6 +505,11 @@ int nconv_launch(const void* src, int64_t src_pitch, const void* wpack, void* ou
   p.tiles_per_cta = g.tiles_per_cta;
   p.stat_slots = stat_slots > g.stat_slots ? stat_slots : g.stat_slots;
   p.stats = stats;
+  if (bs) {
+    if (!rev || !stats || bs->y_pitch % 2 != 0)
+      return set_error(kErrInvalid, "nconv: the norm-backward sums need the data gradient and a partial buffer");
+    p.bs = *bs;
+  }
   int rc;
   if ((rc = make_act_map(&maps.src, static_cast<const __nv_bfloat16*>(src), src_pitch, N, H, W, k_channels, 1, 1, 0, 0, BK,
                          kNcTW, kNcPatchRows)))

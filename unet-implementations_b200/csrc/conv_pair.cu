@@ -44,6 +44,7 @@ struct PConvParams {
   int stat_slots;
   float* stats;
   const __nv_bfloat16* w;  // packed [32 N-side][3][3][32 K-side]
+  BwdSums bs;              // data gradient only: bs.y != NULL turns the statistics warps into the norm-backward reduction
 };
 
 struct PConvMaps {
@@ -265,10 +266,14 @@ __global__ void __launch_bounds__(PConvCfg::kThreads, 1) pconv_kernel(const __gr
     const int q = warp & 3;
     const int n_tiles = tile_hi - tile_lo;
     // InstanceNorm partial sums of the STORED bf16 values: lane = (row group lane >> 3, 16-byte chunk lane & 7) of the
-    // staged 128-byte rows, 8 channels per lane; summed over all tiles of an image in registers
-    float s1[8], s2[8];
+    // staged 128-byte rows, 8 channels per lane; summed over all tiles of an image in registers.
+    // Forward: (sum y, sum y^2).  Data gradient with p.bs.y (producer-side norm-backward sums): the staged values are
+    // dz, the matching 16 bytes of the consuming unit's raw output y come straight from global memory (issued BEFORE the
+    // wait for the staged tile, 8 loads in flight per lane), and the sums are (sum gm, sum gm * y), gm = dz * lrelu'.
+    const bool bwd = REV && p.bs.y != nullptr;
+    float s1[8], s2[8], pa[8], pb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = pa[i] = pb[i] = 0.f;
     int acc_img = -1;
     auto flush = [&](int img) {
       const int first_tile = img * tiles_per_img;
@@ -301,47 +306,100 @@ __global__ void __launch_bounds__(PConvCfg::kThreads, 1) pconv_kernel(const __gr
     int n_img = tile_lo / tiles_per_img;
     int tw = (tile_lo - n_img * tiles_per_img) / p.tiles_h;
     int th = tile_lo - n_img * tiles_per_img - tw * p.tiles_h;
-    for (int it = 0; it < n_tiles; ++it) {
+    const int rsub = lane >> 3, ch = lane & 7;
+    constexpr int kSteps = (kPcValidW + 3) / 4;
+    // y words of tile (img, th_, tw_): this lane's 16 bytes of rows [30q, 30q + 30) four rows per step
+    auto load_y = [&](int img, int th_, int tw_, uint4 (&dst)[kSteps]) {
+      const int hh = th_ * kPcTH + q, ww0 = tw_ * kPcValidW;
+      const __nv_bfloat16* yrow = p.bs.y + (static_cast<int64_t>(img) * p.H + hh) * p.Wp * 64 + ch * 8;
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s) {
+        const int col = 4 * s + rsub;
+        dst[s] = make_uint4(0u, 0u, 0u, 0u);
+        if (hh < p.H && col < kPcValidW && ww0 + col < p.Wp)
+          dst[s] = __ldg(reinterpret_cast<const uint4*>(yrow + static_cast<int64_t>(ww0 + col) * 64));
+      }
+    };
+    // one tile ahead: the loads of tile it + 1 are in flight while tile it is consumed (a whole tile period, ~1.6k
+    // cycles, against ~1k cycles of HBM latency; issued and consumed inside the same tile they sat on the hand-over path
+    // to the epilogue groups and the data gradient ran 2x slower)
+    uint4 ya[kSteps], yb[kSteps];
+    if (bwd && n_tiles > 0) load_y(n_img, th, tw, ya);
+    // one tile: consume `cur` (the y words loaded one tile ago), load the next tile's into `nxt`.  The two buffers swap
+    // roles by calling this twice per loop trip -- a register copy nxt -> cur at the end of the tile would wait for the
+    // loads it is supposed to overlap.
+    auto one_tile = [&](int it, uint4 (&cur)[kSteps], uint4 (&nxt)[kSteps]) {
       const int g = it % NG;
       const uint8_t* stg = staging + g * Cfg::kStageBufBytes;
       const int h0 = th * kPcTH, w0 = tw * kPcValidW;
       if (n_img != acc_img) {
         if (acc_img >= 0) flush(acc_img);
         acc_img = n_img;
+        if (bwd) {  // folded affine of this lane's 8 channels (chunk ch = pixel parity ch >> 2, channel octet ch & 3)
+          const float4* a4 = reinterpret_cast<const float4*>(p.bs.a + n_img * kPcC + ((ch & 3) << 3));
+          const float4* b4 = reinterpret_cast<const float4*>(p.bs.b + n_img * kPcC + ((ch & 3) << 3));
+          const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+          pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
+          pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+        }
       }
+      const bool row_in = (h0 + q) < p.H;
+      // coordinates of the next tile
+      int th_n = th + 1, tw_n = tw, img_n = n_img;
+      if (th_n == p.tiles_h) {
+        th_n = 0;
+        if (++tw_n == p.tiles_w) {
+          tw_n = 0;
+          ++img_n;
+        }
+      }
+      if (bwd && it + 1 < n_tiles) load_y(img_n, th_n, tw_n, nxt);
       named_bar_sync(5 + g, 256);
       {
         // warp q sums staging rows [30q, 30q + 30) (its own image row), four rows per step: one 16-byte chunk
         // (8 channels of one pixel of the pair) per lane; only pairs inside the image count (W is even: a pair is
         // inside or outside as a whole)
-        const int rsub = lane >> 3, ch = lane & 7;
-        const bool row_in = (h0 + q) < p.H;
 #pragma unroll
-        for (int i0 = 0; i0 < kPcValidW; i0 += 4) {
-          const int col = i0 + rsub;
+        for (int s = 0; s < kSteps; ++s) {
+          const int col = 4 * s + rsub;
           const int r = q * kPcValidW + col;
           uint4 w = make_uint4(0u, 0u, 0u, 0u);
           if (row_in && col < kPcValidW && w0 + col < p.Wp)
             w = lds_v4(smem_u32(stg) + r * 128 + (((ch ^ (r & 7)) & 7) << 4));
           const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+          if (bwd) {
+            const uint32_t yy[4] = {cur[s].x, cur[s].y, cur[s].z, cur[s].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x0 = __uint_as_float(ww[i] << 16), x1 = __uint_as_float(ww[i] & 0xffff0000u);
-            s1[2 * i] += x0;
-            s2[2 * i] = fmaf(x0, x0, s2[2 * i]);
-            s1[2 * i + 1] += x1;
-            s2[2 * i + 1] = fmaf(x1, x1, s2[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) {
+              const float x0 = __uint_as_float(ww[i] << 16), x1 = __uint_as_float(ww[i] & 0xffff0000u);
+              const float y0 = __uint_as_float(yy[i] << 16), y1 = __uint_as_float(yy[i] & 0xffff0000u);
+              const float g0 = x0 * (fmaf(pa[2 * i], y0, pb[2 * i]) > 0.f ? 1.f : p.bs.slope);
+              const float g1 = x1 * (fmaf(pa[2 * i + 1], y1, pb[2 * i + 1]) > 0.f ? 1.f : p.bs.slope);
+              s1[2 * i] += g0;
+              s2[2 * i] = fmaf(g0, y0, s2[2 * i]);
+              s1[2 * i + 1] += g1;
+              s2[2 * i + 1] = fmaf(g1, y1, s2[2 * i + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float x0 = __uint_as_float(ww[i] << 16), x1 = __uint_as_float(ww[i] & 0xffff0000u);
+              s1[2 * i] += x0;
+              s2[2 * i] = fmaf(x0, x0, s2[2 * i]);
+              s1[2 * i + 1] += x1;
+              s2[2 * i + 1] = fmaf(x1, x1, s2[2 * i + 1]);
+            }
           }
         }
       }
       if (it + NG < n_tiles) named_bar_arrive(7 + g, 256);  // the group may overwrite its staging buffer
-      if (++th == p.tiles_h) {
-        th = 0;
-        if (++tw == p.tiles_w) {
-          tw = 0;
-          ++n_img;
-        }
-      }
+      th = th_n;
+      tw = tw_n;
+      n_img = img_n;
+    };
+    for (int it = 0; it < n_tiles; it += 2) {
+      one_tile(it, ya, yb);
+      if (it + 1 < n_tiles) one_tile(it + 1, yb, ya);
     }
     if (acc_img >= 0) flush(acc_img);
   }
@@ -382,7 +440,7 @@ int pconv_stat_slots(int N, int H, int W) { return (W % 2 == 0 && W >= 128) ? pc
 
 // src: [N,H,W,32] dense (x for fprop, dy for dgrad); wpack: [32 N-side][3][3][32 K-side]; out: [N,H,W,32] dense
 int pconv_launch(const void* src, const void* wpack, void* out, float* stats, int N, int H, int W, int rev, int stat_slots,
-                 cudaStream_t st) {
+                 cudaStream_t st, const BwdSums* bs) {
   const PConvGrid g = pconv_grid(N, H, W);
   PConvParams p{};
   PConvMaps maps;
@@ -395,6 +453,11 @@ int pconv_launch(const void* src, const void* wpack, void* out, float* stats, in
   p.stat_slots = stat_slots > g.stat_slots ? stat_slots : g.stat_slots;
   p.stats = stats;
   p.w = static_cast<const __nv_bfloat16*>(wpack);
+  if (bs) {
+    if (!rev || !stats || bs->y_pitch != kPcC)
+      return set_error(kErrInvalid, "pconv: the norm-backward sums need the data gradient, a partial buffer and a dense y");
+    p.bs = *bs;
+  }
   int rc;
   if ((rc = make_act_map(&maps.src, static_cast<const __nv_bfloat16*>(src), 64, N, H, W / 2, 64, 1, 1, 0, 0, 64, kPcTW,
                          kPcPatchRows)))

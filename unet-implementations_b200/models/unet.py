@@ -211,7 +211,8 @@ class UNet(nn.Module):
         # InstanceNorm backward (HBM-bound) on the main stream; B200UNET_OVERLAP=0 or this flag = False serialises
         self.overlap_wgrad = os.environ.get("B200UNET_OVERLAP", "1") != "0"
         # kernels that write a gradient dz also reduce the norm-backward sums of the unit that consumes it (A/B knob)
-        self.producer_sums = os.environ.get("B200UNET_PRODUCER_SUMS", "1") != "0"
+        self.producer_sums = os.environ.get("B200UNET_PRODUCER_SUMS", "1") != "0"          # the head backward (a gain)
+        self.producer_sums_dgrad = os.environ.get("B200UNET_PRODUCER_SUMS_DGRAD", "0") == "1"  # dgrad epilogues (a loss)
         self._side_streams: Dict[int, torch.cuda.Stream] = {}
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
         # "bf16": production path (tcgen05 convs, NHWC bf16 arena).  "fp32": verification mode -- the same fused
@@ -833,6 +834,15 @@ def _backward_impl(ctx, dlogits):
             ws2 = model._packed_s2(conv, wd) if (stride == 2 and not simt and wd.dtype == BF16) else None
             if ws2 is not None:
                 dx = ops.conv_dgrad_s2(dy, ws2, (xin.shape[1], xin.shape[2]))
+            elif model.producer_sums_dgrad and L["idx"] > 0 and L["kind"] != "fusion" and li - 1 >= first_needed \
+                    and saved[li - 1]["y"] is not None:
+                # dx is the dz of the previous unit of the same block (no skip operand): the data gradient's epilogue can
+                # reduce that unit's norm-backward sums where its kernel supports it (the 512^2 / 256^2 levels).  OFF by
+                # default: measured a net loss there ("tried and dropped") -- the narrow-output
+                # kernels have no spare issue slots for ~8 instructions per element on a few epilogue warps
+                prev = saved[li - 1]
+                dx, ext_part = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt,
+                                              bwd_sums=(prev["y"], prev["a"], prev["b"], prev["slope"]))
             else:
                 dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         if L["kind"] == "fusion":  # 1x1 weight = centre tap of the 3x3 gradient

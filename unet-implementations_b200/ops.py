@@ -124,8 +124,11 @@ def conv_dgrad_s2(dy, w_stacked, in_hw, out=None):
     return dx
 
 
-def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
-    """Gradient wrt the conv input.  dy [N,OH,OW,Cout]; w_dgrad [Cin,3,3,Cout]; returns dx [N,H,W,Cin] bf16."""
+def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False, bwd_sums=None):
+    """Gradient wrt the conv input.  dy [N,OH,OW,Cout]; w_dgrad [Cin,3,3,Cout]; returns dx [N,H,W,Cin] bf16.
+    bwd_sums = (y, a, b, slope) of the unit whose output feeds this conv (dx is its dz): if the kernel that runs this
+    shape supports it, the epilogue also reduces that unit's norm-backward sums and the call returns (dx, part) with
+    part fp32 [N,P,Cin,2] for in_backward(ext_part=...); otherwise (dx, None)."""
     n, oh, ow, cout = dy.shape
     cin = w_dgrad.shape[0]
     h, w = in_hw
@@ -134,8 +137,16 @@ def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False):
     dx = out if out is not None else torch.empty((n, h, w, cin), dtype=dy.dtype, device=dy.device)
     a = ConvDgradArgs(_p(dy), pitch_of(dy), _p(w_dgrad), _p(dx), pitch_of(dx), n, h, w, cin, cout, stride)
     name = "b200unet_conv_dgrad_f32" if dy.dtype == F32 else ("b200unet_conv_dgrad_simt" if simt else "b200unet_conv_dgrad")
+    part = None
+    if bwd_sums is not None and name == "b200unet_conv_dgrad":
+        y, sa, sb, slope = bwd_sums
+        slots = _lib.call("b200unet_conv_dgrad_bwd_slots", n, h, w, cin, cout, stride)
+        if slots > 0 and y.dtype == BF16 and tuple(y.shape) == (n, h, w, cin):
+            part = torch.empty((n, slots, cin, 2), dtype=torch.float32, device=dy.device)
+            a.bs_y, a.bs_y_pitch, a.bs_a, a.bs_b = y.data_ptr(), pitch_of(y), _f32(sa).data_ptr(), _f32(sb).data_ptr()
+            a.bs_slope, a.bs_part = float(slope), part.data_ptr()
     _lib.call(name, ctypes.byref(a), _stream())
-    return dx
+    return (dx, part) if bwd_sums is not None else dx
 
 
 def conv_wgrad(x, dy, stride=1, simt=False, out=None):
