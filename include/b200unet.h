@@ -164,9 +164,13 @@ typedef struct {
   int ext_P;
   const float* ext_part2;
   int ext_P2;
+  /* != 0: do not reduce dgamma / dbeta here; the caller runs b200unet_in_bwd_params on the same workspace later
+   * (dy does not depend on them: the host takes that 6 us kernel off the critical path of backward). */
+  int defer_params;
 } b200unet_in_bwd_args;
 int64_t b200unet_in_backward_workspace(int N, int64_t HW, int C);
 int b200unet_in_backward(const b200unet_in_bwd_args* a, void* stream);
+int b200unet_in_bwd_params(const float* workspace, int N, int64_t HW, int C, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Exact 2x bilinear upsampling, align_corners=False -- F.interpolate in UpBlock.forward (unet.py:219-225) --

@@ -46,7 +46,7 @@ class InBwdArgs(Structure):
         ("drop_scale", c_void_p), ("gamma", c_void_p), ("slope", c_float), ("dy", c_void_p), ("dy_pitch", c_int64),
         ("dgamma", c_void_p), ("dbeta", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("N", c_int), ("HW", c_int64), ("C", c_int),
-        ("ext_part", c_void_p), ("ext_P", c_int), ("ext_part2", c_void_p), ("ext_P2", c_int),
+        ("ext_part", c_void_p), ("ext_P", c_int), ("ext_part2", c_void_p), ("ext_P2", c_int), ("defer_params", c_int),
     ]
 
 
@@ -89,6 +89,7 @@ SIGNATURES = {
     "b200unet_in_apply": (c_int, [_P, _L, _P, _P, _F, _P, _L, _I, _L, _I, _P]),
     "b200unet_in_backward_workspace": (c_int64, [_I, _L, _I]),
     "b200unet_in_backward": (c_int, [POINTER(InBwdArgs), _P]),
+    "b200unet_in_bwd_params": (c_int, [_P, _I, _L, _I, _P, _P, _P]),
     "b200unet_upsample2x_fwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "b200unet_upsample2x_bwd": (c_int, [_P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "b200unet_head_fwd": (c_int, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _P]),

@@ -639,9 +639,11 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
   // the backward apply re-loads ~56 per-channel parameters per thread at block start: it keeps the coarser grid
   const int64_t chunk_apply = chunk;
   const int P = static_cast<int>(ceil_div64(HW, chunk));
-  float* part = A->workspace;
-  float* coef = part + static_cast<int64_t>(N) * P * C * 2;
-  float* imgsum = coef + static_cast<int64_t>(N) * C * 4;
+  // workspace layout: per-image sums [N][C][2] first (b200unet_in_bwd_params finds them without knowing P), then the
+  // apply coefficients [N][C][4], then the block partials [N][P][C][2]
+  float* imgsum = A->workspace;
+  float* coef = imgsum + static_cast<int64_t>(N) * C * 2;
+  float* part = coef + static_cast<int64_t>(N) * C * 4;
   InBwdK<T> K;
   K.dz = static_cast<const T*>(A->dz);
   K.dzp = A->dz_pitch;
@@ -675,8 +677,10 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
       kern<<<dim3(C / cg, N), 256, smem, st>>>(K, A->gamma, A->rstd, A->drop_scale, static_cast<T*>(A->dy), A->dy_pitch,
                                               imgsum, cg / 8, inv_hw);
       B200_LAUNCH_CHECK("in_bwd_fused_kernel");
-      in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
-      B200_LAUNCH_CHECK("in_bwd_param_kernel");
+      if (!A->defer_params) {
+        in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+        B200_LAUNCH_CHECK("in_bwd_param_kernel");
+      }
       return 0;
     }
   }
@@ -708,7 +712,22 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
-  in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+  if (!A->defer_params) {
+    in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+    B200_LAUNCH_CHECK("in_bwd_param_kernel");
+  }
+  return 0;
+}
+
+// dgamma / dbeta of a b200unet_in_backward call made with defer_params: sums the per-image (sum g, sum g * x_hat) that call
+// left in its workspace.  Off the critical path of backward (dy does not depend on it): the host runs it on the
+// weight-gradient side stream.
+extern "C" int b200unet_in_bwd_params(const float* workspace, int N, int64_t HW, int C, float* dgamma, float* dbeta,
+                                      void* stream) {
+  B200_CHECK_ARG(workspace && dgamma && dbeta && N > 0 && HW > 0 && C > 0, "in_bwd_params: null pointer or bad sizes");
+  (void)HW;
+  const float* imgsum = workspace;  // first block of the workspace layout (in_backward_impl)
+  in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(imgsum, dgamma, dbeta, N, C);
   B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
 }

@@ -265,11 +265,13 @@ def in_apply(y, a, b, slope, out=None):
 
 
 def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgamma=None, out_dbeta=None,
-                ext_part=None, ext_part2=None):
+                ext_part=None, ext_part2=None, defer_params=False):
     """Backward of z = lrelu(IN(y))*drop.  dz2 (optional) is a second gradient contribution added to dz.
     Returns (dy bf16 [N,H,W,C], dgamma [C], dbeta [C]); the parameter gradients go to out_dgamma / out_dbeta if given.
     ext_part / ext_part2: fp32 [N,P,C,2] partial sums (sum gm, sum gm*y) already produced by the kernel that wrote dz /
-    dz2 -- the reduction pass over (dz, y) is then skipped."""
+    dz2 -- the reduction pass over (dz, y) is then skipped.
+    defer_params: returns (dy, finish) instead; finish() enqueues the dgamma / dbeta reduction on the then-current
+    stream and returns (dgamma, dbeta) -- it is off the critical path of backward."""
     n, h, w, c = y.shape
     hw = h * w
     nbytes = _lib.call("b200unet_in_backward_workspace", n, hw, c)
@@ -289,8 +291,16 @@ def in_backward(dz, dz2, y, a, b, mean, rstd, drop_scale, gamma, slope, out_dgam
     args = InBwdArgs(_p(dz), pitch_of(dz), _p(dz2), pitch_of(dz2) if dz2 is not None else 0, _p(y), pitch_of(y), _p(a),
                      _p(b), _p(mean), _p(rstd), _p(drop_scale), _p(_f32(gamma.detach())), float(slope), _p(dy),
                      pitch_of(dy), _p(dgb[0]), _p(dgb[1]), _p(ws), nbytes, n, hw, c,
-                     _p(ep), ep.shape[1] if ep is not None else 0, _p(ep2), ep2.shape[1] if ep2 is not None else 0)
+                     _p(ep), ep.shape[1] if ep is not None else 0, _p(ep2), ep2.shape[1] if ep2 is not None else 0,
+                     1 if defer_params else 0)
     _lib.call("b200unet_in_backward" + _sfx(y), ctypes.byref(args), _stream())
+    if defer_params:
+        # dgamma / dbeta are NOT computed yet: call the returned function (on any stream ordered after this one)
+        def finish_params():
+            _lib.call("b200unet_in_bwd_params", _p(ws), n, hw, c, _p(dgb[0]), _p(dgb[1]), _stream())
+            return dgb[0], dgb[1]
+        finish_params.keep = (ws, dgb)  # what the deferred kernel reads / writes: the caller keeps it alive until it has run
+        return dy, finish_params
     return dy, dgb[0], dgb[1]
 
 
