@@ -506,6 +506,18 @@ def main():
         _lib.PROFILER = None
         model.overlap_wgrad = was
 
+    # ---- the same step with the gradient all-reduce switched off (N > 1): each rank's own compute time.  The spread over
+    # the ranks is the lock-step cost of a synchronous step on eight power-capped GPUs (the slowest one sets the pace);
+    # the difference between its maximum and the headline time is what the all-reduce itself costs.
+    per_rank_no_allreduce = None
+    if reducer is not None:
+        reducer.enabled = False
+        step()
+        timed(step, min(args.steps, 10))
+        per_rank_no_allreduce = timed.per_rank_ms
+        reducer.enabled = True
+        step()
+
     # ---- the gradient all-reduce alone (N > 1): the same buckets, nothing else on the GPU
     allreduce_only_ms = None
     if reducer is not None:
@@ -722,6 +734,7 @@ def main():
             "remeasured": remeasured,
             "peak_memory_gib": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2),
             "per_rank_ms_per_step": per_rank_resident,
+            "per_rank_ms_per_step_without_allreduce": per_rank_no_allreduce,
             "allreduce_only_ms": allreduce_only_ms,
             "clocks": clocks,
             "roofline": roofline,

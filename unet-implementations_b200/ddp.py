@@ -15,11 +15,16 @@ buckets.  The gradients autograd returns are views of the flat buffer.
 
 NCCL and the persistent conv kernels.  The tensor-core conv kernels run one CTA per SM with ~226 KB of shared memory;
 an NCCL kernel that lands on an SM delays that SM's CTA, and a persistent kernel is as slow as its slowest CTA
-(round 1: dgrad +11 %, wgrad +4 % at 8 GPUs).  The payload is tiny against NVLink (78.6 MB per 22 ms step), so the
-communicator is capped to a few CTAs (`nccl_options`, NCCL_MAX_CTAS) and the conv grids of BACKWARD -- the only phase
-in which an all-reduce is in flight -- are sized for that many fewer SMs (`reserve_sms`, b200unet_set_reserved_sms;
-forward keeps the whole device).  The last bucket, whose all-reduce cannot overlap anything, holds only the small
-gradients produced last (`tail_bytes`).
+(round 1: dgrad +11 %, wgrad +4 % at 8 GPUs with NCCL's default channel count).  Two knobs, measured on 8 x B200
+(round 2, ms per step, the slowest rank's compute-only step 21.8 ms): communicator capped to 16 CTAs and no SMs
+reserved 22.29; 4 CTAs + 4 SMs reserved in backward 22.44; 8 + 8: 22.47; 2 + 2: 22.58.  Reserving SMs costs the conv
+kernels of backward that share of the device (2.7 % of 9 ms) and buys nothing once the communicator is small, so the
+default is `DEFAULT_NCCL_CTAS` CTAs (`nccl_options`, NCCL_MAX_CTAS) and no reservation; `B200UNET_RESERVED_SMS=n`
+sizes the conv grids of BACKWARD -- the only phase with an all-reduce in flight -- for n fewer SMs
+(b200unet_set_reserved_sms).  The last bucket, whose all-reduce cannot overlap anything, holds only the small
+gradients produced last (`tail_bytes`).  What remains at 8 GPUs (~0.45 ms over the slowest rank's own step) is the
+exposed tail plus the per-step lock-step jitter of eight power-capped GPUs; the spread between the ranks' own step
+times (21.3 .. 21.9 ms) is the other half of the distance to 8 x one GPU.
 """
 from __future__ import annotations
 
@@ -32,7 +37,7 @@ import torch.nn as nn
 
 from .flat import FlatGradSink, backward_param_order  # noqa: F401  (re-exported)
 
-DEFAULT_NCCL_CTAS = 4
+DEFAULT_NCCL_CTAS = 16
 
 
 def nccl_options(max_ctas: int = DEFAULT_NCCL_CTAS):
@@ -48,13 +53,13 @@ def nccl_options(max_ctas: int = DEFAULT_NCCL_CTAS):
 
 def init_process_group(device: torch.device, max_ctas: Optional[int] = None, reserve_sms: Optional[int] = None):
     """`dist.init_process_group("nccl")` for one process per GPU with the communicator capped to `max_ctas` CTAs and
-    as many SMs kept free by the persistent conv kernels.  Environment overrides: B200UNET_NCCL_CTAS,
-    B200UNET_RESERVED_SMS (0 disables)."""
+    (optionally) `reserve_sms` SMs kept free by the conv kernels of backward.  Environment overrides:
+    B200UNET_NCCL_CTAS, B200UNET_RESERVED_SMS."""
     ctas = int(os.environ.get("B200UNET_NCCL_CTAS", max_ctas if max_ctas is not None else DEFAULT_NCCL_CTAS))
     os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
     os.environ.setdefault("NCCL_MIN_CTAS", "1")
     if "B200UNET_RESERVED_SMS" not in os.environ:
-        os.environ["B200UNET_RESERVED_SMS"] = str(reserve_sms if reserve_sms is not None else ctas)
+        os.environ["B200UNET_RESERVED_SMS"] = str(reserve_sms if reserve_sms is not None else 0)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=device, pg_options=nccl_options(ctas))
     return ctas
