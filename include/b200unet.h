@@ -40,6 +40,10 @@ int b200unet_device_ok(void);
  * free SM instead of delaying one CTA of a persistent one-CTA-per-SM conv kernel.  No reference counterpart (the
  * reference has no distributed code). */
 int b200unet_set_reserved_sms(int n);
+/* Programmatic dependent launch of the library's kernels (off by default -- measured no gain; B200UNET_PDL=1 enables): each kernel's CTAs
+ * become resident and run their set-up while the previous kernel of the stream drains, and wait (griddepcontrol.wait)
+ * before touching global memory.  Returns the previous setting.  No reference counterpart. */
+int b200unet_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3x3 convolution, pad 1, stride 1 or 2 -- replaces nn.Conv2d in ConvBlock (Our_UNet/models/unet.py:106-115)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200unet_last_error": (c_char_p, []),
     "b200unet_device_ok": (c_int, []),
     "b200unet_set_reserved_sms": (c_int, [_I]),
+    "b200unet_set_pdl": (c_int, [_I]),
     "b200unet_launch_count": (c_int64, []),
     "b200unet_conv_fprop_partials": (c_int, [_I, _I, _I, _I]),
     "b200unet_conv_fprop": (c_int, [POINTER(ConvFpropArgs), _P]),
@@ -143,7 +144,7 @@ SIGNATURES = {
 
 # entry points that return a value rather than a status code
 _VALUE_FUNCS = {
-    "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_set_reserved_sms", "b200unet_launch_count", "b200unet_conv_fprop_partials",
+    "b200unet_version", "b200unet_last_error", "b200unet_device_ok", "b200unet_set_reserved_sms", "b200unet_set_pdl", "b200unet_launch_count", "b200unet_conv_fprop_partials",
     "b200unet_conv_fprop_simt_partials", "b200unet_sgd_max_tensors", "b200unet_sgd_flat_block_elems", "b200unet_head_bwd_stat_slots", "b200unet_conv_dgrad_bwd_slots", "b200unet_recon_head_bwd_workspace",
     "b200unet_conv_dgrad_s2_supported",
     "b200unet_mse_workspace",

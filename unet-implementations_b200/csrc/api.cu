@@ -8,6 +8,17 @@ namespace b200 {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+int g_pdl = -1;  // -1: read B200UNET_PDL on first use
+
+bool pdl_enabled() {
+  int v = __atomic_load_n(&g_pdl, __ATOMIC_RELAXED);
+  if (v < 0) {
+    const char* e = getenv("B200UNET_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // OFF by default: measured no gain in graph replay and +0.5..1.4 ms of host time eager
+    __atomic_store_n(&g_pdl, v, __ATOMIC_RELAXED);
+  }
+  return v != 0;
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -114,6 +125,12 @@ int b200unet_set_reserved_sms(int n) {
   const int v = b200::num_sms();  // forces initialisation
   (void)v;
   return __atomic_exchange_n(&b200::g_reserved_sms, n < 0 ? 0 : n, __ATOMIC_RELAXED);
+}
+
+int b200unet_set_pdl(int on) {
+  const int prev = b200::pdl_enabled() ? 1 : 0;
+  __atomic_store_n(&b200::g_pdl, on ? 1 : 0, __ATOMIC_RELAXED);
+  return prev;
 }
 
 int b200unet_device_ok(void) {

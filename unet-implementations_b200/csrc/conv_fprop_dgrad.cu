@@ -95,6 +95,7 @@ struct GConvCfg {
 template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
 __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_constant__ GConvMaps maps,
                                                                  const __grid_constant__ GConvParams p) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
   using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT>;
   constexpr int kBBar = B_RES ? 1 : B_SLOTS;
   extern __shared__ uint8_t smem_raw[];
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
 
   if (warp < kProducerWarps) {
     if (elect_one()) {
@@ -603,7 +605,7 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
   p.stat_slots = conv_stat_slots(p.N, p.OH, p.OW, p.cout);  // P of the caller's buffer (>= gg.stat_slots)
   if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * p.cout * 2 * sizeof(float), st));
   if (kInstr && p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  launch_k(kern, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, st, maps, p);
   B200_LAUNCH_CHECK("gconv_kernel");
   if (kInstr && p.debug) {
     long long h[8];

@@ -72,6 +72,7 @@ struct NConvCfg {
 template <int BK, int CO, int A_SLOTS, bool REV, int NG>
 __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(const __grid_constant__ NConvMaps maps,
                                                                                  const __grid_constant__ NConvParams p) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
   using Cfg = NConvCfg<BK, CO, A_SLOTS, NG>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(32 * (kNcEpiWarp0 + 4 * NG), 1) nconv_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
 
   if (warp < kNcProducers) {
     if (elect_one()) {
@@ -470,7 +472,7 @@ static int launch_nconv(const NConvMaps& maps, NConvParams& p, const NConvGrid& 
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * CO * 2 * sizeof(float), st));
   p.debug = nconv_debug_buffer();
   if (kInstr && p.debug) cudaMemsetAsync(p.debug, 0, 148 * 8 * sizeof(long long), st);
-  kern<<<g.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(maps, p);
+  launch_k(kern, dim3(g.grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, maps, p);
   B200_LAUNCH_CHECK("nconv_kernel");
   if (kInstr && p.debug) {  // developer instrumentation (B200UNET_GCONV_DEBUG=1): per-tile cycle counts of CTA 0
     long long h[8];

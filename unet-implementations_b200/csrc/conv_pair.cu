@@ -79,6 +79,7 @@ __device__ __forceinline__ int pc_tap(int j, int pi) {
 template <bool REV>
 __global__ void __launch_bounds__(PConvCfg::kThreads, 1) pconv_kernel(const __grid_constant__ PConvMaps maps,
                                                                        const __grid_constant__ PConvParams p) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
   using Cfg = PConvCfg;
   constexpr int NG = kPcNG, A_SLOTS = kPcSlots;
   extern __shared__ uint8_t smem_raw[];
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(PConvCfg::kThreads, 1) pconv_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
 
   if (warp < kPcProducers) {
     if (elect_one()) {
@@ -473,7 +475,7 @@ int pconv_launch(const void* src, const void* wpack, void* out, float* stats, in
   }
   if (p.stats)
     B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * kPcC * 2 * sizeof(float), st));
-  kern<<<g.grid, PConvCfg::kThreads, PConvCfg::kSmemBytes, st>>>(maps, p);
+  launch_k(kern, dim3(g.grid), dim3(PConvCfg::kThreads), PConvCfg::kSmemBytes, st, maps, p);
   B200_LAUNCH_CHECK("pconv_kernel");
   return 0;
 }

@@ -37,6 +37,7 @@ constexpr int kWgStages = 3;
 template <int U, int BN>
 __global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_constant__ WgradMaps maps,
                                                                  const __grid_constant__ WgradParams p) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
   constexpr int UPG = 128 / U;                      // units per M-group
   constexpr int kUnitBytes = 64 * U * 2;            // 64 pixels x U channels
   constexpr int kGroupBytes = UPG * kUnitBytes;     // 16 KB
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
 
   // units of this CTA that exist (the last group of a layer may be partially filled)
   int valid_units = p.total_units - group0 * UPG;
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgrad_kernel(const __grid_con
 // dw[co][ci][tap] = sum_s partial[s][tap][ci][co]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int cin,
                                       int cout) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(9) * cin * cout;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -219,6 +223,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* 
 // The plain kernel above scatters 4-byte writes 36 bytes apart: 0.6 ms per step over the 22 layers (ncu).
 __global__ void __launch_bounds__(256) wgrad_finalize_tiled_kernel(const float* __restrict__ partial,
                                                                     float* __restrict__ dw, int S, int cin, int cout) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ float tile[32][73];
   const int co_l = threadIdx.x & 31, ci_l = threadIdx.x >> 5;
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 8;
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(256) wgrad_finalize_tiled_kernel(const float* 
 // output channels of one (tap, ci).
 __global__ void __launch_bounds__(256) wgrad_finalize_splits_kernel(const float* __restrict__ partial,
                                                                      float* __restrict__ dw, int S, int cin, int cout) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ float red[8][32];
   const int co_l = threadIdx.x & 31, z = threadIdx.x >> 5;
   const int64_t total = static_cast<int64_t>(9) * cin * cout;
@@ -271,18 +279,18 @@ __global__ void __launch_bounds__(256) wgrad_finalize_splits_kernel(const float*
 
 int launch_wgrad_finalize(const float* partial, float* dw, int S, int cin, int cout, cudaStream_t st) {
   if (cout % 32 == 0 && S >= 16) {
-    wgrad_finalize_splits_kernel<<<(unsigned)(static_cast<int64_t>(9) * cin * cout / 32), 256, 0, st>>>(partial, dw, S, cin,
+    launch_k(wgrad_finalize_splits_kernel, dim3((unsigned)(static_cast<int64_t>(9) * cin * cout / 32)), dim3(256), 0, st, partial, dw, S, cin,
                                                                                                         cout);
     B200_LAUNCH_CHECK("wgrad_finalize_splits_kernel");
     return 0;
   }
   if (cin % 8 == 0 && cout % 32 == 0) {
-    wgrad_finalize_tiled_kernel<<<dim3(cout / 32, cin / 8), 256, 0, st>>>(partial, dw, S, cin, cout);
+    launch_k(wgrad_finalize_tiled_kernel, dim3(cout / 32, cin / 8), dim3(256), 0, st, partial, dw, S, cin, cout);
     B200_LAUNCH_CHECK("wgrad_finalize_tiled_kernel");
     return 0;
   }
   const int64_t total = static_cast<int64_t>(9) * cin * cout;
-  wgrad_finalize_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, dw, S, cin, cout);
+  launch_k(wgrad_finalize_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, st, partial, dw, S, cin, cout);
   B200_LAUNCH_CHECK("wgrad_finalize_kernel");
   return 0;
 }
@@ -337,7 +345,7 @@ static int launch_wgrad(const WgradMaps& maps, const WgradParams& p, const Wgrad
     attr_bytes = (int)pl.smem_bytes;
   }
   dim3 grid(pl.S, pl.gy, pl.gz);
-  kern<<<grid, kConvThreads, pl.smem_bytes, st>>>(maps, p);
+  launch_k(kern, dim3(grid), dim3(kConvThreads), pl.smem_bytes, st, maps, p);
   B200_LAUNCH_CHECK("wgrad_kernel");
   return 0;
 }

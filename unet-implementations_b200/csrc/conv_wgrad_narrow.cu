@@ -55,6 +55,7 @@ struct WnCfg {
 template <int CH, int CO>
 __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_constant__ WgradNMaps maps,
                                                                   const __grid_constant__ WgradNParams p) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
   using Cfg = WnCfg<CH, CO>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kWnMaxStages];
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
 
   if (warp < kProducerWarps) {
     if (elect_one()) {
@@ -267,7 +269,7 @@ static int launch_wgradn(const WgradNMaps& maps, const WgradNParams& p, const Wg
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     attr_bytes = (int)pl.smem_bytes;
   }
-  kern<<<dim3(pl.S, pl.gy), kConvThreads, pl.smem_bytes, st>>>(maps, p);
+  launch_k(kern, dim3(pl.S, pl.gy), dim3(kConvThreads), pl.smem_bytes, st, maps, p);
   B200_LAUNCH_CHECK("wgradn_kernel");
   return 0;
 }

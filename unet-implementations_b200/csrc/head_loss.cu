@@ -77,6 +77,8 @@ template <typename TT>
 __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(const float* __restrict__ logits,
                                                                  const TT* __restrict__ target, int ignore_index,
                                                                  float* __restrict__ part, int64_t HW) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ float scratch[kLossThreads / 32][kLossVals];
   const int n = blockIdx.y;
   const float* z0 = logits + static_cast<int64_t>(n) * kNC * HW;
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_fwd_kernel(const float* __r
 __global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks, const float* __restrict__ class_w,
                                      int dynamic, float weight_ce, float weight_dice, float smooth,
                                      float* __restrict__ loss_out, float* __restrict__ tables, int N) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   // one block of 32 warps; warp w reduces values i = w, w + 32, ... (value v of image b): lanes stride over the
   // partials, fixed-order shuffle tree (the serial version took 46 us on the critical path between forward and backward)
   extern __shared__ double sred[];  // [N][12]
@@ -213,6 +217,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const float* __r
                                                                  const float* __restrict__ grad_out, float weight_ce,
                                                                  float weight_dice, int ignore_index,
                                                                  float* __restrict__ dlogits, int64_t HW) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int n = blockIdx.y;
   const float gs = grad_out ? grad_out[0] : 1.f;
   const float wn0 = tables[0], wn1 = tables[1], wn2 = tables[2];
@@ -289,6 +295,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ z, 
                                                         float* __restrict__ logits, int64_t HW,
                                                         const float* __restrict__ na, const float* __restrict__ nb,
                                                         float slope) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ float ws[K][C];
   __shared__ float bs[K];
   __shared__ float sa[C], sb[C];
@@ -340,6 +348,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) head_bwd_kernel(c
                                                         float* __restrict__ partial, int64_t HW,
                                                         const float* __restrict__ na, const float* __restrict__ nb,
                                                         float slope, float* __restrict__ tpart) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   constexpr int C8N = C / 8;
   constexpr int L = 256 / C8N;  // pixel lanes of a block
   static_assert(C8N >= 1 && C8N <= 32 && (C8N & (C8N - 1)) == 0, "C/8 must be a power of two <= 32");
@@ -465,6 +475,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) head_bwd_kernel(c
 // rows, fixed-order shuffle tree)
 __global__ void __launch_bounds__(1024) head_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int KC,
                                                                   int K, float* __restrict__ dw, float* __restrict__ db) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = warp; i < KC + K; i += 32) {
     double s = 0.0;
@@ -587,11 +599,11 @@ static int loss_fwd_impl(const float* logits_nchw, const TT* target, const float
   B200_CHECK_ARG(workspace_bytes >= b200unet_loss_workspace(N, HW), "loss_fwd: workspace too small");
   const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  loss_fwd_kernel<TT><<<dim3(blocks, N), kLossThreads, 0, st>>>(logits_nchw, target, ignore_index, workspace, HW);
+  launch_k(loss_fwd_kernel<TT>, dim3(blocks, N), dim3(kLossThreads), 0, st, logits_nchw, target, ignore_index, workspace, HW);
   B200_LAUNCH_CHECK("loss_fwd_kernel");
   const size_t smem = static_cast<size_t>(N) * kLossVals * sizeof(double);
   B200_CHECK_ARG(smem <= 48 * 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
-  loss_finalize_kernel<<<1, 1024, smem, st>>>(workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
+  launch_k(loss_finalize_kernel, dim3(1), dim3(1024), smem, st, workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
                                              loss_out, tables, N);
   B200_LAUNCH_CHECK("loss_finalize_kernel");
   return 0;
@@ -603,7 +615,7 @@ static int loss_bwd_impl(const float* logits_nchw, const TT* target, const float
                          void* stream) {
   B200_CHECK_ARG(logits_nchw && target && tables && dlogits_nchw, "loss_bwd: null pointer");
   const int blocks = static_cast<int>(ceil_div64(HW, kLossThreads * kLossPxPerThread));
-  loss_bwd_kernel<TT><<<dim3(blocks, N), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(loss_bwd_kernel<TT>, dim3(blocks, N), dim3(kLossThreads), 0, static_cast<cudaStream_t>(stream), 
       logits_nchw, target, tables, grad_out, weight_ce, weight_dice, ignore_index, dlogits_nchw, HW);
   B200_LAUNCH_CHECK("loss_bwd_kernel");
   return 0;
@@ -645,7 +657,7 @@ static int head_fwd_impl(const void* z, int64_t z_pitch, const float* w, const f
   B200_CHECK_ARG(z_pitch % 8 == 0, "head_fwd: pitch must be a multiple of 8");
   if (!(C == 32 && K == 3)) return set_error(kErrUnsupported, "head_fwd: only C=32, K=3 is built (got C=%d K=%d)", C, K);
   dim3 grid((unsigned)ceil_div64(HW, 256), N);
-  head_fwd_kernel<T, 32, 3><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(z), z_pitch, w,
+  launch_k(head_fwd_kernel<T, 32, 3>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const T*>(z), z_pitch, w,
                                                                                   bias, logits_nchw, HW, na, nb, slope);
   B200_LAUNCH_CHECK("head_fwd_kernel");
   return 0;
@@ -686,15 +698,15 @@ static int head_bwd_impl(const float* dlogits_nchw, const void* z, int64_t z_pit
   B200_CHECK_ARG(workspace_bytes >= b200unet_head_bwd_workspace(N, HW, C, K), "head_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tpart)
-    head_bwd_kernel<T, 32, 3, true><<<dim3(bpi, N), 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
+    launch_k(head_bwd_kernel<T, 32, 3, true>, dim3(bpi, N), dim3(256), 0, st, dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
                                                                   static_cast<T*>(dz), dz_pitch, workspace, HW, na, nb,
                                                                   slope, tpart);
   else
-    head_bwd_kernel<T, 32, 3, false><<<dim3(bpi, N), 256, 0, st>>>(dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
+    launch_k(head_bwd_kernel<T, 32, 3, false>, dim3(bpi, N), dim3(256), 0, st, dlogits_nchw, static_cast<const T*>(z), z_pitch, w,
                                                                    static_cast<T*>(dz), dz_pitch, workspace, HW, na, nb,
                                                                    slope, nullptr);
   B200_LAUNCH_CHECK("head_bwd_kernel");
-  head_bwd_finalize_kernel<<<1, 1024, 0, st>>>(workspace, bpi * N, K * C, K, dw, db);
+  launch_k(head_bwd_finalize_kernel, dim3(1), dim3(1024), 0, st, workspace, bpi * N, K * C, K, dw, db);
   B200_LAUNCH_CHECK("head_bwd_finalize_kernel");
   return 0;
 }

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256) in_finalize_kernel(const float* __restric
                                                            float* __restrict__ mean, float* __restrict__ rstd,
                                                            float* __restrict__ a, float* __restrict__ b, int C,
                                                            double inv_hw) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ double red[8][32][2];
   const int n = blockIdx.x;
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_kernel(const T* __restr
                                                                  const float* __restrict__ b, float slope,
                                                                  T* __restrict__ z, int64_t zp, int64_t HW,
                                                                  int C, int c8n, int lanes, int64_t chunk) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   // images in REVERSE launch order: the producing conv wrote image N-1 last, so the first blocks find their input in
   // L2; this kernel then leaves image 0 in L2 for the next conv, which starts there
   const int n = gridDim.y - 1 - blockIdx.y;
@@ -173,6 +177,8 @@ struct InBwdK {
 // T1 = sum dz*m, T2 = sum dz*m*(y - mean) over the block's pixels, m = lrelu'(a*y+b).   grid (P, images)
 template <typename T, bool HAS2>
 __global__ void __launch_bounds__(kNormThreads, (HAS2 || sizeof(T) != 2) ? 2 : 3) in_bwd_reduce_kernel(InBwdK<T> K, float* __restrict__ part, int P) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   using Acc = typename AccT<T>::type;
   extern __shared__ __align__(8) unsigned char red_raw[];
   Acc* red = reinterpret_cast<Acc*>(red_raw);  // [lanes][c8n][16]
@@ -257,6 +263,8 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
                                                                const float* __restrict__ drop,
                                                                float* __restrict__ coef, float* __restrict__ imgsum,
                                                                int C, int n0, double inv_hw) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ double red[8][32][2];
   const int n = n0 + blockIdx.x;
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
@@ -314,6 +322,8 @@ __global__ void __launch_bounds__(256) in_bwd_finalize_kernel(const float* __res
 // fixed-order combine across the 8 groups -- the kernel sits between the apply pass and the next data gradient
 __global__ void __launch_bounds__(256) in_bwd_param_kernel(const float* __restrict__ imgsum, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int N, int C) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   __shared__ double red[8][32][2];
   const int cl = threadIdx.x & 31, ng = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -345,6 +355,8 @@ __global__ void __launch_bounds__(256) in_bwd_param_kernel(const float* __restri
 template <typename T, bool HAS2>
 __global__ void __launch_bounds__(kNormThreads, 2) in_bwd_apply_kernel(InBwdK<T> K, const float* __restrict__ coef,
                                                                         T* __restrict__ dy, int64_t dyp) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int n = K.n0 + blockIdx.y;
   const int c0 = (threadIdx.x % K.c8n) << 3;
   const int lane = threadIdx.x / K.c8n;
@@ -417,6 +429,8 @@ __global__ void __launch_bounds__(256, 2) in_bwd_fused_kernel(InBwdK<__nv_bfloat
                                                                const float* __restrict__ drop,
                                                                __nv_bfloat16* __restrict__ dy, int64_t dyp,
                                                                float* __restrict__ imgsum, int cg8, double inv_hw) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   using T = __nv_bfloat16;
   extern __shared__ __align__(16) unsigned char fz_raw[];
   const int HW = static_cast<int>(K.HW);
@@ -567,7 +581,7 @@ extern "C" int b200unet_in_finalize(const float* stats, int P, const float* gamm
                                     int N, int C, int64_t HW, void* stream) {
   B200_CHECK_ARG(stats && gamma && beta && mean && rstd && a && b, "in_finalize: null pointer");
   B200_CHECK_ARG(P > 0 && HW > 0 && N > 0 && C > 0, "in_finalize: bad sizes");
-  in_finalize_kernel<<<dim3(N, ceil_div(C, 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(in_finalize_kernel, dim3(N, ceil_div(C, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       stats, P, gamma, beta, drop_scale, eps, mean, rstd, a, b, C, 1.0 / static_cast<double>(HW));
   B200_LAUNCH_CHECK("in_finalize_kernel");
   return 0;
@@ -581,7 +595,7 @@ static int in_apply_impl(const void* y, int64_t y_pitch, const float* a, const f
   if (rc) return rc;
   const PixelMap m = make_map(C);
   const int64_t chunk = pixels_per_block(HW, N, m, 4 * blocks_per_sm());
-  in_apply_kernel<T><<<dim3((unsigned)ceil_div64(HW, chunk), N), m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(in_apply_kernel<T>, dim3((unsigned)ceil_div64(HW, chunk), N), dim3(m.threads), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const T*>(y), y_pitch, a, b, slope, static_cast<T*>(z), z_pitch, HW, C, m.c8n, m.lanes, chunk);
   B200_LAUNCH_CHECK("in_apply_kernel");
   return 0;
@@ -674,11 +688,11 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
         attr_set[has2 ? 1 : 0] = true;
       }
       K.n0 = 0;
-      kern<<<dim3(C / cg, N), 256, smem, st>>>(K, A->gamma, A->rstd, A->drop_scale, static_cast<T*>(A->dy), A->dy_pitch,
+      launch_k(kern, dim3(C / cg, N), dim3(256), smem, st, K, A->gamma, A->rstd, A->drop_scale, static_cast<T*>(A->dy), A->dy_pitch,
                                               imgsum, cg / 8, inv_hw);
       B200_LAUNCH_CHECK("in_bwd_fused_kernel");
       if (!A->defer_params) {
-        in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+        launch_k(in_bwd_param_kernel, dim3(ceil_div(C, 32)), dim3(256), 0, st, imgsum, A->dgamma, A->dbeta, N, C);
         B200_LAUNCH_CHECK("in_bwd_param_kernel");
       }
       return 0;
@@ -691,29 +705,29 @@ static int in_backward_impl(const b200unet_in_bwd_args* A, void* stream) {
     const int nn = (N - n0 < ipc) ? N - n0 : ipc;
     K.n0 = n0;
     if (ext) {
-      in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(A->ext_part, A->ext_P, has2 ? A->ext_part2 : nullptr,
+      launch_k(in_bwd_finalize_kernel, dim3(nn, ceil_div(C, 32)), dim3(256), 0, st, A->ext_part, A->ext_P, has2 ? A->ext_part2 : nullptr,
                                                                        A->ext_P2, A->mean, A->gamma, A->rstd, A->drop_scale,
                                                                        coef, imgsum, C, n0, inv_hw);
     } else {
-      if (has2) in_bwd_reduce_kernel<T, true><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
-      else in_bwd_reduce_kernel<T, false><<<dim3(P, nn), m.threads, red_bytes, st>>>(K, part, P);
+      if (has2) launch_k(in_bwd_reduce_kernel<T, true>, dim3(P, nn), dim3(m.threads), red_bytes, st, K, part, P);
+      else launch_k(in_bwd_reduce_kernel<T, false>, dim3(P, nn), dim3(m.threads), red_bytes, st, K, part, P);
       B200_LAUNCH_CHECK("in_bwd_reduce_kernel");
-      in_bwd_finalize_kernel<<<dim3(nn, ceil_div(C, 32)), 256, 0, st>>>(part, P, nullptr, 0, nullptr, A->gamma, A->rstd,
+      launch_k(in_bwd_finalize_kernel, dim3(nn, ceil_div(C, 32)), dim3(256), 0, st, part, P, nullptr, 0, nullptr, A->gamma, A->rstd,
                                                                        A->drop_scale, coef, imgsum, C, n0, inv_hw);
     }
     B200_LAUNCH_CHECK("in_bwd_finalize_kernel");
     K.chunk = chunk_apply;
     if (has2)
-      in_bwd_apply_kernel<T, true><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+      launch_k(in_bwd_apply_kernel<T, true>, dim3((unsigned)ceil_div64(HW, chunk_apply), nn), dim3(m.threads), 0, st, 
           K, coef, static_cast<T*>(A->dy), A->dy_pitch);
     else
-      in_bwd_apply_kernel<T, false><<<dim3((unsigned)ceil_div64(HW, chunk_apply), nn), m.threads, 0, st>>>(
+      launch_k(in_bwd_apply_kernel<T, false>, dim3((unsigned)ceil_div64(HW, chunk_apply), nn), dim3(m.threads), 0, st, 
           K, coef, static_cast<T*>(A->dy), A->dy_pitch);
     K.chunk = chunk;
     B200_LAUNCH_CHECK("in_bwd_apply_kernel");
   }
   if (!A->defer_params) {
-    in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, st>>>(imgsum, A->dgamma, A->dbeta, N, C);
+    launch_k(in_bwd_param_kernel, dim3(ceil_div(C, 32)), dim3(256), 0, st, imgsum, A->dgamma, A->dbeta, N, C);
     B200_LAUNCH_CHECK("in_bwd_param_kernel");
   }
   return 0;
@@ -727,7 +741,7 @@ extern "C" int b200unet_in_bwd_params(const float* workspace, int N, int64_t HW,
   B200_CHECK_ARG(workspace && dgamma && dbeta && N > 0 && HW > 0 && C > 0, "in_bwd_params: null pointer or bad sizes");
   (void)HW;
   const float* imgsum = workspace;  // first block of the workspace layout (in_backward_impl)
-  in_bwd_param_kernel<<<ceil_div(C, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(imgsum, dgamma, dbeta, N, C);
+  launch_k(in_bwd_param_kernel, dim3(ceil_div(C, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), imgsum, dgamma, dbeta, N, C);
   B200_LAUNCH_CHECK("in_bwd_param_kernel");
   return 0;
 }

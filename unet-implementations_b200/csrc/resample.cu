@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256, 2) upsample2x_fwd_kernel(const T* __restr
                                                                  T* __restrict__ out, int64_t op, int H, int W,
                                                                  int c8n, int c8shift, const float* __restrict__ na,
                                                                  const float* __restrict__ nb, float slope) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int iw = t >> c8shift;  // c8n is a power of two on this path
   if (iw >= W) return;
@@ -108,6 +110,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dout, int64_t dp,
                                                               T* __restrict__ dx, int64_t xp, int H, int W,
                                                               int c8n, int c8shift) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int iw = t >> c8shift;
   if (iw >= W) return;
@@ -208,6 +212,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int64
 // One thread per pixel: C coalesced plane reads, one 64-byte row written.
 __global__ void __launch_bounds__(256) image_to_nhwc32_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                int C, int64_t HW) {
+  pdl_launch_dependents();  // PDL (common.cuh): the next kernel may get resident; wait for the previous one
+  pdl_wait();
   const int n = blockIdx.y;
   const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (p >= HW) return;
@@ -241,11 +247,10 @@ static int upsample_fwd_impl(const void* x, int64_t x_pitch, void* out, int64_t 
   B200_CHECK_ARG(sh >= 0, "upsample2x_fwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_fwd: H and N must fit the grid");
   const dim3 block(256);
-#define B200_UP_LAUNCH(RR)                                                                                          \
-  upsample2x_fwd_kernel<T, RR><<<dim3(ceil_div(W * c8n, 256), ceil_div(H, RR), N), block, 0,                        \
-                                 static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(x), x_pitch,            \
-                                                                      static_cast<T*>(out), out_pitch, H, W, c8n,   \
-                                                                      sh, na, nb, slope)
+#define B200_UP_LAUNCH(RR)                                                                                             \
+  launch_k(upsample2x_fwd_kernel<T, RR>, dim3(ceil_div(W * c8n, 256), ceil_div(H, RR), N), block, 0,                     \
+           static_cast<cudaStream_t>(stream), static_cast<const T*>(x), x_pitch, static_cast<T*>(out), out_pitch, H, W,  \
+           c8n, sh, na, nb, slope)
   // 8 rows per thread measured best at 64^2 .. 256^2 inputs (4: -6 %, 16: -1 %); the small levels need the blocks
   if (H >= 64) B200_UP_LAUNCH(8);
   else B200_UP_LAUNCH(2);
@@ -262,7 +267,7 @@ static int upsample_bwd_impl(const void* dout, int64_t dout_pitch, void* dx, int
   const int c8n = C / 8, sh = ilog2_exact(c8n);
   B200_CHECK_ARG(sh >= 0, "upsample2x_bwd: C/8 = %d must be a power of two", c8n);
   B200_CHECK_ARG(H <= 65535 && N <= 65535, "upsample2x_bwd: H and N must fit the grid");
-  upsample2x_bwd_kernel<T><<<dim3(ceil_div(W * c8n, 256), ceil_div(H, kUpRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(upsample2x_bwd_kernel<T>, dim3(ceil_div(W * c8n, 256), ceil_div(H, kUpRows), N), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const T*>(dout), dout_pitch, static_cast<T*>(dx), dx_pitch, H, W, c8n, sh);
   B200_LAUNCH_CHECK("upsample2x_bwd_kernel");
   return 0;
@@ -328,7 +333,7 @@ extern "C" int b200unet_nhwc_bf16_to_nchw_f32(const void* src, int64_t src_pitch
 extern "C" int b200unet_image_to_nhwc32_bf16(const float* src, void* dst, int N, int C, int64_t HW, void* stream) {
   B200_CHECK_ARG(src && dst, "image_to_nhwc32_bf16: null pointer");
   B200_CHECK_ARG(C >= 1 && C <= 8 && N <= 65535, "image_to_nhwc32_bf16: C must be in [1,8]");
-  image_to_nhwc32_kernel<<<dim3((unsigned)ceil_div64(HW, 256), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(image_to_nhwc32_kernel, dim3((unsigned)ceil_div64(HW, 256), N), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       src, static_cast<__nv_bfloat16*>(dst), C, HW);
   B200_LAUNCH_CHECK("image_to_nhwc32_kernel");
   return 0;
