@@ -182,7 +182,8 @@ def oracle_step_fn(workload, batch, size, device="cpu", autocast=False):
     x, target = O.synthetic_batch(batch, size, seed=0)
     x, target = x.to(device), target.to(device)
     g = torch.Generator().manual_seed(5)
-    clip = torch.randn(batch, 512, size >> 5, size >> 5, generator=g).to(device) if workload == "clip" else None
+    clip = (torch.randn(batch, 512, 1, 1, generator=g).expand(-1, -1, size >> 5, size >> 5).contiguous().to(device)
+            if workload == "clip" else None)
     recon_target = torch.rand(batch, 3, size, size, generator=g).to(device) if workload == "ae" else None
 
     def step():
@@ -284,7 +285,7 @@ def run_torch_gpu(args, rank, world):
 class Workload:
     """Model + loss + synthetic batches of one BASELINE.json configuration, behind the modules' public API."""
 
-    def __init__(self, name, B, S, dev, rank):
+    def __init__(self, name, B, S, dev, rank, dense_clip=False):
         import torch
 
         from unet_implementations_b200 import data
@@ -304,15 +305,22 @@ class Workload:
             self.resident["target"] = torch.rand(B, 3, S, S, generator=g).to(dev)
         else:
             self.resident["mask"] = mask.to(dev)
-        if name == "clip":  # stands in for ClipPatchExtractor's output (CLIP_UNet/models/unet.py:581-617); no gradient
-            self.resident["clip"] = torch.randn(B, 512, S >> 5, S >> 5, generator=g).to(dev)
+        if name == "clip":
+            # stands in for ClipPatchExtractor's output (CLIP_UNet/models/unet.py:581-617; frozen ViT, no gradient): ONE
+            # pooled 512-d embedding per image, expanded over the 16x16 grid by the extractor (unet.py:611-612).  --clip-dense
+            # feeds a dense [B,512,16,16] tensor instead (per-patch features, which the reference's extractor does not make)
+            if dense_clip:
+                self.resident["clip"] = torch.randn(B, 512, S >> 5, S >> 5, generator=g).to(dev)
+            else:
+                self.resident["clip"] = torch.randn(B, 512, 1, 1, generator=g).to(dev)
         # the batch as the dataset stores it (train.py:299-311 before the float conversion): uint8 HWC image, uint8 mask
         self.host = {"image": torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()}
         if name != "ae":
             m8 = mask.to(torch.uint8)
             self.host["mask"] = m8.pin_memory()
         if name == "clip":
-            self.host["clip"] = torch.randn(B, 512, S >> 5, S >> 5, generator=g).pin_memory()
+            self.host["clip"] = (torch.randn(B, 512, S >> 5, S >> 5, generator=g) if dense_clip
+                                 else torch.randn(B, 512, 1, 1, generator=g)).pin_memory()
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
 
     def zero_grad(self):
@@ -324,7 +332,10 @@ class Workload:
         self.zero_grad()
         img = batch["image"]
         if self.name == "clip":
-            out = self.model(img, batch["clip"])
+            clip = batch["clip"]
+            if clip.shape[2] == 1:  # the extractor's expand over the patch grid (a view: spatial strides 0)
+                clip = clip.expand(-1, -1, self.S >> 5, self.S >> 5)
+            out = self.model(img, clip)
         else:
             out = self.model(img)
         if self.name == "ae":
@@ -351,6 +362,8 @@ def main():
     ap.add_argument("--no-profile", action="store_true", help="skip the per-entry-point CUDA-event timing")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer, optimizer and graph legs (ncu captures)")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay leg")
+    ap.add_argument("--clip-dense", action="store_true", help="clip workload: dense per-patch features instead of the "
+                    "reference extractor's pooled embedding expanded over the grid")
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = WORKLOADS[args.workload][1]
@@ -383,7 +396,7 @@ def main():
             dist.barrier()
 
     B, S = args.batch, args.size
-    wl = Workload(args.workload, B, S, dev, rank)
+    wl = Workload(args.workload, B, S, dev, rank, dense_clip=args.clip_dense)
     model = wl.model
     reducer = None
     if world > 1:

@@ -134,3 +134,42 @@ def test_clip_unet_default_model_with_patch_grid():
     with torch.no_grad():
         a, b = model.eval()(x, clip), model(x, clip * 0.5)
     assert not torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_pooled_embedding_broadcast_over_the_grid_cancels_in_the_instance_norm():
+    """What the reference's ClipPatchExtractor actually feeds the model is ONE pooled embedding per image expanded over
+    the 16x16 grid (CLIP_UNet/models/unet.py:611-612).  A plane-constant input of the 1x1 fusion conv adds a plane-
+    constant to its output, which the following InstanceNorm removes: the fused path skips that half of the conv.
+    Against the oracle on the SAME expanded features (fp32 mode, 1e-4): identical outputs, and a clip-half weight
+    gradient that is zero up to the reference's own rounding noise."""
+    from unet_implementations_b200.models.losses import SimpleLoss
+    g = load_golden("small_clip_unet.pt")
+    model = _build(g, "fp32").train()
+    cfg = O.config_of(model)
+    pooled = g["clip"].mean((2, 3), keepdim=True)
+    expanded = pooled.expand(-1, -1, g["clip"].shape[2], g["clip"].shape[3])
+    assert expanded.stride(2) == 0 and expanded.stride(3) == 0
+    torch.manual_seed(g["dropout_seed"])
+    masks = O.draw_dropout_masks(cfg, 2, g["x"])
+    ref = O.training_step(g["state_dict"], g["x"], g["target"], cfg, masks, clip_features=expanded.contiguous())
+    res = {}
+    for mode in (True, False):  # the shortcut, and the full concat path on the same values
+        model.skip_constant_features = mode
+        model.zero_grad(set_to_none=True)
+        model._mask_override = [m.clone() for m in masks]
+        logits = model(g["x"].cuda(), expanded.cuda())
+        loss = SimpleLoss()(logits, g["target"].cuda())
+        loss.backward()
+        res[mode] = (logits.detach().cpu(), loss.item(), {k: p.grad.detach().cpu() for k, p in model.named_parameters()})
+        assert O.rel_l2(res[mode][0], ref["logits"]) <= 1e-4
+        assert abs(res[mode][1] - ref["loss"].item()) <= 1e-4 * abs(ref["loss"].item())
+    gw = res[True][2]["clip_fusion_conv.0.weight"]
+    enc_c = gw.shape[1] - g["clip"].shape[1]
+    assert float(gw[:, enc_c:].abs().max()) == 0.0
+    ref_gw = ref["grads"]["clip_fusion_conv.0.weight"]
+    assert float(ref_gw[:, enc_c:].abs().max()) <= 1e-4 * float(ref_gw[:, :enc_c].abs().max())  # the reference's is noise
+    assert O.rel_l2(gw[:, :enc_c], ref_gw[:, :enc_c]) <= 1e-4
+    for k, v in res[True][2].items():
+        if k != "clip_fusion_conv.0.weight" and not _dead_bias(k, model):
+            assert O.rel_l2(v, ref["grads"][k]) <= 1e-4, k

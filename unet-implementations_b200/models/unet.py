@@ -212,6 +212,8 @@ class UNet(nn.Module):
         self.overlap_wgrad = os.environ.get("B200UNET_OVERLAP", "1") != "0"
         # kernels that write a gradient dz also reduce the norm-backward sums of the unit that consumes it (A/B knob)
         self.producer_sums = os.environ.get("B200UNET_PRODUCER_SUMS", "1") != "0"          # the head backward (a gain)
+        # fusion variant: extra features that are constant over each (sample, channel) plane cancel in the InstanceNorm
+        self.skip_constant_features = True
         self.producer_sums_dgrad = os.environ.get("B200UNET_PRODUCER_SUMS_DGRAD", "0") == "1"  # dgrad epilogues (a loss)
         self._side_streams: Dict[int, torch.cuda.Stream] = {}
         self._pack_cache: Dict[int, Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = {}
@@ -322,20 +324,21 @@ class UNet(nn.Module):
         self._pack_cache[key] = (wd, ws, None, None)
         return ws
 
-    def _packed_1x1(self, conv: nn.Conv2d, need_dgrad: bool, dtype):
+    def _packed_1x1(self, conv: nn.Conv2d, need_dgrad: bool, dtype, cin_used: Optional[int] = None):
         """A 1x1 conv on the 3x3 conv kernels: its weight as the centre tap of a zero 3x3 kernel (the fusion layer is
         2.4 GFLOP per image this way, 0.6 % of the step), packed and cached like _packed."""
         w = conv.weight
+        cin = conv.in_channels if cin_used is None else cin_used  # leading input channels only (constant extra features)
         ext = self._ext(w, dtype)
-        if ext is not None and ext["key"] == "k1":
+        if ext is not None and ext["key"] == "k1" and cin == conv.in_channels:
             return ext["wf"], ext["wd"]
-        key = ("k1", id(w))
+        key = ("k1", id(w), cin)
         hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == w._version and hit[1].device == w.device and hit[3] == w.data_ptr() \
                 and hit[1].dtype == dtype and (hit[2] is not None or not need_dgrad):
             return hit[1], hit[2]
-        w3 = torch.zeros((conv.out_channels, conv.in_channels, 3, 3), dtype=torch.float32, device=w.device)
-        w3[:, :, 1, 1] = w.detach()[:, :, 0, 0]
+        w3 = torch.zeros((conv.out_channels, cin, 3, 3), dtype=torch.float32, device=w.device)
+        w3[:, :, 1, 1] = w.detach()[:, :cin, 0, 0]
         wf, wd = ops.pack_conv_weights(w3, need_dgrad=need_dgrad, dtype=dtype)
         self._pack_cache[key] = (w._version, wf, wd, w.data_ptr())
         return wf, wd
@@ -515,12 +518,22 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
     extra = getattr(model, "_extra_features", None)
     fusion = model._fusion_unit() if extra is not None else None
     catf = None
+    const_extra = False
     if fusion is not None:
         fh, fw = sizes[-1]
-        if extra.shape[2:] != (fh, fw):
-            extra = F.interpolate(extra.float(), size=(fh, fw), mode="bilinear", align_corners=False)  # unet.py:444-451
-        catf = torch.empty((B, fh, fw, feats[-1] + extra.shape[1]), dtype=adt, device=dev)
-        ops.nchw_to_nhwc(extra.detach().float().contiguous(), out=catf[..., feats[-1]:])
+        # A pooled embedding broadcast over the grid -- what the reference's ClipPatchExtractor produces
+        # (`features.view(B, D, 1, 1).expand(-1, -1, 16, 16)`, CLIP_UNet/models/unet.py:611-612: spatial strides 0) -- is
+        # constant over each (sample, channel) plane.  Its half of the 1x1 fusion conv is then a per-(sample, channel)
+        # constant added to the conv output, which the InstanceNorm that follows subtracts again with the plane mean:
+        # like the conv biases it cancels exactly, and its weight gradient is exactly zero.  The fusion
+        # conv then runs over the bottleneck's channels only (half the K, no concat buffer, no feature re-layout).
+        const_extra = model.skip_constant_features and extra.dim() == 4 and (
+            tuple(extra.shape[2:]) == (1, 1) or (extra.stride(2) == 0 and extra.stride(3) == 0))
+        if not const_extra:
+            if extra.shape[2:] != (fh, fw):
+                extra = F.interpolate(extra.float(), size=(fh, fw), mode="bilinear", align_corners=False)  # unet.py:444-451
+            catf = torch.empty((B, fh, fw, feats[-1] + extra.shape[1]), dtype=adt, device=dev)
+            ops.nchw_to_nhwc(extra.detach().float().contiguous(), out=catf[..., feats[-1]:])
         layers = [L for L in layers if L["kind"] == "enc"] + [dict(kind="fusion", stage=0, idx=0, last=True, unit=fusion)] + \
                  [L for L in layers if L["kind"] == "dec"]
 
@@ -567,10 +580,14 @@ def _forward_impl(ctx, model: UNet, x: torch.Tensor, params):
                 rec["stem"] = False
         else:
             if L["kind"] == "fusion":
-                if conv.kernel_size != (1, 1) or conv.in_channels != catf.shape[3]:
+                if conv.kernel_size != (1, 1) or conv.in_channels != feats[-1] + extra.shape[1]:
                     raise NotImplementedError("b200unet: the fusion layer must be a 1x1 conv over cat([bottleneck, features])")
-                cur = catf
-                wf, wd = model._packed_1x1(conv, need_grad, adt)
+                if const_extra:
+                    wf, wd = model._packed_1x1(conv, need_grad, adt, cin_used=feats[-1])
+                    rec["cin_used"] = feats[-1]
+                else:
+                    cur = catf
+                    wf, wd = model._packed_1x1(conv, need_grad, adt)
             else:
                 wf, wd = model._packed(conv, need_grad, adt)
             y, stats = _conv_fwd(cur, wf, stride)
@@ -861,8 +878,14 @@ def _backward_impl(ctx, dlogits):
             else:
                 dx = ops.conv_dgrad(dy, wd, (xin.shape[1], xin.shape[2]), stride, simt=simt)
         if L["kind"] == "fusion":  # 1x1 weight = centre tap of the 3x3 gradient
-            wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2].contiguous(), [xin, dy],
-                        trec)
+            def fusion_dw():
+                g = ops.conv_wgrad(xin, dy, stride, simt=simt)[:, :, 1:2, 1:2]
+                if rec.get("cin_used") is None:
+                    return g.contiguous()
+                full = torch.zeros_like(conv.weight)  # the constant-feature half: exactly zero (cancelled by the norm)
+                full[:, :rec["cin_used"]] = g
+                return full
+            wgrad_async(conv.weight, fusion_dw, [xin, dy], trec)
         else:
             wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt, out=dest(conv.weight)), [xin, dy], trec)
         if trec is not None:
@@ -880,7 +903,7 @@ def _backward_impl(ctx, dlogits):
             if btrace is not None:
                 btrace.append(dict(kind="up", d=d, dout=dx[..., :c_low], dx=dz))
         elif L["kind"] == "fusion":
-            dz = dx[..., :feats[-1]]  # the extra features are inputs: their half of the gradient is dropped
+            dz = dx[..., :feats[-1]]  # the extra features are inputs: their half of the gradient is dropped (if computed)
         else:
             dz = dx
     collect()
