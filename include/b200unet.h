@@ -82,6 +82,12 @@ typedef struct {
   const float* bs_b;
   float bs_slope;
   float* bs_part;
+  /* Optional second output (stride 1): channels [0, dx_split) of the gradient go to dx, channels [dx_split, Cin) to dx2
+   * -- the [upsampled | skip] halves of a decoder concat buffer's gradient (torch.cat backward, unet.py:228) as two
+   * dense tensors instead of two slices of one.  NULL = one output. */
+  void* dx2;
+  int64_t dx2_pitch;
+  int dx_split;
 } b200unet_conv_dgrad_args;
 int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stream);
 int b200unet_conv_dgrad_bwd_slots(int N, int H, int W, int Cin, int Cout, int stride);

@@ -158,7 +158,9 @@ def test_pooled_embedding_broadcast_over_the_grid_cancels_in_the_instance_norm()
         model.skip_constant_features = mode
         model.zero_grad(set_to_none=True)
         model._mask_override = [m.clone() for m in masks]
-        logits = model(g["x"].cuda(), expanded.cuda())
+        feats = pooled.cuda().expand(-1, -1, g["clip"].shape[2], g["clip"].shape[3])  # expanded ON the device (a .cuda() of
+        assert feats.stride(2) == 0                                                    # an expanded tensor materialises it)
+        logits = model(g["x"].cuda(), feats if mode else feats.contiguous())
         loss = SimpleLoss()(logits, g["target"].cuda())
         loss.backward()
         res[mode] = (logits.detach().cpu(), loss.item(), {k: p.grad.detach().cpu() for k, p in model.named_parameters()})

@@ -335,6 +335,21 @@ def test_data_gradient_epilogue_reduces_the_consuming_units_norm_backward_sums(n
     assert O.rel_l2(dg1, dg0) <= 1e-4 and O.rel_l2(db1, db0) <= 1e-4
 
 
+def test_data_gradient_written_as_two_dense_tensors():
+    """The gradient of the level-0 concat buffer ([64 upsampled | 32 skip] channels, torch.cat backward, unet.py:228) as two
+    dense tensors: bit-identical to the two channel slices of the single-tensor data gradient."""
+    from unet_implementations_b200 import ops
+    n, h, w, cin, cout = 2, 24, 40, 96, 32
+    g = torch.Generator().manual_seed(51)
+    dy, _ = rand_act(n, h, w, cout, seed=52)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    _, wd = ops.pack_conv_weights(wt.cuda())
+    dx = ops.conv_dgrad(dy, wd, (h, w), 1)
+    d1, d2 = ops.conv_dgrad_split(dy, wd, (h, w), 64)
+    assert d1.shape == (n, h, w, 64) and d2.shape == (n, h, w, 32) and d1.is_contiguous() and d2.is_contiguous()
+    assert torch.equal(d1, dx[..., :64]) and torch.equal(d2, dx[..., 64:])
+
+
 def _guarded(shape, dtype=torch.bfloat16, guard=4096, fill=3.0):
     """A tensor of `shape` carved out of the middle of a larger allocation whose margins hold a sentinel value."""
     n = 1

@@ -27,7 +27,7 @@ class ConvDgradArgs(Structure):
         ("dy", c_void_p), ("dy_pitch", c_int64), ("wt", c_void_p), ("dx", c_void_p), ("dx_pitch", c_int64),
         ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("stride", c_int),
         ("bs_y", c_void_p), ("bs_y_pitch", c_int64), ("bs_a", c_void_p), ("bs_b", c_void_p), ("bs_slope", c_float),
-        ("bs_part", c_void_p),
+        ("bs_part", c_void_p), ("dx2", c_void_p), ("dx2_pitch", c_int64), ("dx_split", c_int),
     ]
 
 

@@ -62,7 +62,7 @@ struct GConvParams {
 struct GConvMaps {
   CUtensorMap src[kMaxLoads];  // one per patch load (the box height is part of the descriptor)
   CUtensorMap w;
-  CUtensorMap out[4];
+  CUtensorMap out[8];  // one per output channel block when the output is split (parity sub-lattices / two tensors)
 };
 
 // MT = 2: the CTA tile is TWO vertically adjacent 8 x 16 patches (one 18-row TMA patch per column shift, two
@@ -726,7 +726,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
   if (!BK || !BN)
     return set_error(kErrUnsupported, "conv_dgrad: Cin=%d Cout=%d outside the tensor-core envelope", a->Cin, a->Cout);
   B200_CHECK_ARG(a->dx_pitch % 8 == 0 && a->dy_pitch % 8 == 0, "conv_dgrad: pitches must be multiples of 8 elements");
-  if (nconv_supported(a->Cout, a->Cin, a->stride, a->W)) {
+  if (nconv_supported(a->Cout, a->Cin, a->stride, a->W) && !a->dx2) {
     if (a->bs_part) {
       B200_CHECK_ARG(a->bs_y && a->bs_a && a->bs_b, "conv_dgrad: norm-backward sums need y, a and b");
       BwdSums bs{static_cast<const __nv_bfloat16*>(a->bs_y), a->bs_y_pitch, a->bs_a, a->bs_b, a->bs_slope};
@@ -764,9 +764,30 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
     for (int kw = 0; kw < 3; ++kw)
       for (int kh = 2; kh >= 0; --kh) taps[n++] = TapSpec{0, 1 - kh, 1 - kw, (kh * 3 + kw) * a->Cout};  // row offsets 0,1,2
     if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
+    if (a->dx2) {
+      // Two output tensors: channels [0, dx_split) go to dx, the rest to dx2 -- the two halves of the gradient of a
+      // decoder concat buffer ([upsampled | skip], unet.py:228) written as two DENSE tensors.  At the 512^2 level the
+      // concat gradient has a 192-byte pixel pitch: its 128-byte and 64-byte halves straddle / half-fill 128-byte
+      // lines, and each consumer (upsample backward; the two passes of the encoder's norm backward) paid up to 2x the
+      // DRAM bytes it used (ncu, profiles/r2_step_launches.md: 2.15 GB read for a 1.6 GB pass).
+      B200_CHECK_ARG(a->dx_split > 0 && a->dx_split < a->Cin && a->dx_split % OC == 0 && a->Cin / OC <= 8 && BN == a->Cin,
+                     "conv_dgrad: dx_split=%d must be a multiple of %d inside (0, %d), one N tile", a->dx_split, OC, a->Cin);
+      B200_CHECK_ARG(a->dx2_pitch % 8 == 0, "conv_dgrad: dx2 pitch must be a multiple of 8 elements");
+      p.out_split = OC;
+      const __nv_bfloat16* dx2 = static_cast<const __nv_bfloat16*>(a->dx2);
+      for (int j = 0; j < a->Cin / OC; ++j) {
+        const int c0 = j * OC;
+        const bool first = c0 < a->dx_split;
+        if ((rc = make_act_map(&maps.out[j], first ? dx + c0 : dx2 + (c0 - a->dx_split), first ? a->dx_pitch : a->dx2_pitch,
+                               a->N, a->H, a->W, OC, 1, 1, 0, 0, OC, kTW, kTH)))
+          return rc;
+      }
+      return dispatch_gconv(maps, p, BK, BN, st);
+    }
     if ((rc = make_act_map(&maps.out[0], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, kTW, kTH))) return rc;
     return dispatch_gconv(maps, p, BK, BN, st);
   }
+  B200_CHECK_ARG(!a->dx2, "conv_dgrad: a split output needs stride 1");
   // stride 2: one launch per parity class (ph,pw) of the input pixel; ih = 2a + ph receives
   //   ph = 0: kh = 1 from oh = a;      ph = 1: kh = 0 from oh = a + 1 and kh = 2 from oh = a   (same along w)
   for (int ph = 0; ph < 2; ++ph)

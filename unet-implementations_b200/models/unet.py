@@ -212,6 +212,7 @@ class UNet(nn.Module):
         self.overlap_wgrad = os.environ.get("B200UNET_OVERLAP", "1") != "0"
         # kernels that write a gradient dz also reduce the norm-backward sums of the unit that consumes it (A/B knob)
         self.producer_sums = os.environ.get("B200UNET_PRODUCER_SUMS", "1") != "0"          # the head backward (a gain)
+        self.split_concat_grad = os.environ.get("B200UNET_SPLIT_DCAT", "1") != "0"  # A/B knob (models/unet.py backward)
         # fusion variant: extra features that are constant over each (sample, channel) plane cancel in the InstanceNorm
         self.skip_constant_features = True
         self.producer_sums_dgrad = os.environ.get("B200UNET_PRODUCER_SUMS_DGRAD", "0") == "1"  # dgrad epilogues (a loss)
@@ -864,8 +865,16 @@ def _backward_impl(ctx, dlogits):
         if not last:
             wd = rec["wd"]
             ws2 = model._packed_s2(conv, wd) if (stride == 2 and not simt and wd.dtype == BF16) else None
+            split_out = None
+            if (L["kind"] == "dec" and L["idx"] == 0 and not simt and stride == 1 and dy.dtype == BF16
+                    and cin == 96 and feats[n - 1 - L["stage"]] == 64 and model.split_concat_grad):
+                # the gradient of a concat buffer whose pixel pitch is not a multiple of 128 bytes (level 0: 64 + 32
+                # channels = 192 B) goes to two dense tensors: its consumers then read whole lines (see conv_dgrad_split)
+                split_out = feats[n - 1 - L["stage"]]
             if ws2 is not None:
                 dx = ops.conv_dgrad_s2(dy, ws2, (xin.shape[1], xin.shape[2]))
+            elif split_out is not None:
+                dx = ops.conv_dgrad_split(dy, wd, (xin.shape[1], xin.shape[2]), split_out)
             elif model.producer_sums_dgrad and L["idx"] > 0 and L["kind"] != "fusion" and li - 1 >= first_needed \
                     and saved[li - 1]["y"] is not None:
                 # dx is the dz of the previous unit of the same block (no skip operand): the data gradient's epilogue can
@@ -889,19 +898,20 @@ def _backward_impl(ctx, dlogits):
         else:
             wgrad_async(conv.weight, lambda: ops.conv_wgrad(xin, dy, stride, simt=simt, out=dest(conv.weight)), [xin, dy], trec)
         if trec is not None:
-            trec["dx"] = dx
+            trec["dx"] = torch.cat(dx, dim=-1) if isinstance(dx, tuple) else dx
         if conv._backward_hooks:
-            _fire_backward_hooks(conv, dx, dy)
+            _fire_backward_hooks(conv, torch.cat(dx, dim=-1) if isinstance(dx, tuple) else dx, dy)
         if last:
             break
         rec["xin"] = None
         if L["kind"] == "dec" and L["idx"] == 0:
             d = n - 2 - L["stage"]
             c_low = feats[d + 1]
-            dskip[d] = dx[..., c_low:]
-            dz = ops.upsample2x_backward(dx[..., :c_low])
+            dup, dsk = dx if isinstance(dx, tuple) else (dx[..., :c_low], dx[..., c_low:])
+            dskip[d] = dsk
+            dz = ops.upsample2x_backward(dup)
             if btrace is not None:
-                btrace.append(dict(kind="up", d=d, dout=dx[..., :c_low], dx=dz))
+                btrace.append(dict(kind="up", d=d, dout=dup, dx=dz))
         elif L["kind"] == "fusion":
             dz = dx[..., :feats[-1]]  # the extra features are inputs: their half of the gradient is dropped (if computed)
         else:

@@ -124,6 +124,21 @@ def conv_dgrad_s2(dy, w_stacked, in_hw, out=None):
     return dx
 
 
+def conv_dgrad_split(dy, w_dgrad, in_hw, split):
+    """Stride-1 data gradient written as TWO dense tensors: channels [0, split) and [split, Cin) -- the gradient of a
+    decoder concat buffer without the concat (each half is consumed by a different kernel)."""
+    n, oh, ow, cout = dy.shape
+    cin = w_dgrad.shape[0]
+    h, w = in_hw
+    assert w_dgrad.shape == (cin, 3, 3, cout) and w_dgrad.dtype == dy.dtype == BF16 and (oh, ow) == (h, w) and 0 < split < cin
+    d1 = torch.empty((n, h, w, split), dtype=BF16, device=dy.device)
+    d2 = torch.empty((n, h, w, cin - split), dtype=BF16, device=dy.device)
+    a = ConvDgradArgs(_p(dy), pitch_of(dy), _p(w_dgrad), _p(d1), pitch_of(d1), n, h, w, cin, cout, 1)
+    a.dx2, a.dx2_pitch, a.dx_split = d2.data_ptr(), pitch_of(d2), split
+    _lib.call("b200unet_conv_dgrad", ctypes.byref(a), _stream())
+    return d1, d2
+
+
 def conv_dgrad(dy, w_dgrad, in_hw, stride=1, out=None, simt=False, bwd_sums=None):
     """Gradient wrt the conv input.  dy [N,OH,OW,Cout]; w_dgrad [Cin,3,3,Cout]; returns dx [N,H,W,Cin] bf16.
     bwd_sums = (y, a, b, slope) of the unit whose output feeds this conv (dx is its dz): if the kernel that runs this
