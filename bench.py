@@ -629,7 +629,8 @@ def main():
     run_step = step
     if not args.no_e2e:
         from unet_implementations_b200.optim import FusedSGD
-        opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4, model=model)
+        opt = FusedSGD(model.parameters(), lr=1e-6, momentum=0.99, nesterov=True, weight_decay=1e-4, model=model,
+                       capturable=True)
 
         def sgd_step():
             step()
@@ -639,7 +640,20 @@ def main():
             sgd_step()
         l0 = _lib.call("b200unet_launch_count")
         ms_sgd = timed(sgd_step, args.steps) / args.steps
+        ms_sgd_graph = None
+        if world == 1 and not args.no_graph:
+            try:  # the WHOLE training step (forward + loss + backward + optimizer) as one graph
+                from unet_implementations_b200.graph import GraphedStep
+                gso = GraphedStep(sgd_step, warmup=1, optimizer=opt)
+                for _ in range(3):
+                    gso.replay()
+                ms_sgd_graph = timed(gso.replay, args.steps) / args.steps
+                del gso
+            except Exception as e:  # noqa: BLE001
+                graph_err = repr(e)[:300]
+                torch.cuda.synchronize()
         with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT, "step_form": "eager",
+                    "graph_replay_ms_per_step": ms_sgd_graph,
                     "gpu_launches_per_step": (_lib.call("b200unet_launch_count") - l0) / args.steps,
                     "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4, model=model): one launch over the "
                                  "flat master/grad/momentum buffers, emits the bf16 weight packs (weights change every step; "

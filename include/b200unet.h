@@ -352,7 +352,8 @@ typedef struct {
 int b200unet_sgd_flat_block_elems(void);
 int b200unet_sgd_flat_step(const b200unet_flat_tensor* table_dev, int count, int total_blocks, float* master,
                            const float* grad, float* momentum_buf, float lr, float momentum, float weight_decay,
-                           int nesterov, float grad_scale, void* stream);
+                           int nesterov, float grad_scale, const float* lr_dev /* device scalar overriding lr, or NULL */,
+                           void* stream);
 int b200unet_argmax_counts(const float* logits_nchw, const int64_t* target, int ignore_index, int64_t* pred_or_null,
                            int64_t* counts9, int N, int64_t HW, void* stream);
 

@@ -22,10 +22,13 @@ def _worker(rank, world, port, q):
                  decoder_dropout_rates=[0.2, 0])
     ddp.broadcast_parameters(model)
     w0 = model.segmentation_output.weight.detach().clone()
-    red = ddp.BucketedGradAllReduce(model, bucket_bytes=64 << 10, device=torch.device("cpu"))
+    red = ddp.BucketedGradAllReduce(model, bucket_bytes=64 << 10, device=torch.device("cpu"), tail_bytes=16 << 10)
     order = ddp.backward_param_order(model)
     assert len(order) == len(list(model.parameters())) and len({id(p) for p in order}) == len(order)
     assert len(red.buckets) >= 3
+    # the last bucket (its all-reduce cannot overlap anything) holds only the small gradients produced last
+    assert (red.buckets[-1][1] - red.buckets[-1][0]) * 4 <= 16 << 10 and red.buckets[-1][1] == red.numel
+    assert all(a[1] == b[0] for a, b in zip(red.buckets, red.buckets[1:])) and red.buckets[0][0] == 0
     views = {}
     g = torch.Generator().manual_seed(7)  # same base on both ranks; rank enters as a known offset
     expect = {}
@@ -54,6 +57,25 @@ def _worker(rank, world, port, q):
         views[id(p)] = red(p, vals[id(p)] * (rank + 1))     # mean over ranks = vals * (1 + 2) / 2
     red.finish()
     ok &= all(torch.allclose(views[id(p)], vals[id(p)] * (world + 1) / 2.0, atol=1e-5) for p in order)
+    # third step: one parameter gets NO gradient (a frozen layer, an unused fusion conv): its bucket never fills up, but
+    # finish() must still reduce the gradients that did arrive in it
+    skipped = order[len(order) // 2]
+    g3 = torch.Generator().manual_seed(9)
+    vals3 = {id(p): torch.randn(p.shape, generator=g3) for p in order}
+    for p in order:
+        if p is not skipped:
+            views[id(p)] = red(p, vals3[id(p)] * (rank + 1))
+    red.finish()
+    ok &= all(torch.allclose(views[id(p)], vals3[id(p)] * (world + 1) / 2.0, atol=1e-5) for p in order if p is not skipped)
+    # a gradient that autograd adopted as p.grad and the caller kept must not be overwritten in place
+    w = order[0]
+    w.grad = red.dest(w)
+    try:
+        red.dest(w)
+        ok = False
+    except RuntimeError:
+        pass
+    w.grad = None
     # bytes, not a tensor: a tensor travels as a shared-memory handle that dies with this process if the parent is slow
     q.put((rank, bool(ok), w0.numpy().tobytes()))
     dist.destroy_process_group()

@@ -128,7 +128,7 @@ SIGNATURES = {
     "b200unet_preprocess_u8": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _P]),
     "b200unet_preprocess_u8_nhwc32": (c_int, [_P, _P, _P, _P, _I, _L, _P]),
     "b200unet_sgd_flat_block_elems": (c_int, []),
-    "b200unet_sgd_flat_step": (c_int, [_P, _I, _I, _P, _P, _P, _F, _F, _F, _I, _F, _P]),
+    "b200unet_sgd_flat_step": (c_int, [_P, _I, _I, _P, _P, _P, _F, _F, _F, _I, _F, _P, _P]),
     "b200unet_sgd_max_tensors": (c_int, []),
     "b200unet_sgd_nesterov_step": (c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _P]),
     "b200unet_argmax_counts": (c_int, [_P, _P, _I, _P, _P, _I, _L, _P]),

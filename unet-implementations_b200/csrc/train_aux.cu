@@ -69,8 +69,12 @@ constexpr int kFlatThreads = 256, kFlatPerThread = 4;
 __global__ void __launch_bounds__(kFlatThreads) sgd_flat_kernel(const b200unet_flat_tensor* __restrict__ T, int count,
                                                                  float* __restrict__ master,
                                                                  const float* __restrict__ grad,
-                                                                 float* __restrict__ mom, float lr, float momentum,
-                                                                 float wd, int nesterov, float grad_scale) {
+                                                                 float* __restrict__ mom, float lr_arg, float momentum,
+                                                                 float wd, int nesterov, float grad_scale,
+                                                                 const float* __restrict__ lr_dev) {
+  // the learning rate as a device scalar (when given) keeps a CUDA graph of the whole training step valid across
+  // LambdaLR updates (train.py:454-477): the host rewrites one float instead of re-capturing
+  const float lr = lr_dev ? __ldg(lr_dev) : lr_arg;
   int lo = 0, hi = count;
   const int b = blockIdx.x;
   while (hi - lo > 1) {
@@ -275,11 +279,12 @@ extern "C" int b200unet_sgd_flat_block_elems(void) { return kFlatThreads * kFlat
 
 extern "C" int b200unet_sgd_flat_step(const b200unet_flat_tensor* table_dev, int count, int total_blocks, float* master,
                                       const float* grad, float* momentum_buf, float lr, float momentum,
-                                      float weight_decay, int nesterov, float grad_scale, void* stream) {
+                                      float weight_decay, int nesterov, float grad_scale, const float* lr_dev,
+                                      void* stream) {
   B200_CHECK_ARG(table_dev && master && grad && count > 0 && total_blocks > 0, "sgd_flat_step: null pointer or empty table");
   B200_CHECK_ARG(momentum == 0.f || momentum_buf, "sgd_flat_step: momentum buffer required");
   sgd_flat_kernel<<<total_blocks, kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      table_dev, count, master, grad, momentum_buf, lr, momentum, weight_decay, nesterov, grad_scale);
+      table_dev, count, master, grad, momentum_buf, lr, momentum, weight_decay, nesterov, grad_scale, lr_dev);
   B200_LAUNCH_CHECK("sgd_flat_kernel");
   return 0;
 }

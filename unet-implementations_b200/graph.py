@@ -11,8 +11,9 @@ What is captured: every kernel of libb200unet.so on the capture stream, the side
 (forked and joined inside the capture), the dropout draws (torch's graph-safe Philox offsets: every replay draws new
 masks) and the allocations of the step (a private pool: replays reuse the same addresses, which is also why the TMA
 descriptors baked into the kernel parameters stay valid).  The reference has no counterpart (its loop is eager,
-Our_UNet/src/train.py:630-670); the optimizer step is left outside the graph because its learning rate is a kernel
-argument that LambdaLR changes every epoch (train.py:454-477).
+Our_UNet/src/train.py:630-670).  The optimizer step can be part of the graph: `FusedSGD(..., model=model,
+capturable=True)` reads its learning rate from a device scalar, which replay() refreshes from `param_groups` -- what
+LambdaLR changes every epoch (train.py:454-477) -- so the schedule works without re-capturing.
 """
 from __future__ import annotations
 
@@ -22,9 +23,15 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn: Callable[[], torch.Tensor], warmup: int = 2):
+    """step_fn: zero_grad(set_to_none=True) -> forward -> loss -> backward [-> optimizer.step()], returning the loss.
+    optimizer: a `FusedSGD(..., model=model, capturable=True)` whose step() is INSIDE step_fn -- the whole training step
+    then replays as one graph; its learning rate lives in a device scalar that replay() refreshes from param_groups
+    (what LambdaLR updates), so the schedule keeps working without re-capturing."""
+
+    def __init__(self, step_fn: Callable[[], torch.Tensor], warmup: int = 2, optimizer=None):
         if not torch.cuda.is_available():
             raise RuntimeError("b200unet: GraphedStep needs a CUDA device; there is no CPU path")
+        self.optimizer = optimizer
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -48,5 +55,7 @@ class GraphedStep:
             pass
 
     def replay(self) -> torch.Tensor:
+        if self.optimizer is not None and hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
         self.graph.replay()
         return self.loss

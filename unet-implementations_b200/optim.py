@@ -39,7 +39,7 @@ def _bump_versions(params) -> None:
 
 class FusedSGD(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, model=None,
-                 grad_scale: float = 1.0):
+                 grad_scale: float = 1.0, capturable: bool = False):
         if dampening != 0.0:
             raise ValueError("FusedSGD: dampening is not supported (the trainer uses 0)")
         if nesterov and momentum <= 0:
@@ -47,6 +47,11 @@ class FusedSGD(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
                                       nesterov=nesterov))
         self.grad_scale = float(grad_scale)  # multiplies every gradient inside the flat step (e.g. 1 / loss scale)
+        # capturable (flat mode): the learning rate is read from a device scalar, so that `step()` can sit inside a CUDA
+        # graph (graph.GraphedStep(..., optimizer=opt)); `sync_lr()` copies param_groups[0]["lr"] there before a replay
+        self.capturable = bool(capturable)
+        self._lr_dev: Optional[torch.Tensor] = None
+        self._lr_host: Optional[torch.Tensor] = None
         self._flat: Optional[_FlatState] = None
         if model is not None:
             if len(self.param_groups) != 1:
@@ -96,18 +101,43 @@ class FusedSGD(torch.optim.Optimizer):
                 _bump_versions(sel)
         return loss
 
+    def sync_lr(self):
+        """capturable mode: copy the current learning rate (what LambdaLR wrote into param_groups) to the device scalar
+        the captured optimizer kernel reads.  Called by step() when eager, and by GraphedStep.replay() before a replay."""
+        if not self.capturable or self._flat is None:
+            return
+        dev = self._flat.master.device
+        if self._lr_dev is None:
+            self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self._lr_last = None
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_last:
+            torch.cuda.current_stream().synchronize()  # the pinned scalar may still be in flight from the last change
+            self._lr_host[0] = lr
+            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            self._lr_last = lr
+
     def _flat_step(self):
         group = self.param_groups[0]
         fs = self._flat
         mom = float(group["momentum"])
-        fs.sync(self.state, mom != 0)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            fs.sync(self.state, mom != 0)
+            self.sync_lr()
+        elif not self.capturable or self._lr_dev is None or any(f < 0 or (f & 2) for f in fs.flags):
+            raise RuntimeError("FusedSGD: capture step() with capturable=True and after two eager steps (the first one "
+                               "initialises the momentum buffers, the second uploads the steady-state tensor table)")
         with torch.cuda.device(fs.master.device):
             _lib.call("b200unet_sgd_flat_step", ctypes.c_void_p(fs.table_dev.data_ptr()), fs.count, fs.total_blocks,
                       ctypes.c_void_p(fs.master.data_ptr()), ctypes.c_void_p(fs.sink.flat.data_ptr()),
                       ctypes.c_void_p(fs.momentum.data_ptr()) if mom != 0 else None, float(group["lr"]), mom,
                       float(group["weight_decay"]), int(bool(group["nesterov"])), float(self.grad_scale),
+                      ctypes.c_void_p(self._lr_dev.data_ptr()) if self._lr_dev is not None else None,
                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        fs.after_step(self.state, mom != 0)
+        if not capturing:
+            fs.after_step(self.state, mom != 0)
 
 
 class _FlatState:
