@@ -640,6 +640,7 @@ def main():
             sgd_step()
         l0 = _lib.call("b200unet_launch_count")
         ms_sgd = timed(sgd_step, args.steps) / args.steps
+        launches_sgd = (_lib.call("b200unet_launch_count") - l0) / args.steps
         ms_sgd_graph = None
         if world == 1 and not args.no_graph:
             try:  # the WHOLE training step (forward + loss + backward + optimizer) as one graph
@@ -654,7 +655,7 @@ def main():
                 torch.cuda.synchronize()
         with_sgd = {"ms_per_step": ms_sgd, "value": world * B / (ms_sgd * 1e-3), "unit": UNIT, "step_form": "eager",
                     "graph_replay_ms_per_step": ms_sgd_graph,
-                    "gpu_launches_per_step": (_lib.call("b200unet_launch_count") - l0) / args.steps,
+                    "gpu_launches_per_step": launches_sgd,
                     "optimizer": "FusedSGD(momentum=0.99, nesterov=True, weight_decay=1e-4, model=model): one launch over the "
                                  "flat master/grad/momentum buffers, emits the bf16 weight packs (weights change every step; "
                                  "no pack kernel runs)"}

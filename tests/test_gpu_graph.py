@@ -33,9 +33,8 @@ def test_replay_of_forward_loss_backward_is_bit_identical_to_the_eager_step():
         loss.backward()
         return loss
 
-    ref = step()
-    ref_loss = ref.detach().clone()
-    ref_grads = [p.grad.clone() for p in model.parameters()]
+    ref_loss = step().detach().clone()  # (keeping the loss itself would keep the eager step's autograd graph -- and its
+    ref_grads = [p.grad.clone() for p in model.parameters()]  # default-stream AccumulateGrad nodes -- alive into the capture)
     gs = GraphedStep(step)
     out = gs.replay()
     torch.cuda.synchronize()

@@ -43,6 +43,7 @@ DEFAULT_NCCL_CTAS = 16
 def nccl_options(max_ctas: int = DEFAULT_NCCL_CTAS):
     """ProcessGroupNCCL options that cap the communicator at `max_ctas` CTAs (ncclConfig.maxCTAs)."""
     opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True  # the few NCCL CTAs go first when a persistent conv kernel's CTAs retire
     try:
         opts.config.max_ctas = int(max_ctas)
         opts.config.min_ctas = 1

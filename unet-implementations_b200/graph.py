@@ -7,6 +7,9 @@ capturing forward + loss + backward once and replaying the graph removes the hos
     gs = GraphedStep(lambda: step_fn(static_batch))   # step_fn: zero_grad(set_to_none) -> model -> loss -> backward
     loss = gs.replay()                                # same static inputs; refresh them with .copy_() between replays
 
+Do not keep the loss tensor (or anything else that holds the autograd graph) of an EAGER step alive across the capture:
+its AccumulateGrad nodes belong to the stream that step ran on, and torch would synchronise the capture with it.
+
 What is captured: every kernel of libb200unet.so on the capture stream, the side stream of the weight gradients
 (forked and joined inside the capture), the dropout draws (torch's graph-safe Philox offsets: every replay draws new
 masks) and the allocations of the step (a private pool: replays reuse the same addresses, which is also why the TMA
