@@ -418,18 +418,18 @@ def main():
         sampler.start()
     # untimed pre-steps: the step runs at the 1 kW power cap and the SM clock it sustains drifts for the first second;
     # all timed regions below then see the same steady state (these steps are not counted in `warmup`)
-    presteps = 30
+    presteps = 30 if world == 1 else 60  # (8 GPUs: the first 30 steps after start-up still ran 1.5 % slower)
     for _ in range(presteps):
         step()
     torch.cuda.synchronize()
 
     # ---- the production form of the step: forward + loss + backward captured ONCE into a CUDA graph and replayed
     # (unet_implementations_b200.graph.GraphedStep; SURVEY.md 8d "CUDA events around a CUDA-graph-replayed step").  The
-    # eager form (one Python-enqueued launch per kernel) is timed beside it.  N > 1 replays the graph too when
-    # B200UNET_GRAPH_DDP=1 (NCCL all-reduces inside the capture); otherwise data-parallel runs stay eager.
+    # eager form (one Python-enqueued launch per kernel) is timed beside it.  N > 1 replays the graph too, the bucketed
+    # NCCL all-reduces inside the capture (measured at 2 and 8 GPUs; B200UNET_GRAPH_DDP=0 keeps those runs eager).
     gs = None
     graph_err = None
-    if not args.no_graph and (world == 1 or os.environ.get("B200UNET_GRAPH_DDP", "0") == "1"):
+    if not args.no_graph and (world == 1 or os.environ.get("B200UNET_GRAPH_DDP", "1") == "1"):
         try:
             from unet_implementations_b200.graph import GraphedStep
             gs = GraphedStep(step, warmup=2)
@@ -747,7 +747,7 @@ def main():
                                          "their cached bf16 packs are reused (no per-step repack there)",
                        "step_form": ("value: CUDA-graph replay of forward + loss + backward (graph.GraphedStep), eager form in "
                                      "`eager`" if eager_leg is not None else "eager (one host-enqueued launch per kernel)"),
-                       "presteps": "30 untimed steps after the warm-up (power-cap steady state)",
+                       "presteps": f"{presteps} untimed steps after the warm-up (power-cap steady state)",
                        "overlap": "weight-gradient kernels on a side stream beside the next layer's norm backward"
                                   if model.overlap_wgrad else "none (single stream)",
                        "nccl": (f"communicator capped to {nccl_ctas} CTAs; conv grids sized for "
