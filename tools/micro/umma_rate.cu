@@ -26,7 +26,7 @@ constexpr int STAGES = 4;
 constexpr int BK = 64;
 
 template <int CG, int MN>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long long* cycles, int commit_every) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long long* cycles, int commit_every, int M1) {
   __shared__ __align__(8) uint64_t scratch_bar[4];
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
   const bool leader = (CG == 1) || cluster_ctarank() == 0;
   long long t0 = 0, t1 = 0;
   if (warp == 1 && lane == 0 && leader) {
-    const uint32_t idesc = umma_idesc_bf16(CG == 2 ? 256 : 128, N, MN, MN);
+    const uint32_t idesc = umma_idesc_bf16(CG == 2 ? 256 : M1, N, MN, MN);
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
 
 static int g_commit_every = 0;
 template <int CG, int MN>
-void run(int N, int iters) {
+void run(int N, int iters, int M1 = 128) {
   long long* d;
   int ctas = 148;
   cudaMalloc(&d, ctas * sizeof(long long));
@@ -108,7 +108,7 @@ void run(int N, int iters) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int rep = 0; rep < 2; ++rep) {
     cudaEventRecord(e0);
-    cudaError_t err = cudaLaunchKernelEx(&cfg, rate_kernel<CG, MN>, N, iters, d, g_commit_every);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, rate_kernel<CG, MN>, N, iters, d, g_commit_every, M1);
     cudaEventRecord(e1);
     if (err != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { printf("CG%d N=%d failed: %s\n", CG, N, cudaGetErrorString(cudaGetLastError())); exit(1); }
   }
@@ -116,7 +116,7 @@ void run(int N, int iters) {
   long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   long long mx = 0; for (int i = 0; i < ctas; ++i) if (h[i] > mx) mx = h[i];
   const double mmas = (double)iters * (BK / 16);
-  const int Mtot = CG == 2 ? 256 : 128;
+  const int Mtot = CG == 2 ? 256 : M1;
   const double flops = 2.0 * Mtot * N * 16 * mmas * (ctas / CG);
   printf("commit/%d %s cta_group::%d M=%3d N=%3d  cycles/MMA %7.2f  (floor %5.1f)  chip %7.1f TFLOP/s  (%.3f ms)\n", g_commit_every, MN ? "MN-major" : "K-major ", CG, Mtot, N, mx / mmas,
          128.0 * N / 256.0 , flops / (ms * 1e-3) / 1e12, ms);
@@ -205,5 +205,8 @@ void run_lean(int N, int iters) {
 int main() {
   const int iters = 20000;
   for (int N : {32, 64, 128}) { run_lean<0>(N, iters); run_lean<8>(N, iters); run_lean<2>(N, iters); run_lean<1>(N, iters); }
+  // round 2: K-major against MN-major operands (the weight-gradient kernels read both operands MN-major), N up to 256, M = 64
+  for (int N : {64, 128, 192, 256}) { run<1, 0>(N, iters); run<1, 1>(N, iters); }
+  for (int N : {128, 192, 256}) { run<1, 0>(N, iters, 64); run<1, 1>(N, iters, 64); }
   return 0;
 }
