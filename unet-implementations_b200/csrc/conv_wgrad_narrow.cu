@@ -28,7 +28,6 @@ struct WgradNParams {
   int cin, cout;
   int chunks_per_cta;  // CPB: channel chunks (of CH) whose accumulators live in this CTA's TMEM
   int stages;
-  int base_offset_mode;  // ONE only, developer knob: 1 = put (start address >> 7) & 7 into the B descriptor's base offset
   float* partial;      // [S][9][cin][cout]
 };
 
@@ -52,7 +51,9 @@ struct WnCfg {
   static constexpr int kNcols = 3 * CO;                     // accumulator columns per MMA group
   // ONE: a single (16 + 2)-pixel wide dY tile; the three kw shifts are three N units ONE 128-byte ROW apart (LBO = one
   // row) -- the swizzle is a function of the absolute shared-memory address, so a start address that is a multiple of
-  // 128 but not of 1024 bytes reads what TMA wrote.  18 KB instead of 48 KB per stage for Cout = 64.
+  // 128 (or, MODE 2, of 16) but not of 1024 bytes reads what TMA wrote: results bit-identical to the three-tile form,
+  // measured; with the descriptor's base-offset field set to (address >> 7) & 7 they are wrong, so it stays 0.
+  // 18 KB instead of 48 KB per stage for Cout = 64.
   static constexpr int kDyBytes1 = ((kWnR * kWnDyW * kRowB + 1023) / 1024) * 1024;
   static constexpr uint32_t kSwzA = (CH == 64) ? kSwz128 : kSwz64;
   static constexpr uint32_t kSwzB = (CO == 64) ? kSwz128 : kSwz64;
@@ -169,14 +170,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
 #pragma unroll 2
         for (int r = 0; r < kWnR; ++r) {
           const uint32_t b_lo = b0 + r * kRowStepB;
-          uint32_t bh = b_hi;
-          if (ONE && p.base_offset_mode) bh |= ((b_lo >> 3) & 7u) << 17;  // descriptor bits 49-51
           uint32_t a_lo = x0 + r * kRowStepA;
           for (int j = 0; j < CPB; ++j, a_lo += (Cfg::kXBytes >> 4)) {
 #pragma unroll
             for (int g = 0; g < Cfg::kGroups; ++g)
               umma_bf16_lean(tmem_base + (j * Cfg::kGroups + g) * kNcols, a_lo + g * Cfg::kSlots * kRowStepA, a_hi,
-                             b_lo, bh, idesc, acc | r);
+                             b_lo, b_hi, idesc, acc | r);
           }
         }
         acc = 1;
@@ -325,10 +324,6 @@ static bool wgradn_one_dy(int Cin, int Cout) {
   const char* e = getenv("B200UNET_WGRAD_ONEDY");
   return Cout == 64 && Cin % 64 == 0 && !(e && e[0] == '0');
 }
-static int wgradn_base_offset_mode() {
-  const char* e = getenv("B200UNET_WGRAD_ONEDY");
-  return (e && e[0] == '2') ? 1 : 0;
-}
 
 static void plan_wgradn(int N, int H, int W, int Cin, int Cout, WgradNPlan* pl, int force_one = -1) {
   pl->CO = Cout;
@@ -420,7 +415,6 @@ static int wgradn_launch_pairs(const b200unet_conv_wgrad_args* a, cudaStream_t s
   if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64, 16,
                          kWnR + 3)))
     return rc;
-  p.base_offset_mode = wgradn_base_offset_mode();
   if ((rc = make_act_map(&maps.dy, static_cast<const __nv_bfloat16*>(a->dy), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64,
                          one ? kWnDyW : 16, kWnR)))
     return rc;
@@ -463,7 +457,6 @@ int wgradn_launch(const b200unet_conv_wgrad_args* a, cudaStream_t st) {
                          0, pl.CH, 16, kWnR + 3)))
     return rc;
   const bool one = wgradn_one_dy(a->Cin, a->Cout);
-  p.base_offset_mode = wgradn_base_offset_mode();
   if ((rc = make_act_map(&maps.dy, static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, a->N, a->H, a->W, a->Cout, 1,
                          1, 0, 0, pl.CO, one ? kWnDyW : 16, kWnR)))
     return rc;
