@@ -5,15 +5,18 @@
 //
 //   D[128 pixels, BN] = sum over taps (kh,kw) and channel chunks c of
 //        A_tap[128 pixels, BK channels]  x  W[BN, tap*C + c*BK .. +BK]^T
-//   A 128-pixel tile is an 8 x 16 patch of one image of the output lattice.
+//   A 128-pixel tile is a 16-row x 8-pixel patch of one image of the output lattice.
 //
-// Operand staging ("patch loads").  A tap-shifted A tile is 8 whole image rows of 16 pixels, i.e. 128 contiguous
-// 128-byte (64-byte for BK = 32) rows in shared memory.  Taps that differ only in their ROW shift are therefore windows
-// of ONE (8 + r) x 16 patch at a 16-row (2048-byte: swizzle-aligned) offset: a stride-1 conv loads 3 patches of 10
-// rows per channel chunk (one per column shift, the column shift and the zero padding are TMA coordinates /
-// out-of-bounds fill) instead of 9 tiles -- 2.4x less L2->SM traffic and 3x fewer TMA instructions, which matters
-// because a 4-D cp.async.bulk.tensor costs its issuing thread ~420 cycles on B200 (tools/micro/tma_rate.cu).
-// Stride 2: fprop reads the four parity sub-lattices of the input (6 patch loads per chunk); dgrad writes the four
+// Operand staging ("patch loads").  The K-major A operand of an MMA is 16 core-matrix groups of 8 rows (128-byte rows,
+// 64-byte for BK = 32) at a uniform stride (SBO).  With an 8-pixel wide tile every group is ONE image row of the tile,
+// so a tap-shifted A tile is a WINDOW of a (16 + 2) x (8 + 2) input patch: SBO = the patch's row pitch (10 pixels),
+// start = the tap's (row, column) offset inside the patch.  The shared-memory swizzle is a function of the absolute
+// address, so a window may start at any pixel (measured: bit-identical results for starts that are not multiples of
+// the 1024-byte swizzle period, conv_wgrad_narrow.cu).  ONE patch load per channel chunk therefore serves all 9 taps:
+// 1.4x the tile's own bytes from L2 instead of 3.75x with one 10 x 16 patch per column shift (round 1) or 9x with one
+// tile per tap, and 1 instead of 3 / 9 TMA instructions (a 4-D cp.async.bulk.tensor costs its issuing thread ~420
+// cycles on B200, tools/micro/tma_rate.cu).  The zero padding is TMA out-of-bounds fill.
+// Stride 2: fprop reads the four parity sub-lattices of the input (4 patch loads per chunk); dgrad writes the four
 // parity sub-lattices of dx through four launches (gather form: no scatter, no atomics).
 // Weights (B): K-major [BN x BK] tiles of the packed weight matrix; when the whole slab of a layer (taps x chunks)
 // fits in ~72 KB it is loaded ONCE per CTA and stays resident (all Cout <= 96 layers), otherwise it streams through
@@ -32,21 +35,24 @@
 
 namespace b200 {
 
-constexpr int kTH = 8, kTW = 16;  // output patch of a tile
-constexpr int kMaxLoads = 9;
+constexpr int kTH = 16, kTW = 8;  // output patch of a tile (rows x pixels)
+constexpr int kMaxLoads = 4;      // one patch per source lattice (stride 1: one; stride-2 fprop: the four parity classes)
+constexpr int kMaxTaps = 9;
 
 struct ALoad {
-  int dh, dw;       // patch origin relative to the tile origin (in the load's source lattice)
-  int rows;         // patch height in image rows (8 .. 10)
-  int ntaps;        // taps served by this patch
-  int rowoff[3];    // image-row offset of each tap's window inside the patch
-  int koff[3];      // K offset (elements) of each tap in the packed weight matrix
+  int dh, dw;              // patch origin relative to the tile origin (in the load's source lattice)
+  int rows, cols;          // patch size in image rows / pixels: tile + the span of the taps it serves
+  int ntaps;               // taps served by this patch
+  uint32_t a_hi;           // high word of the A descriptors of this patch (SBO = cols pixels)
+  uint32_t mt_step16;      // window offset of the next M tile of a CTA tile (kTH image rows), 16-byte units
+  uint32_t winoff16[kMaxTaps];  // start of each tap's window inside the patch, 16-byte units
+  int koff[kMaxTaps];      // K offset (elements) of each tap in the packed weight matrix
 };
 
 struct GConvParams {
   int N, OH, OW, tiles_w, tiles_h;
   int nloads, ntaps_total;
-  int s1;  // 1 when the loads are the stride-1 pattern: 3 patches, each serving row windows 0, 1, 2 in this order
+  int s1;  // 1 when ONE patch serves 9 taps (every stride-1 conv): the issue loop is fully unrolled
   ALoad loads[kMaxLoads];
   int cin;   // channels per tap on the K side (multiple of BK)
   int cout;  // total N of the GEMM
@@ -65,14 +71,14 @@ struct GConvMaps {
   CUtensorMap out[8];  // one per output channel block when the output is split (parity sub-lattices / two tensors)
 };
 
-// MT = 2: the CTA tile is TWO vertically adjacent 8 x 16 patches (one 18-row TMA patch per column shift, two
-// accumulators); every streamed weight tile feeds both, which halves the dominant L2->SM stream of the N = 128 layers
-// (their MMA thread waited on weight tiles 35 % of the time: 204 -> 126 KB per 128 pixels and chunk).
+// MT > 1: the CTA tile is MT vertically adjacent 16 x 8 patches (one (16 MT + 2)-row TMA patch, MT accumulators);
+// every streamed weight tile feeds all of them, which divides the dominant L2->SM stream of the N <= 128 layers by MT
+// (their MMA thread waited on weight tiles 35 % of the time).
 template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
 struct GConvCfg {
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kTHc = kTH * MT;                                         // image rows of a CTA tile
-  static constexpr int kASlotBytes = (kTHc + 2) * kTW * kRowBytes;             // largest patch (10 / 18 rows)
+  static constexpr int kASlotBytes = (((kTHc + 2) * (kTW + 2) * kRowBytes + 1023) / 1024) * 1024;  // largest patch
   static constexpr int kBTileBytes = ((BN * BK * 2 + 1023) / 1024) * 1024;     // one [BN x BK] weight tile
   static constexpr int kBTileTx = BN * BK * 2;
   static constexpr int kBResBytes = 72 * 1024;                                 // resident weight slab budget
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
             const long long t0 = (kInstr && p.debug) ? clock64() : 0;
             mbar_wait(&a_empty[slot], ph ^ 1);
             const long long t1 = (kInstr && p.debug) ? clock64() : 0;
-            mbar_expect_tx(&a_full[slot], L.rows * kTW * Cfg::kRowBytes);
+            mbar_expect_tx(&a_full[slot], L.rows * L.cols * Cfg::kRowBytes);
             tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src[l], &a_full[slot], c * BK, w0 + L.dw, h0 + L.dh, n_img);
             if (kInstr && p.debug) {
               dbg_wait += t1 - t0;
@@ -224,10 +230,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     if (elect_one()) {
       // ONE thread issues every MMA of the CTA: its scalar instruction stream is the critical path, so everything
       // that can be is hoisted -- descriptors are 32-bit adds on precomputed halves, barrier addresses are
-      // precomputed, the stride-1 tap pattern (3 patches x 3 row windows) is fully unrolled.
+      // precomputed, the stride-1 tap pattern (one patch, 9 windows) is fully unrolled.
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);
-      constexpr uint32_t kWin = (kTW * Cfg::kRowBytes) >> 4;       // one image row of the patch, in 16-byte units
+      constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);  // B: dense [BN x BK] tiles
       constexpr uint32_t kASlot16 = Cfg::kASlotBytes >> 4, kBTile16 = Cfg::kBTileBytes >> 4;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b), 16);
@@ -251,17 +256,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         uint32_t acc = 0;
         uint32_t b_res = b_lo0;  // next resident weight tile
         for (int c = 0; c < chunks; ++c) {
-          const int nl = s1 ? 3 : p.nloads;
-#pragma unroll 3
+          const int nl = s1 ? 1 : p.nloads;
           for (int l = 0; l < nl; ++l) {
             const long long t1 = (kInstr && p.debug) ? clock64() : 0;
             mbar_wait_u32(a_full0 + aslot * 8, aph);
             if (kInstr && p.debug) dbg_af += clock64() - t1;
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + aslot * kASlot16;
-            const int nt = s1 ? 3 : p.loads[l].ntaps;
-#pragma unroll 3
-            for (int t = 0; t < nt; ++t) {
+            const ALoad& L = p.loads[s1 ? 0 : l];
+            const uint32_t a_hi = L.a_hi, mt_step = L.mt_step16;
+            auto tap = [&](int t) {
               uint32_t b_lo;
               if (B_RES) {
                 b_lo = b_res;
@@ -271,18 +275,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
                 tc_fence_after();
                 b_lo = b_lo0 + bslot * kBTile16;
               }
-              const uint32_t at_lo = a_lo + (s1 ? static_cast<uint32_t>(t) : static_cast<uint32_t>(p.loads[l].rowoff[t])) * kWin;
+              const uint32_t at_lo = a_lo + L.winoff16[t];
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {  // the same weight tile for every M tile: window 8 image rows further down
+              for (int mt = 0; mt < MT; ++mt) {  // the same weight tile for every M tile: window kTH image rows further down
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16_lean(d_tmem + mt * BN, at_lo + mt * (kTH * kWin) + 2 * k, hi, b_lo + 2 * k, hi, idesc, acc | k);
+                  umma_bf16_lean(d_tmem + mt * BN, at_lo + mt * mt_step + 2 * k, a_hi, b_lo + 2 * k, hi, idesc, acc | k);
               }
               acc = 1;
               if (!B_RES) {
                 umma_commit_u32(b_empty0 + bslot * 8);
                 if (++bslot == B_SLOTS) { bslot = 0; bph ^= 1; }
               }
+            };
+            if (s1) {
+#pragma unroll
+              for (int t = 0; t < kMaxTaps; ++t) tap(t);
+            } else {
+              const int nt = L.ntaps;
+              for (int t = 0; t < nt; ++t) tap(t);
             }
             umma_commit_u32(a_empty0 + aslot * 8);
             if (++aslot == A_SLOTS) { aslot = 0; aph ^= 1; }
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
               const uint32_t off = (OC == 64) ? (r * 128 + (((cw ^ (r & 7)) & 7) << 4) + wi)
                                               : (r * 64 + (((cw ^ ((r >> 1) & 3)) & 3) << 4) + wi);
               w[i] = lds_u32(smem_u32(sbase) + off);
-              if (!full && !((h0 + (r >> 4) < p.OH) && (w0 + (r & 15) < p.OW))) w[i] = 0;  // outside the image
+              if (!full && !((h0 + (r >> 3) < p.OH) && (w0 + (r & 7) < p.OW))) w[i] = 0;  // outside the image
             }
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -502,42 +513,49 @@ static int pick_mt(int BK, int BN, int cout_total, int k_channels, int ntaps) {
   return BN == 128 ? 2 : (BN == 64 ? 4 : 1);  // as many accumulators as TMEM holds twice (double buffering)
 }
 
-// Group taps that share (lattice, column shift) into patch loads and build one tensor map per load.  p->mt must be set.
+// Group the taps of each source lattice into ONE patch load and build its tensor map.  p->mt must be set.
 static int build_loads(const TapSpec* taps, int ntaps, const SrcLattice* lat, int BK, GConvParams* p, GConvMaps* maps) {
   p->nloads = 0;
   p->ntaps_total = ntaps;
-  bool used[9] = {false};
+  if (ntaps > kMaxTaps) return set_error(kErrInvalid, "gconv: %d taps", ntaps);
+  const int row_bytes = BK * 2;
+  const uint32_t swz = (BK == 64) ? kSwz128 : kSwz64;
+  bool used[kMaxTaps] = {false};
   for (int i = 0; i < ntaps; ++i) {
     if (used[i]) continue;
-    int idx[3], n = 0;
-    for (int j = i; j < ntaps && n < 3; ++j)
-      if (!used[j] && taps[j].map == taps[i].map && taps[j].dw == taps[i].dw) idx[n++] = j;
-    int dh_min = taps[idx[0]].dh, dh_max = dh_min;
+    if (p->nloads == kMaxLoads) return set_error(kErrInvalid, "gconv: more than %d source lattices", kMaxLoads);
+    int idx[kMaxTaps], n = 0;
+    for (int j = i; j < ntaps; ++j)
+      if (!used[j] && taps[j].map == taps[i].map) idx[n++] = j;
+    int dh_min = taps[idx[0]].dh, dh_max = dh_min, dw_min = taps[idx[0]].dw, dw_max = dw_min;
     for (int k = 1; k < n; ++k) {
-      if (taps[idx[k]].dh < dh_min) dh_min = taps[idx[k]].dh;
-      if (taps[idx[k]].dh > dh_max) dh_max = taps[idx[k]].dh;
+      dh_min = taps[idx[k]].dh < dh_min ? taps[idx[k]].dh : dh_min;
+      dh_max = taps[idx[k]].dh > dh_max ? taps[idx[k]].dh : dh_max;
+      dw_min = taps[idx[k]].dw < dw_min ? taps[idx[k]].dw : dw_min;
+      dw_max = taps[idx[k]].dw > dw_max ? taps[idx[k]].dw : dw_max;
     }
-    if (dh_max - dh_min > 2) return set_error(kErrInvalid, "gconv: tap row span %d too large", dh_max - dh_min);
+    if (dh_max - dh_min > 2 || dw_max - dw_min > 2)
+      return set_error(kErrInvalid, "gconv: tap span %d x %d too large", dh_max - dh_min, dw_max - dw_min);
     ALoad& L = p->loads[p->nloads];
     L.dh = dh_min;
-    L.dw = taps[i].dw;
+    L.dw = dw_min;
     L.rows = kTH * p->mt + (dh_max - dh_min);
+    L.cols = kTW + (dw_max - dw_min);
     L.ntaps = n;
+    L.a_hi = umma_desc_hi(static_cast<uint32_t>(L.cols * row_bytes), swz);
+    L.mt_step16 = static_cast<uint32_t>(kTH * L.cols * row_bytes) >> 4;
     for (int k = 0; k < n; ++k) {
       used[idx[k]] = true;
-      L.rowoff[k] = taps[idx[k]].dh - dh_min;
+      L.winoff16[k] = static_cast<uint32_t>(((taps[idx[k]].dh - dh_min) * L.cols + (taps[idx[k]].dw - dw_min)) * row_bytes) >> 4;
       L.koff[k] = taps[idx[k]].koff;
     }
     const SrcLattice& S = lat[taps[i].map];
     int rc = make_act_map(&maps->src[p->nloads], S.base, S.pitch, S.N, S.H, S.W, S.C, S.hstep, S.wstep, S.hoff, S.woff,
-                          BK, kTW, L.rows);
+                          BK, L.cols, L.rows);
     if (rc) return rc;
     ++p->nloads;
   }
-  p->s1 = (p->nloads == 3);
-  for (int l = 0; l < p->nloads && p->s1; ++l)
-    if (p->loads[l].ntaps != 3 || p->loads[l].rowoff[0] != 0 || p->loads[l].rowoff[1] != 1 || p->loads[l].rowoff[2] != 2)
-      p->s1 = 0;
+  p->s1 = (p->nloads == 1 && p->loads[0].ntaps == kMaxTaps);
   return 0;
 }
 
@@ -628,10 +646,11 @@ static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, i
   const bool res = gconv_weights_resident(BK, BN, p.cout, p.cin, p.ntaps_total);
 #define GC(bk, bn, as, bs, r) \
   if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
-  GC(64, 256, 3, 4, false)
-  GC(64, 192, 4, 4, false)
-  if (BK == 64 && BN == 128 && !res && p.mt == 2) return launch_gconv<64, 128, 3, 4, false, 0, 2>(maps, p, st);
-  if (BK == 64 && BN == 64 && !res && p.mt == 4) return launch_gconv<64, 64, 2, 4, false, 0, 4>(maps, p, st);
+  // A slots now hold a whole channel chunk (all taps) of a CTA tile: two or three are a deep enough ring
+  GC(64, 256, 2, 4, false)
+  GC(64, 192, 3, 4, false)
+  if (BK == 64 && BN == 128 && !res && p.mt == 2) return launch_gconv<64, 128, 2, 6, false, 0, 2>(maps, p, st);
+  if (BK == 64 && BN == 64 && !res && p.mt == 4) return launch_gconv<64, 64, 2, 3, false, 0, 4>(maps, p, st);
   GC(64, 128, 4, 4, false)
   GC(64, 64, 6, 4, false)
   GC(64, 64, 4, 1, true)
