@@ -438,6 +438,10 @@ static int nconv_bk(int k_channels) { return k_channels > 32 ? 64 : 32; }
 bool nconv_supported(int k_channels, int n_channels, int stride, int W) {
   if (stride != 1 || (n_channels != 32 && n_channels != 64) || k_channels % 32 != 0 || k_channels <= 0) return false;
   if (W < 64) return false;  // the 30-of-32 column tiling only pays on wide images
+  {  // developer knob: B200UNET_NO_NCONV=<n_channels> sends that output width to gconv_kernel instead (A/B)
+    const char* e = getenv("B200UNET_NO_NCONV");
+    if (e && atoi(e) == n_channels) return false;
+  }
   const int BK = nconv_bk(k_channels);
   return static_cast<long long>(ceil_div(k_channels, BK)) * 3 * (3 * n_channels * BK * 2) <= 80 * 1024;  // resident weights
 }

@@ -37,7 +37,10 @@ struct WgradNMaps {
 };
 
 constexpr int kWnR = 8;         // image rows per pixel block (K = 16*R = 128 pixels per stage)
-constexpr int kWnDyW = 18;      // ONE: width of the single dY tile (16 pixels + one on each side)
+// MODE >= 1: pixel blocks of kWnR1 rows x kWnW1 pixels.  Measured with 4 x 32 (4 KB instead of 2 KB contiguous per TMA
+// row, 7/4 instead of 11/8 halo rows): 216-236 against 226 us (32 -> 32 pairs), 165 against 167 (64 -> 64), 421 against
+// 429 us (192 -> 64): no difference, the block shape is not what bounds the loads (DRAM reads at 5.3 TB/s are).
+constexpr int kWnR1 = 8, kWnW1 = 16;
 constexpr int kWnMaxStages = 6;  // the loop is bound by load latency x bytes in flight (ncu: 47 % of samples on the
                                  // full barrier, DRAM 45 %, tensor 31 % with 4 stages of 35 KB): use all of shared memory
 
@@ -54,7 +57,9 @@ struct WnCfg {
   // 128 (or, MODE 2, of 16) but not of 1024 bytes reads what TMA wrote: results bit-identical to the three-tile form,
   // measured; with the descriptor's base-offset field set to (address >> 7) & 7 they are wrong, so it stays 0.
   // 18 KB instead of 48 KB per stage for Cout = 64.
-  static constexpr int kDyBytes1 = ((kWnR * kWnDyW * kRowB + 1023) / 1024) * 1024;
+  static constexpr int kXBytes1 = (kWnR1 + 3) * kWnW1 * kRowA;
+  static constexpr int kDyTx1 = kWnR1 * (kWnW1 + 2) * kRowB;
+  static constexpr int kDyBytes1 = ((kDyTx1 + 1023) / 1024) * 1024;
   static constexpr uint32_t kSwzA = (CH == 64) ? kSwz128 : kSwz64;
   static constexpr uint32_t kSwzB = (CO == 64) ? kSwz128 : kSwz64;
 };
@@ -72,6 +77,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
   constexpr bool ONE = MODE >= 1, PAIR = MODE == 2;
   static_assert(!PAIR || (CH == 64 && CO == 64), "the pair form runs on the 64-channel pair views");
   constexpr int kNcols = PAIR ? 128 : Cfg::kNcols;  // accumulator columns per MMA group
+  constexpr int R = ONE ? kWnR1 : kWnR, BW = ONE ? kWnW1 : 16;  // pixel block: rows x pixels
+  constexpr int kXBytes = ONE ? Cfg::kXBytes1 : Cfg::kXBytes;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kWnMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kWnMaxStages];
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
   const int STAGES = p.stages;
   constexpr int kNB = ONE ? 1 : 3;                                          // dY loads per stage
   constexpr int kDyTotal = ONE ? Cfg::kDyBytes1 : 3 * Cfg::kDyBytes;
-  const int stage_bytes = ONE ? ((CPB * Cfg::kXBytes + kDyTotal + 1023) / 1024) * 1024 : CPB * Cfg::kXBytes + kDyTotal;
+  const int stage_bytes = ONE ? ((CPB * kXBytes + kDyTotal + 1023) / 1024) * 1024 : CPB * kXBytes + kDyTotal;
   const int split = blockIdx.x;
   const int chunk0 = blockIdx.y * CPB;  // first channel chunk of this CTA
   const int kb_begin = split * p.kb_per_split;
@@ -126,13 +133,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
         // 32 KB jumps between consecutive blocks cost more than that: 381 vs 345 us at 512^2 x 32)
         const int bh = b_in / p.blocks_w;
         const int bw = b_in - bh * p.blocks_w;
-        const int h0 = bh * kWnR, w0 = bw * 16;
+        const int h0 = bh * R, w0 = bw * BW;
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint32_t my_bytes = 0;
         for (int j = warp; j < kNB + CPB; j += kProducerWarps)
-          my_bytes += (j < kNB) ? (ONE ? kWnR * kWnDyW * Cfg::kRowB : Cfg::kDyBytes) : Cfg::kXBytes;
+          my_bytes += (j < kNB) ? (ONE ? Cfg::kDyTx1 : Cfg::kDyBytes) : kXBytes;
         mbar_expect_tx(&full_bar[s], my_bytes);
         uint8_t* sb = smem + s * stage_bytes;
         for (int j = warp; j < kNB + CPB; j += kProducerWarps) {
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
             else tma_load_4d(sb + j * Cfg::kDyBytes, &maps.dy, &full_bar[s], 0, w0 + 1 - j, h0, n_img);
           } else {
             // A: X patch rows [h0 - 1, h0 + R + 2) of channel chunk j - kNB
-            tma_load_4d(sb + kDyTotal + (j - kNB) * Cfg::kXBytes, &maps.x, &full_bar[s],
+            tma_load_4d(sb + kDyTotal + (j - kNB) * kXBytes, &maps.x, &full_bar[s],
                         (chunk0 + j - kNB) * CH, w0, h0 - 1, n_img);
           }
         }
@@ -153,11 +160,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
       // lean issue loop (see ptx.cuh): 32-bit descriptor halves, image-row advance = an add on the low word
       constexpr uint32_t idesc = umma_idesc_bf16(128, kNcols, 1, 1);
       constexpr uint32_t a_hi = umma_desc_hi(8 * Cfg::kRowA, Cfg::kSwzA), b_hi = umma_desc_hi(8 * Cfg::kRowB, Cfg::kSwzB);
-      constexpr uint32_t kRowStepA = (16 * Cfg::kRowA) >> 4;                                      // one image row
-      constexpr uint32_t kRowStepB = ((ONE ? kWnDyW : 16) * Cfg::kRowB) >> 4;
+      constexpr uint32_t kRowStepA = (BW * Cfg::kRowA) >> 4;                                      // one image row
+      constexpr uint32_t kRowStepB = ((ONE ? BW + 2 : 16) * Cfg::kRowB) >> 4;
+      constexpr uint32_t kHalfA = (16 * Cfg::kRowA) >> 4, kHalfB = (16 * Cfg::kRowB) >> 4;  // 16 pixels of K
       // A: leading-dimension stride = one image row (kh slots);  B: leading-dimension stride = one shifted dY tile
       // (ONE: one pixel row of the wide tile; N unit u starts at column u, i.e. holds the shift kw = 2 - u)
-      constexpr uint32_t a_lbo = (((16 * Cfg::kRowA) >> 4) & 0x3FFFu) << 16;
+      constexpr uint32_t a_lbo = (((BW * Cfg::kRowA) >> 4) & 0x3FFFu) << 16;
       constexpr uint32_t b_lbo = (((ONE ? Cfg::kRowB : Cfg::kDyBytes) >> 4) & 0x3FFFu) << 16;
       const uint32_t lo0 = umma_desc_lo(smem_u32(smem), 0);
       const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
@@ -168,14 +176,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
         const uint32_t b0 = lo0 + s * stage16 + b_lbo + (PAIR ? 4u : 0u);  // PAIR: the window starts 64 bytes into row 0
         const uint32_t x0 = lo0 + s * stage16 + (kDyTotal >> 4) + a_lbo;
 #pragma unroll 2
-        for (int r = 0; r < kWnR; ++r) {
-          const uint32_t b_lo = b0 + r * kRowStepB;
-          uint32_t a_lo = x0 + r * kRowStepA;
-          for (int j = 0; j < CPB; ++j, a_lo += (Cfg::kXBytes >> 4)) {
+        for (int rh = 0; rh < R * (BW / 16); ++rh) {  // one K = 16 step: 16 pixels of one image row of the block
+          const int r = rh / (BW / 16), h = rh % (BW / 16);
+          const uint32_t b_lo = b0 + r * kRowStepB + h * kHalfB;
+          uint32_t a_lo = x0 + r * kRowStepA + h * kHalfA;
+          for (int j = 0; j < CPB; ++j, a_lo += (kXBytes >> 4)) {
 #pragma unroll
             for (int g = 0; g < Cfg::kGroups; ++g)
               umma_bf16_lean(tmem_base + (j * Cfg::kGroups + g) * kNcols, a_lo + g * Cfg::kSlots * kRowStepA, a_hi,
-                             b_lo, b_hi, idesc, acc | r);
+                             b_lo, b_hi, idesc, acc | rh);
           }
         }
         acc = 1;
@@ -337,8 +346,9 @@ static void plan_wgradn(int N, int H, int W, int Cin, int Cout, WgradNPlan* pl, 
   if (cpb > chunks) cpb = chunks;
   // shared memory: at least 2 stages must fit
   const bool one = force_one >= 0 ? force_one != 0 : wgradn_one_dy(Cin, Cout);
-  const int xbytes = (kWnR + 3) * 16 * pl->CH * 2;
-  const int dybytes = one ? ((kWnR * kWnDyW * Cout * 2 + 1023) / 1024) * 1024 : 3 * kWnR * 16 * Cout * 2;
+  const int R = one ? kWnR1 : kWnR, BW = one ? kWnW1 : 16;
+  const int xbytes = (R + 3) * BW * pl->CH * 2;
+  const int dybytes = one ? ((R * (BW + 2) * Cout * 2 + 1023) / 1024) * 1024 : 3 * kWnR * 16 * Cout * 2;
   while (cpb > 1 && 2 * (cpb * xbytes + dybytes + 1023) > 216 * 1024) --cpb;
   while (chunks % cpb != 0) --cpb;  // every CTA gets the same number of chunks
   pl->CPB = cpb;
@@ -349,8 +359,8 @@ static void plan_wgradn(int N, int H, int W, int Cin, int Cout, WgradNPlan* pl, 
   if (stages < 2) stages = 2;
   pl->stages = stages;
   pl->smem_bytes = static_cast<int64_t>(stages) * stage + 1024;
-  pl->blocks_w = ceil_div(W, 16);
-  pl->blocks_h = ceil_div(H, kWnR);
+  pl->blocks_w = ceil_div(W, BW);
+  pl->blocks_h = ceil_div(H, R);
   pl->total_kb = N * pl->blocks_w * pl->blocks_h;
   int S = num_sms() / pl->gy;
   if (S < 1) S = 1;
@@ -412,11 +422,11 @@ static int wgradn_launch_pairs(const b200unet_conv_wgrad_args* a, cudaStream_t s
   p.stages = pl.stages;
   p.partial = a->workspace;
   int rc;
-  if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64, 16,
-                         kWnR + 3)))
+  if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64,
+                         one ? kWnW1 : 16, (one ? kWnR1 : kWnR) + 3)))
     return rc;
   if ((rc = make_act_map(&maps.dy, static_cast<const __nv_bfloat16*>(a->dy), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64,
-                         one ? kWnDyW : 16, kWnR)))
+                         one ? kWnW1 + 2 : 16, one ? kWnR1 : kWnR)))
     return rc;
   if ((rc = window ? launch_wgradn<64, 64, 2>(maps, p, pl, st)
                    : one ? launch_wgradn<64, 64, 1>(maps, p, pl, st) : launch_wgradn<64, 64>(maps, p, pl, st)))
@@ -453,12 +463,12 @@ int wgradn_launch(const b200unet_conv_wgrad_args* a, cudaStream_t st) {
   p.stages = pl.stages;
   p.partial = a->workspace;
   int rc;
-  if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0,
-                         0, pl.CH, 16, kWnR + 3)))
-    return rc;
   const bool one = wgradn_one_dy(a->Cin, a->Cout);
+  if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), a->x_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0,
+                         0, pl.CH, one ? kWnW1 : 16, (one ? kWnR1 : kWnR) + 3)))
+    return rc;
   if ((rc = make_act_map(&maps.dy, static_cast<const __nv_bfloat16*>(a->dy), a->dy_pitch, a->N, a->H, a->W, a->Cout, 1,
-                         1, 0, 0, pl.CO, one ? kWnDyW : 16, kWnR)))
+                         1, 0, 0, pl.CO, one ? kWnW1 + 2 : 16, one ? kWnR1 : kWnR)))
     return rc;
   if (pl.CH == 32 && pl.CO == 32) rc = launch_wgradn<32, 32>(maps, p, pl, st);
   else if (pl.CH == 32 && pl.CO == 64) rc = launch_wgradn<32, 64>(maps, p, pl, st);
