@@ -274,9 +274,10 @@ __global__ void __launch_bounds__(256) wgrad_finalize_pairs_kernel(const float* 
   const int s_per = (S + 7) / 8;
   const int s_lo = z * s_per, s_hi = min(S, s_lo + s_per);
   float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
   for (int s = s_lo; s < s_hi; ++s) {
-    a0 += partial[static_cast<int64_t>(s) * total + i0];
-    a1 += partial[static_cast<int64_t>(s) * total + i1];
+    a0 += __ldcs(partial + static_cast<int64_t>(s) * total + i0);
+    a1 += __ldcs(partial + static_cast<int64_t>(s) * total + i1);
   }
   red[z][co] = a0 + a1;
   __syncthreads();
@@ -304,9 +305,10 @@ __global__ void __launch_bounds__(256) wgrad_finalize_pairs_window_kernel(const 
   const int s_per = (S + 7) / 8;
   const int s_lo = z * s_per, s_hi = min(S, s_lo + s_per);
   float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
   for (int s = s_lo; s < s_hi; ++s) {
-    a0 += partial[static_cast<int64_t>(s) * total + i0];
-    a1 += partial[static_cast<int64_t>(s) * total + i1];
+    a0 += __ldcs(partial + static_cast<int64_t>(s) * total + i0);
+    a1 += __ldcs(partial + static_cast<int64_t>(s) * total + i1);
   }
   red[z][co] = a0 + a1;
   __syncthreads();
