@@ -28,6 +28,7 @@ struct WgradNParams {
   int cin, cout;
   int chunks_per_cta;  // CPB: channel chunks (of CH) whose accumulators live in this CTA's TMEM
   int stages;
+  int col_major;       // block order inside an image: 1 = down the columns (the 3 halo rows of the next block are in L2)
   float* partial;      // [S][9][cin][cout]
 };
 
@@ -129,10 +130,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) wgradn_kernel(const __grid_co
         const int kb = kb_begin + i;
         const int n_img = kb / blocks_per_img;
         const int b_in = kb - n_img * blocks_per_img;
-        // row-major block order (measured: column-major would keep the 3 halo rows in L2, -10 % DRAM reads, but the
-        // 32 KB jumps between consecutive blocks cost more than that: 381 vs 345 us at 512^2 x 32)
-        const int bh = b_in / p.blocks_w;
-        const int bw = b_in - bh * p.blocks_w;
+        // block order: down the columns, so that the 3 halo rows of the next block are still in L2.  Round 1 measured
+        // the opposite (381 vs 345 us at 512^2 x 32) when the loads were bound by 64-byte TMA rows; now that these kernels
+        // run at the DRAM rate the saved re-reads win: 538 -> 519 us (96 -> 32), 218 -> 216 (32 -> 32 pairs)
+        int bh, bw;
+        if (p.col_major) {
+          bw = b_in / p.blocks_h;
+          bh = b_in - bw * p.blocks_h;
+        } else {
+          bh = b_in / p.blocks_w;
+          bw = b_in - bh * p.blocks_w;
+        }
         const int h0 = bh * R, w0 = bw * BW;
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -422,6 +430,7 @@ static int wgradn_launch_pairs(const b200unet_conv_wgrad_args* a, cudaStream_t s
   p.cout = 64;
   p.chunks_per_cta = pl.CPB;
   p.stages = pl.stages;
+  { const char* e = getenv("B200UNET_WGRADN_COLMAJOR"); p.col_major = (e && e[0] == '0') ? 0 : 1; }
   p.partial = a->workspace;
   int rc;
   if ((rc = make_act_map(&maps.x, static_cast<const __nv_bfloat16*>(a->x), 64, a->N, a->H, Wp, 64, 1, 1, 0, 0, 64,
@@ -463,6 +472,7 @@ int wgradn_launch(const b200unet_conv_wgrad_args* a, cudaStream_t st) {
   p.cout = a->Cout;
   p.chunks_per_cta = pl.CPB;
   p.stages = pl.stages;
+  { const char* e = getenv("B200UNET_WGRADN_COLMAJOR"); p.col_major = (e && e[0] == '0') ? 0 : 1; }
   p.partial = a->workspace;
   int rc;
   const bool one = wgradn_one_dy(a->Cin, a->Cout);
