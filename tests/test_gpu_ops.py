@@ -34,6 +34,10 @@ CONV_CASES = [
     (1, 12, 70, 32, 32, 1), (1, 9, 64, 96, 32, 1), (2, 8, 96, 64, 64, 1), (1, 6, 121, 64, 32, 1), (1, 7, 90, 32, 64, 1),
     # 32 -> 32 on dense tensors at least 128 wide: pixel pairs as operand rows (60-of-64 column tiles); odd width -> nconv
     (1, 12, 128, 32, 32, 1), (2, 9, 190, 32, 32, 1), (3, 5, 250, 32, 32, 1), (1, 6, 129, 32, 32, 1),
+    # streamed-weight layers as CTA pairs (cta_group::2, an even number of 16 x 8 tiles per image): several pair tiles,
+    # ragged edges, two M tiles per CTA (N = 128), N = 192 data gradient; an odd tile count falls back to single CTAs
+    (2, 32, 32, 256, 256, 1), (1, 16, 24, 256, 256, 1), (1, 48, 16, 128, 128, 1), (1, 40, 20, 384, 128, 1),
+    (1, 70, 12, 192, 64, 1),
 ]
 
 

@@ -74,13 +74,19 @@ struct GConvMaps {
 // MT > 1: the CTA tile is MT vertically adjacent 16 x 8 patches (one (16 MT + 2)-row TMA patch, MT accumulators);
 // every streamed weight tile feeds all of them, which divides the dominant L2->SM stream of the N <= 128 layers by MT
 // (their MMA thread waited on weight tiles 35 % of the time).
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
+// CG = 2: a CTA PAIR (cluster of two, one TPC) runs every MMA with cta_group::2, M = 256: each CTA keeps its own
+// 128-pixel tile(s), A patches, accumulators and epilogue, but only HALF of every streamed weight tile (BN / 2 rows of
+// B) -- the pair's tensor cores exchange the halves.  That halves the L2 -> SM weight stream AND the shared-memory
+// operand reads of B per SM, the two things that hold the streamed-weight layers at 65-84 % tensor pipe.
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1, int CG = 1>
 struct GConvCfg {
+  static_assert(CG == 1 || (CG == 2 && !B_RES && BN % 32 == 0), "CTA pairs stream their weights");
   static constexpr int kRowBytes = BK * 2;
   static constexpr int kTHc = kTH * MT;                                         // image rows of a CTA tile
   static constexpr int kASlotBytes = (((kTHc + 2) * (kTW + 2) * kRowBytes + 1023) / 1024) * 1024;  // largest patch
-  static constexpr int kBTileBytes = ((BN * BK * 2 + 1023) / 1024) * 1024;     // one [BN x BK] weight tile
-  static constexpr int kBTileTx = BN * BK * 2;
+  static constexpr int kBRows = BN / CG;                                        // weight rows this CTA loads per tile
+  static constexpr int kBTileBytes = ((kBRows * BK * 2 + 1023) / 1024) * 1024; // one [BN / CG x BK] weight tile
+  static constexpr int kBTileTx = kBRows * BK * 2;
   static constexpr int kBResBytes = 72 * 1024;                                 // resident weight slab budget
   static constexpr int kBBytes = B_RES ? kBResBytes : B_SLOTS * kBTileBytes;
   static constexpr int kOC = OC_ ? OC_ : ((BN % 64 == 0) ? 64 : 32);           // channels per TMA-store box
@@ -98,11 +104,11 @@ struct GConvCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1, int CG = 1>
 __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_constant__ GConvMaps maps,
                                                                  const __grid_constant__ GConvParams p) {
   pdl_launch_dependents();  // PDL (common.cuh): the next kernel of the stream may become resident as CTAs retire
-  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT>;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, B_RES, OC_, MT, CG>;
   constexpr int kBBar = B_RES ? 1 : B_SLOTS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
@@ -116,15 +122,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
   uint8_t* smem_b = smem + A_SLOTS * Cfg::kASlotBytes;
   uint8_t* staging = smem_b + Cfg::kBBytes;
 
+  // CTA pairs: the work unit is a PAIR tile = two consecutive M tiles (rank 0 / rank 1) of the same image x one N
+  // tile; the host dispatches pairs only when an image has an even number of M tiles
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int cta = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int n_tiles = p.cout / BN;
-  const int total_tiles = tiles_per_img * p.N * n_tiles;
+  const int total_tiles = (tiles_per_img / CG) * p.N * n_tiles;
+  auto m_tile_of = [&](int tile) { return (tile / n_tiles) * CG + static_cast<int>(rank); };
   const int chunks = p.cin / BK;
   const int loads_per_tile = chunks * p.nloads;
   const int btiles_per_tile = chunks * p.ntaps_total;
   // contiguous tile range of this CTA (tile = m_tile * n_tiles + n_tile): consecutive patches of one image, which
   // keeps the halo rows in L2 and lets the epilogue accumulate the InstanceNorm partial sums across tiles
-  const int tile_lo = min(static_cast<int>(blockIdx.x) * p.tiles_per_cta, total_tiles);
+  const int tile_lo = min(cta * p.tiles_per_cta, total_tiles);
   const int tile_hi = min(tile_lo + p.tiles_per_cta, total_tiles);
 
   if (threadIdx.x == 0) {
@@ -138,16 +149,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], 4 * CG);  // one arrival per epilogue warp (of both CTAs of a pair: the leader's barrier)
     }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(&tmem_base_holder, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(&tmem_base_holder, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&tmem_base_holder, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
   pdl_wait();  // barrier init / TMEM allocation above ran under the previous kernel's tail; global memory from here on
@@ -168,10 +185,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
       if (warp < Cfg::NA) {
         // ------------------------------------------------------------ A producer `warp` of NA: patch loads
         tma_prefetch_desc(&maps.src[0]);
+        const uint32_t a_full_leader = (CG == 2) ? mapa_u32(smem_u32(&a_full[0]), 0) : 0u;
         long long dbg_wait = 0, dbg_issue = 0;
         int it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-          const int m_tile = tile / n_tiles;
+          const int m_tile = m_tile_of(tile);
           const int n_img = m_tile / tiles_per_img;
           const int t_in = m_tile - n_img * tiles_per_img;
           // column-major tile order inside an image: the next tile is the one BELOW, so the 2 halo rows of its
@@ -190,8 +208,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
             const long long t0 = (kInstr && p.debug) ? clock64() : 0;
             mbar_wait(&a_empty[slot], ph ^ 1);
             const long long t1 = (kInstr && p.debug) ? clock64() : 0;
-            mbar_expect_tx(&a_full[slot], L.rows * L.cols * Cfg::kRowBytes);
-            tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src[l], &a_full[slot], c * BK, w0 + L.dw, h0 + L.dh, n_img);
+            if (CG == 2) {
+              // both CTAs' patches complete on the LEADER's barrier, which expects the bytes of both
+              if (rank == 0) mbar_expect_tx(&a_full[slot], 2 * L.rows * L.cols * Cfg::kRowBytes);
+              tma_load_4d_pair(smem + slot * Cfg::kASlotBytes, &maps.src[l], a_full_leader + slot * 8, c * BK, w0 + L.dw, h0 + L.dh, n_img);
+            } else {
+              mbar_expect_tx(&a_full[slot], L.rows * L.cols * Cfg::kRowBytes);
+              tma_load_4d(smem + slot * Cfg::kASlotBytes, &maps.src[l], &a_full[slot], c * BK, w0 + L.dw, h0 + L.dh, n_img);
+            }
             if (kInstr && p.debug) {
               dbg_wait += t1 - t0;
               dbg_issue += clock64() - t1;
@@ -206,10 +230,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
         // ------------------------------------------------------------ B producer: one [BN x BK] tile per (tap, chunk)
         const int me = warp - (kProducerWarps - Cfg::NB);
         tma_prefetch_desc(&maps.w);
+        const uint32_t b_full_leader = (CG == 2) ? mapa_u32(smem_u32(&b_full[0]), 0) : 0u;
         int it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-          const int m_tile = tile / n_tiles;
-          const int n0 = (tile - m_tile * n_tiles) * BN;
+          const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * Cfg::kBRows;  // this CTA's half of the rows
           const long long g0 = static_cast<long long>(it) * btiles_per_tile;
           int u = 0;
           for (int c = 0; c < chunks; ++c)
@@ -220,18 +244,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
                 const int slot = static_cast<int>(g % B_SLOTS);
                 const uint32_t ph = static_cast<uint32_t>((g / B_SLOTS) & 1);
                 mbar_wait(&b_empty[slot], ph ^ 1);
-                mbar_expect_tx(&b_full[slot], Cfg::kBTileTx);
-                tma_load_2d(smem_b + slot * Cfg::kBTileBytes, &maps.w, &b_full[slot], p.loads[l].koff[t] + c * BK, n0);
+                if (CG == 2) {
+                  if (rank == 0) mbar_expect_tx(&b_full[slot], 2 * Cfg::kBTileTx);
+                  tma_load_2d_pair(smem_b + slot * Cfg::kBTileBytes, &maps.w, b_full_leader + slot * 8, p.loads[l].koff[t] + c * BK, n0);
+                } else {
+                  mbar_expect_tx(&b_full[slot], Cfg::kBTileTx);
+                  tma_load_2d(smem_b + slot * Cfg::kBTileBytes, &maps.w, &b_full[slot], p.loads[l].koff[t] + c * BK, n0);
+                }
               }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    if (elect_one()) {
+    if (rank == 0 && elect_one()) {  // pairs: the leader issues for both CTAs
       // ONE thread issues every MMA of the CTA: its scalar instruction stream is the critical path, so everything
       // that can be is hoisted -- descriptors are 32-bit adds on precomputed halves, barrier addresses are
       // precomputed, the stride-1 tap pattern (one patch, 9 windows) is fully unrolled.
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
+      auto commit = [](uint32_t bar) {
+        if (CG == 2) umma_commit_pair_u32(bar); else umma_commit_u32(bar);
+      };
       constexpr uint32_t hi = umma_desc_hi(Cfg::kSbo, Cfg::kSwz);  // B: dense [BN x BK] tiles
       constexpr uint32_t kASlot16 = Cfg::kASlotBytes >> 4, kBTile16 = Cfg::kBTileBytes >> 4;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem), 16);
@@ -280,11 +312,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
               for (int mt = 0; mt < MT; ++mt) {  // the same weight tile for every M tile: window kTH image rows further down
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16_lean(d_tmem + mt * BN, at_lo + mt * mt_step + 2 * k, a_hi, b_lo + 2 * k, hi, idesc, acc | k);
+                  if (CG == 2)
+                    umma_bf16_lean_pair(d_tmem + mt * BN, at_lo + mt * mt_step + 2 * k, a_hi, b_lo + 2 * k, hi, idesc, acc | k);
+                  else
+                    umma_bf16_lean(d_tmem + mt * BN, at_lo + mt * mt_step + 2 * k, a_hi, b_lo + 2 * k, hi, idesc, acc | k);
               }
               acc = 1;
               if (!B_RES) {
-                umma_commit_u32(b_empty0 + bslot * 8);
+                commit(b_empty0 + bslot * 8);
                 if (++bslot == B_SLOTS) { bslot = 0; bph ^= 1; }
               }
             };
@@ -295,11 +330,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
               const int nt = L.ntaps;
               for (int t = 0; t < nt; ++t) tap(t);
             }
-            umma_commit_u32(a_empty0 + aslot * 8);
+            commit(a_empty0 + aslot * 8);
             if (++aslot == A_SLOTS) { aslot = 0; aph ^= 1; }
           }
         }
-        umma_commit(&tmem_full_bar[buf]);
+        commit(smem_u32(&tmem_full_bar[buf]));
       }
       if (kInstr && p.debug) {
         p.debug[blockIdx.x * 8 + 2] = dbg_te;
@@ -326,9 +361,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     int acc_img = -1;
     auto flush = [&](int img) {
       // slot of this (CTA, q) among the CTAs that cover image `img`
-      const int first_tile = img * tiles_per_img * n_tiles;
+      const int first_tile = img * (tiles_per_img / CG) * n_tiles;
       const int b0 = first_tile / p.tiles_per_cta;
-      const int slot = (static_cast<int>(blockIdx.x) - b0) * 4 + q;
+      const int slot = ((cta - b0) * CG + static_cast<int>(rank)) * 4 + q;
       float* dst = p.stats + (static_cast<size_t>(img) * p.stat_slots + slot) * p.cout * 2;
 #pragma unroll
       for (int i = 0; i < kAccChunks; ++i) {
@@ -352,8 +387,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
     long long dbg_tf = 0, dbg_e0 = kInstr ? clock64() : 0;
     uint32_t sbuf = 0;  // staging buffer toggle (runs across tiles)
     for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-      const int m_tile = tile / n_tiles;
-      const int nt_idx = tile - m_tile * n_tiles;
+      const int m_tile = m_tile_of(tile);
+      const int nt_idx = tile % n_tiles;
       const int n0 = nt_idx * BN;
       const int n_img = m_tile / tiles_per_img;
       const int t_in = m_tile - n_img * tiles_per_img;
@@ -412,7 +447,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
           // this warp's TMEM reads of the tile are complete: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[buf], 0); else mbar_arrive(&tmem_empty_bar[buf]);
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -483,9 +520,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) gconv_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while its peer may still arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -564,16 +602,34 @@ struct GConvGrid {
 };
 // Persistent grid: contiguous tile ranges of equal length; P = partial-sum slots per image = 4 (lane quarters) x the
 // largest number of CTAs whose range can intersect one image.
-static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN, int mt = 1) {
+// cg = 2 (CTA pairs): the unit of work is a pair tile (two M tiles x one N tile), the unit of the grid a cluster of two
+// CTAs; `units` = clusters that can be resident (at most one per TPC), grid = 2 x the clusters used, tiles_per_cta =
+// pair tiles per cluster, and each pair owns 8 partial-sum slots per image it touches.
+static GConvGrid gconv_grid(int N, int OH, int OW, int cout, int BN, int mt = 1, int cg = 1, int units = 0) {
   GConvGrid g;
-  const long long per_img = static_cast<long long>(ceil_div(OW, kTW)) * ceil_div(OH, kTH * mt) * (cout / BN);
+  const long long per_img = static_cast<long long>(ceil_div(OW, kTW)) * ceil_div(OH, kTH * mt) / cg * (cout / BN);
   const long long total = per_img * N;
-  const int sms = num_sms();
-  g.tiles_per_cta = static_cast<int>(ceil_div64(total, sms));
+  if (units <= 0) units = num_sms() / cg;
+  g.tiles_per_cta = static_cast<int>(ceil_div64(total, units));
   if (g.tiles_per_cta < 1) g.tiles_per_cta = 1;
-  g.grid = static_cast<int>(ceil_div64(total, g.tiles_per_cta));
-  g.stat_slots = 4 * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);
+  g.grid = cg * static_cast<int>(ceil_div64(total, g.tiles_per_cta));
+  g.stat_slots = 4 * cg * (static_cast<int>(ceil_div64(per_img, g.tiles_per_cta)) + 1);
   return g;
+}
+
+// CTA pairs (GConvCfg CG = 2) for the streamed-weight configurations.  B200UNET_CG2=0 turns them off (developer knob).
+static bool cg2_enabled() {
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("B200UNET_CG2");
+    state = (e && e[0] == '0') ? 0 : 1;
+  }
+  return state != 0;
+}
+static bool gconv_pairs(int BK, int BN, int mt, bool resident, int out_split, int tiles_w, int tiles_h) {
+  if (!cg2_enabled() || BK != 64 || resident || out_split != 0) return false;
+  if ((static_cast<long long>(tiles_w) * tiles_h) % 2 != 0) return false;  // a pair never straddles two images
+  return (BN == 256 && mt == 1) || (BN == 192 && mt == 1) || (BN == 128 && mt == 2) || (BN == 64 && mt == 4);
 }
 
 int conv_stat_slots(int N, int OH, int OW, int Cout) {
@@ -583,14 +639,19 @@ int conv_stat_slots(int N, int OH, int OW, int Cout) {
   int slots = gconv_grid(N, OH, OW, Cout, BN64).stat_slots;
   const int s32 = gconv_grid(N, OH, OW, Cout, BN32).stat_slots;
   if (s32 > slots) slots = s32;
-  const int s2 = gconv_grid(N, OH, OW, Cout, BN64, BN64 == 64 ? 4 : 2).stat_slots;  // the multi-M-tile variants
+  const int mt64 = BN64 == 64 ? 4 : (BN64 == 128 ? 2 : 1);
+  const int s2 = gconv_grid(N, OH, OW, Cout, BN64, mt64 == 1 ? 2 : mt64).stat_slots;  // the multi-M-tile variants
   if (s2 > slots) slots = s2;
+  const int s3 = gconv_grid(N, OH, OW, Cout, BN64, mt64, 2).stat_slots;  // ... as CTA pairs (an upper bound: fewer
+  if (s3 > slots) slots = s3;                                            // resident clusters mean fewer slots)
   if (Cout == 32 || Cout == 64) {
     const int sn = nconv_stat_slots(N, OH, OW);
     if (sn > slots) slots = sn;
   }
   return slots;
 }
+
+static int device_pairs_fallback() { return num_sms() / 2; }
 
 // Developer instrumentation: B200UNET_GCONV_DEBUG=1 makes every launch synchronise and print per-role wait cycles.
 static long long* debug_buffer() {
@@ -602,6 +663,66 @@ static long long* debug_buffer() {
     if (state) cudaMalloc(&buf, 148 * 8 * sizeof(long long));
   }
   return state ? buf : nullptr;
+}
+
+// A cluster of two CTAs per TPC; `units` of them can be resident at once (queried once per kernel).
+template <typename Kern>
+static int pair_units(Kern kern, int smem_bytes) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 74);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = device_pairs_fallback();
+  }
+  return n;
+}
+
+template <int BK, int BN, int A_SLOTS, int B_SLOTS, int MT>
+static int launch_gconv_pairs(const GConvMaps& maps, const GConvParams& p_in, cudaStream_t st) {
+  GConvParams p = p_in;
+  p.debug = nullptr;
+  using Cfg = GConvCfg<BK, BN, A_SLOTS, B_SLOTS, false, 0, MT, 2>;
+  auto kern = gconv_kernel<BK, BN, A_SLOTS, B_SLOTS, false, 0, MT, 2>;
+  if (p.mt != MT) return set_error(kErrInvalid, "gconv: tile height multiplier %d does not match the kernel (%d)", p.mt, MT);
+  static int units = 0;
+  if (units == 0) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    units = pair_units(kern, Cfg::kSmemBytes);
+  }
+  int u = num_sms() / 2;  // honours the SMs reserved for NCCL
+  if (units < u) u = units;
+  GConvGrid gg = gconv_grid(p.N, p.OH, p.OW, p.cout, BN, MT, 2, u);
+  p.tiles_per_cta = gg.tiles_per_cta;
+  p.stat_slots = conv_stat_slots(p.N, p.OH, p.OW, p.cout);  // P of the caller's buffer (>= gg.stat_slots)
+  if (gg.stat_slots > p.stat_slots) return set_error(kErrInvalid, "gconv: %d partial-sum slots needed, %d provided", gg.stat_slots, p.stat_slots);
+  if (p.stats) B200_CUDA(cudaMemsetAsync(p.stats, 0, static_cast<size_t>(p.N) * p.stat_slots * p.cout * 2 * sizeof(float), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gg.grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kern, maps, p);
+  B200_LAUNCH_CHECK("gconv_kernel (CTA pairs)");
+  return 0;
 }
 
 template <int BK, int BN, int A_SLOTS, int B_SLOTS, bool B_RES, int OC_ = 0, int MT = 1>
@@ -639,11 +760,30 @@ static int launch_gconv(const GConvMaps& maps, const GConvParams& p_in, cudaStre
   return 0;
 }
 
-static int dispatch_gconv(const GConvMaps& maps, const GConvParams& p, int BK, int BN, cudaStream_t st) {
-  if (p.out_split == 32 && BK == 64 && BN == 128) return launch_gconv<64, 128, 4, 4, false, 32>(maps, p, st);
-  if (p.out_split == 32 && BK == 32 && BN == 128) return launch_gconv<32, 128, 8, 4, false, 32>(maps, p, st);
+// The packed weight matrix of a launch ([rows][K] bf16, K-major): its TMA box depends on the kernel chosen here.
+struct WSpec {
+  const void* w;
+  int rows, K;
+};
+
+static int dispatch_gconv(GConvMaps& maps, const GConvParams& p, const WSpec& ws, int BK, int BN, cudaStream_t st) {
+  int rc;
+  if (p.out_split == 32 && BN == 128 && (BK == 64 || BK == 32)) {
+    if ((rc = make_weight_map(&maps.w, ws.w, ws.rows, ws.K, BK, BN))) return rc;
+    if (BK == 64) return launch_gconv<64, 128, 4, 4, false, 32>(maps, p, st);
+    return launch_gconv<32, 128, 8, 4, false, 32>(maps, p, st);
+  }
   // resident weights: one N tile and the whole (taps x chunks) slab inside the 72 KB budget
   const bool res = gconv_weights_resident(BK, BN, p.cout, p.cin, p.ntaps_total);
+  if (gconv_pairs(BK, BN, p.mt, res, p.out_split, p.tiles_w, p.tiles_h)) {
+    // each CTA holds HALF of every weight tile: the ring is twice as deep in the same shared memory
+    if ((rc = make_weight_map(&maps.w, ws.w, ws.rows, ws.K, BK, BN / 2))) return rc;
+    if (BN == 256) return launch_gconv_pairs<64, 256, 3, 6, 1>(maps, p, st);
+    if (BN == 192) return launch_gconv_pairs<64, 192, 3, 8, 1>(maps, p, st);
+    if (BN == 128) return launch_gconv_pairs<64, 128, 2, 8, 2>(maps, p, st);
+    return launch_gconv_pairs<64, 64, 2, 6, 4>(maps, p, st);
+  }
+  if ((rc = make_weight_map(&maps.w, ws.w, ws.rows, ws.K, BK, BN))) return rc;
 #define GC(bk, bn, as, bs, r) \
   if (BK == bk && BN == bn && res == r) return launch_gconv<bk, bn, as, bs, r>(maps, p, st);
   // A slots now hold a whole channel chunk (all taps) of a CTA tile: two or three are a deep enough ring
@@ -721,12 +861,12 @@ extern "C" int b200unet_conv_fprop(const b200unet_conv_fprop_args* a, void* stre
         taps[n++] = TapSpec{par[kh] * 2 + par[kw], sh[kh], sh[kw], (kh * 3 + kw) * a->Cin};
   }
   if ((rc = build_loads(taps, 9, lat, BK, &p, &maps))) return rc;
-  if ((rc = make_weight_map(&maps.w, a->w, a->Cout, 9 * a->Cin, BK, BN))) return rc;
+  const WSpec ws{a->w, a->Cout, 9 * a->Cin};
   const int OC = (BN % 64 == 0) ? 64 : 32;
   if ((rc = make_act_map(&maps.out[0], static_cast<const __nv_bfloat16*>(a->y), a->y_pitch, a->N, OH, OW, a->Cout, 1, 1, 0,
                          0, OC, kTW, kTH)))
     return rc;
-  return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
+  return dispatch_gconv(maps, p, ws, BK, BN, static_cast<cudaStream_t>(stream));
 }
 
 // Partial-sum slots per image of the producer-side norm-backward sums, 0 when the kernel that runs this data gradient
@@ -764,7 +904,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   GConvMaps maps;
-  if ((rc = make_weight_map(&maps.w, a->wt, a->Cin, 9 * a->Cout, BK, BN))) return rc;
+  const WSpec ws{a->wt, a->Cin, 9 * a->Cout};
   SrcLattice lat[1] = {SrcLattice{dy, a->dy_pitch, a->N, OH, OW, a->Cout, 1, 1, 0, 0}};
   if (s == 1) {
     GConvParams p{};
@@ -801,10 +941,10 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
                                a->N, a->H, a->W, OC, 1, 1, 0, 0, OC, kTW, kTH)))
           return rc;
       }
-      return dispatch_gconv(maps, p, BK, BN, st);
+      return dispatch_gconv(maps, p, ws, BK, BN, st);
     }
     if ((rc = make_act_map(&maps.out[0], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 1, 1, 0, 0, OC, kTW, kTH))) return rc;
-    return dispatch_gconv(maps, p, BK, BN, st);
+    return dispatch_gconv(maps, p, ws, BK, BN, st);
   }
   B200_CHECK_ARG(!a->dx2, "conv_dgrad: a split output needs stride 1");
   // stride 2: one launch per parity class (ph,pw) of the input pixel; ih = 2a + ph receives
@@ -833,7 +973,7 @@ extern "C" int b200unet_conv_dgrad(const b200unet_conv_dgrad_args* a, void* stre
       if ((rc = build_loads(taps, n, lat, BK, &p, &maps))) return rc;
       if ((rc = make_act_map(&maps.out[0], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, OC, kTW, kTH)))
         return rc;
-      if ((rc = dispatch_gconv(maps, p, BK, BN, st))) return rc;
+      if ((rc = dispatch_gconv(maps, p, ws, BK, BN, st))) return rc;
     }
   return 0;
 }
@@ -907,11 +1047,11 @@ extern "C" int b200unet_conv_dgrad_s2(const b200unet_conv_dgrad_args* a, void* s
   for (int dw = 0; dw < 2; ++dw)
     for (int dh = 0; dh < 2; ++dh) taps[n++] = TapSpec{0, dh, dw, (dh * 2 + dw) * a->Cout};
   if ((rc = build_loads(taps, 4, lat, BK, &p, &maps))) return rc;
-  if ((rc = make_weight_map(&maps.w, a->wt, BN, 4 * a->Cout, BK, BN))) return rc;
+  const WSpec ws{a->wt, BN, 4 * a->Cout};
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw)
       if ((rc = make_act_map(&maps.out[ph * 2 + pw], dx, a->dx_pitch, a->N, a->H, a->W, a->Cin, 2, 2, ph, pw, a->Cin, kTW,
                              kTH)))
         return rc;
-  return dispatch_gconv(maps, p, BK, BN, static_cast<cudaStream_t>(stream));
+  return dispatch_gconv(maps, p, ws, BK, BN, static_cast<cudaStream_t>(stream));
 }
