@@ -626,10 +626,17 @@ static bool cg2_enabled() {
   }
   return state != 0;
 }
-static bool gconv_pairs(int BK, int BN, int mt, bool resident, int out_split, int tiles_w, int tiles_h) {
-  if (!cg2_enabled() || BK != 64 || resident || out_split != 0) return false;
-  if ((static_cast<long long>(tiles_w) * tiles_h) % 2 != 0) return false;  // a pair never straddles two images
-  return (BN == 256 && mt == 1) || (BN == 192 && mt == 1) || (BN == 128 && mt == 2) || (BN == 64 && mt == 4);
+// Measured per layer at batch 32 (tools/conv_bench.py, B200UNET_CG2=0 against 1): -4..-14 % on every streamed-weight
+// layer with at least two channel chunks and more pair tiles than clusters; +8 % on the one layer with a single chunk
+// (192 <- 64 data gradient: 9 weight tiles per tile, the pair's hand-overs are not amortised) and +4 % at 16^2, where
+// a cluster gets a single tile (nothing to pipeline; the cluster launch costs more than it saves) -- those stay single.
+static bool gconv_pairs(const GConvParams& p, int BK, int BN, bool resident) {
+  if (!cg2_enabled() || BK != 64 || resident || p.out_split != 0) return false;
+  const long long per_img = static_cast<long long>(p.tiles_w) * p.tiles_h;
+  if (per_img % 2 != 0) return false;  // a pair never straddles two images
+  if (p.cin < 2 * BK) return false;
+  if (per_img / 2 * p.N * (p.cout / BN) <= num_sms() / 2) return false;
+  return (BN == 256 && p.mt == 1) || (BN == 192 && p.mt == 1) || (BN == 128 && p.mt == 2) || (BN == 64 && p.mt == 4);
 }
 
 int conv_stat_slots(int N, int OH, int OW, int Cout) {
@@ -775,7 +782,7 @@ static int dispatch_gconv(GConvMaps& maps, const GConvParams& p, const WSpec& ws
   }
   // resident weights: one N tile and the whole (taps x chunks) slab inside the 72 KB budget
   const bool res = gconv_weights_resident(BK, BN, p.cout, p.cin, p.ntaps_total);
-  if (gconv_pairs(BK, BN, p.mt, res, p.out_split, p.tiles_w, p.tiles_h)) {
+  if (gconv_pairs(p, BK, BN, res)) {
     // each CTA holds HALF of every weight tile: the ring is twice as deep in the same shared memory
     if ((rc = make_weight_map(&maps.w, ws.w, ws.rows, ws.K, BK, BN / 2))) return rc;
     if (BN == 256) return launch_gconv_pairs<64, 256, 3, 6, 1>(maps, p, st);

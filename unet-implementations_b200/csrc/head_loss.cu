@@ -148,15 +148,49 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks,
   pdl_wait();
   // one block of 32 warps; warp w reduces values i = w, w + 32, ... (value v of image b): lanes stride over the
   // partials, fixed-order shuffle tree (the serial version took 46 us on the critical path between forward and backward)
-  extern __shared__ double sred[];  // [N][12]
+  extern __shared__ double sred[];  // [N][12] sums, then [N][3] per-(image, class) Dice ratios
+  double* dterm = sred + N * kLossVals;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int i = warp; i < N * kLossVals; i += nwarps) {
-    const int b = i / kLossVals, v = i - b * kLossVals;
-    double s = 0.0;
-    for (int k = lane; k < blocks; k += 32) s += part[(static_cast<int64_t>(b) * blocks + k) * kLossVals + v];
+  // four values per warp at a time: their loads are independent (one value at a time was a chain of dependent L2 round
+  // trips, 12 per warp); each value keeps its own fixed-order sum
+  constexpr int UV = 4;
+  const int total = N * kLossVals;
+  for (int i = warp * UV; i < total; i += nwarps * UV) {
+    double s[UV];
+    const float* src[UV];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sred[i] = s;
+    for (int u = 0; u < UV; ++u) {
+      const int iu = min(i + u, total - 1);
+      const int b = iu / kLossVals, v = iu - b * kLossVals;
+      src[u] = part + static_cast<int64_t>(b) * blocks * kLossVals + v;
+      s[u] = 0.0;
+    }
+    for (int k = lane; k < blocks; k += 32) {
+      float x[UV];
+#pragma unroll
+      for (int u = 0; u < UV; ++u) x[u] = src[u][static_cast<int64_t>(k) * kLossVals];
+#pragma unroll
+      for (int u = 0; u < UV; ++u) s[u] += x[u];
+    }
+#pragma unroll
+    for (int u = 0; u < UV; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+      if (lane == 0 && i + u < total) sred[i + u] = s[u];
+    }
+  }
+  __syncthreads();
+  // the per-(image, class) Dice terms and backward tables in parallel (96 double divisions were a serial tail)
+  if (threadIdx.x < N * kNC) {
+    const int b = threadIdx.x / kNC, c = threadIdx.x - b * kNC;
+    const double T = sred[b * kLossVals + c];
+    const double I = sred[b * kLossVals + 2 * kNC + c];
+    const double Pc = sred[b * kLossVals + 3 * kNC + c];
+    const double U = Pc + T + smooth;
+    const double two_i = 2.0 * I + smooth;
+    dterm[b * kNC + c] = two_i / U;
+    tables[kNC + (b * 2 + 0) * kNC + c] = static_cast<float>(-(2.0 / (kNC * static_cast<double>(N))) / U);
+    tables[kNC + (b * 2 + 1) * kNC + c] = static_cast<float>((1.0 / (kNC * static_cast<double>(N))) * two_i / (U * U));
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -191,16 +225,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ part, int blocks,
   double dice_loss = 0.0;
   for (int c = 0; c < kNC; ++c) {
     double dsum = 0.0;
-    for (int b = 0; b < N; ++b) {
-      const double T = sred[b * kLossVals + c];
-      const double I = sred[b * kLossVals + 2 * kNC + c];
-      const double Pc = sred[b * kLossVals + 3 * kNC + c];
-      const double U = Pc + T + smooth;
-      const double two_i = 2.0 * I + smooth;
-      dsum += two_i / U;
-      tables[kNC + (b * 2 + 0) * kNC + c] = static_cast<float>(-(2.0 / (kNC * static_cast<double>(N))) / U);
-      tables[kNC + (b * 2 + 1) * kNC + c] = static_cast<float>((1.0 / (kNC * static_cast<double>(N))) * two_i / (U * U));
-    }
+    for (int b = 0; b < N; ++b) dsum += dterm[b * kNC + c];  // same terms, same order as the serial form
     dice_loss += 1.0 - dsum / N;
   }
   dice_loss /= kNC;
@@ -622,7 +647,8 @@ static int loss_fwd_impl(const float* logits_nchw, const TT* target, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   launch_k(loss_fwd_kernel<TT>, dim3(blocks, N), dim3(kLossThreads), 0, st, logits_nchw, target, ignore_index, workspace, HW);
   B200_LAUNCH_CHECK("loss_fwd_kernel");
-  const size_t smem = static_cast<size_t>(N) * kLossVals * sizeof(double);
+  const size_t smem = static_cast<size_t>(N) * (kLossVals + kNC) * sizeof(double);
+  B200_CHECK_ARG(N * kNC <= 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
   B200_CHECK_ARG(smem <= 48 * 1024, "loss_fwd: batch %d too large for the finalize kernel", N);
   launch_k(loss_finalize_kernel, dim3(1), dim3(1024), smem, st, workspace, blocks, class_weights, dynamic, weight_ce, weight_dice, smooth,
                                              loss_out, tables, N);
@@ -695,7 +721,9 @@ extern "C" int b200unet_head_fwd_f32(const void* z, int64_t z_pitch, const float
 // blocks per image of the head backward = partial-sum slots per image of its norm-backward sums ([N][P][C][2])
 extern "C" int b200unet_head_bwd_stat_slots(int N, int64_t HW) {
   if (N <= 0 || HW <= 0) return 0;
-  int64_t per = ceil_div64(static_cast<int64_t>(num_sms()) * 4, N);
+  // ONE wave: the kernel holds two blocks per SM (128 registers); round DOWN so that N * per <= the resident blocks
+  // (19 blocks per image at batch 32 were 608 blocks for 296 places: a third, almost empty wave)
+  int64_t per = (static_cast<int64_t>(num_sms()) * 2) / N;
   const int64_t mx = ceil_div64(HW, 64);  // at least one sweep of 64 pixel lanes per block
   if (per > mx) per = mx;
   return static_cast<int>(per < 1 ? 1 : per);
