@@ -37,6 +37,21 @@ def test_version_and_sizing_calls_need_no_gpu():
     assert _lib.call("b200unet_loss_workspace", 4, 512 * 512) > 0
 
 
+def test_statistics_slots_cover_the_cta_pair_layout():
+    """The fprop epilogue writes one partial-sum slot per (image, CTA, TMEM lane quarter); as CTA pairs (cta_group::2)
+    a cluster owns 8 slots per image it touches.  The sizing call the caller allocates from must cover that layout
+    for every streamed-weight layer of the model at the benchmark batch (conv_fprop_dgrad.cu: gconv_grid)."""
+    from unet_implementations_b200 import _lib
+    sms = 148  # without a device the library sizes for 148 SMs
+    for n, hw, cout, bn, mt in [(32, 128, 128, 128, 2), (32, 64, 256, 256, 1), (32, 32, 512, 256, 1), (32, 256, 64, 64, 4),
+                                (4, 128, 128, 128, 2), (1, 64, 256, 256, 1)]:
+        per_img_pairs = -(-hw // 8) * -(-hw // (16 * mt)) // 2 * (cout // bn)
+        total = per_img_pairs * n
+        tiles_per_cluster = max(1, -(-total // (sms // 2)))
+        need = 8 * (-(-per_img_pairs // tiles_per_cluster) + 1)
+        assert _lib.call("b200unet_conv_fprop_partials", n, hw, hw, cout) >= need, (n, hw, cout)
+
+
 def test_product_path_fails_loudly_without_a_device():
     import torch
     if torch.cuda.is_available():
