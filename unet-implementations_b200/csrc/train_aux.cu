@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(kSgdThreads) sgd_nesterov_kernel(const __grid_
 // operations in the same order: bit-exact with torch.optim.SGD for scale 1) and (iii) emits the bf16 operand packs
 // the conv kernels consume -- [Cout][3][3][Cin] (fprop), [Cin][3][3][Cout] (dgrad) and the parity-stacked stride-2
 // dgrad pack -- so that no repack kernel runs between the optimizer and the next forward and the packs can never be
-// stale.  Threads walk a tensor in OIHW order (the 20 B/parameter of fp32 traffic is coalesced); the two or three
-// 2-byte pack stores per parameter are scattered and merge in L2 (the packs are 80 MB, the L2 126 MB).
+// stale.  The 3x3 weights of the tensor-core layers (99.9 % of the parameters) are processed in 32 x 32 x 9 tiles
+// through shared memory so that the fp32 traffic AND the pack stores are coalesced; every other tensor (norm
+// parameters, biases, the stem, 1x1 and padded heads) is walked element by element in storage order.
 constexpr int kFlatThreads = 256, kFlatPerThread = 4;
 
 __global__ void __launch_bounds__(kFlatThreads) sgd_flat_kernel(const b200unet_flat_tensor* __restrict__ T, int count,
@@ -92,11 +93,8 @@ __global__ void __launch_bounds__(kFlatThreads) sgd_flat_kernel(const b200unet_f
   __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(D.ws);
   const int kk = D.ksize * D.ksize;
   const int per_o = D.cin * kk;
-  const int base = (b - D.first_block) * kFlatThreads * kFlatPerThread;
-#pragma unroll
-  for (int k = 0; k < kFlatPerThread; ++k) {
-    const int i = base + k * kFlatThreads + threadIdx.x;
-    if (i >= D.numel) break;
+  // the per-element update: torch's CUDA foreach arithmetic, operation by operation
+  auto update = [&](int i) -> float {
     const float pv = p[i];
     float gv = g[i];
     if (grad_scale != 1.f) gv = __fmul_rn(gv, grad_scale);
@@ -109,6 +107,56 @@ __global__ void __launch_bounds__(kFlatThreads) sgd_flat_kernel(const b200unet_f
     }
     const float pn = fmaf(-lr, upd, pv);
     p[i] = pn;
+    return pn;
+  };
+  if (wf && kk == 9 && (D.cin & 31) == 0 && (D.cout & 31) == 0 && D.cin_pad == D.cin && D.cout_pad == D.cout) {
+    // ---- 3x3 conv weights of the tensor-core path: TILES of 32 output x 32 input channels x 9 taps (9216 elements).
+    // Walking a tensor in OIHW order made every bf16 pack store a lone 2-byte write (2-3 per parameter, 0.45 ms per
+    // step for 0.5 GB of traffic); a tile is read as 32 runs of 288 contiguous floats (128-byte aligned), staged as
+    // bf16 in shared memory, and written as 64-byte runs: 32 consecutive ci per (o, tap) into [Cout][3][3][Cin],
+    // 32 consecutive o per (ci, tap) into [Cin][3][3][Cout] and the parity-stacked stride-2 pack.  The tensor owns
+    // numel / 1024 = 9 x tiles blocks of the launch (the descriptor table's block count is unchanged): block j < tiles
+    // takes tile j, the others have nothing to do.
+    constexpr int kTileR = 288, kRowPad = 290;  // 145-word rows: the o-major read below is bank-conflict free
+    __shared__ __nv_bfloat16 st[32 * kRowPad];
+    const int ct_n = D.cin >> 5;
+    const int tiles = (D.cout >> 5) * ct_n;
+    const int j = b - D.first_block;
+    if (j >= tiles) return;
+    const int o0 = (j / ct_n) << 5, ci0 = (j - (j / ct_n) * ct_n) << 5;
+    const int tile_base = o0 * per_o + ci0 * 9;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < 32 * kTileR; e += kFlatThreads) {
+      const int ol = e / kTileR, rl = e - ol * kTileR;
+      st[ol * kRowPad + rl] = __float2bfloat16_rn(update(tile_base + ol * per_o + rl));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * kTileR; e += kFlatThreads) {  // [o][tap][ci]: ci fastest
+      const int cl = e & 31, tap = (e >> 5) % 9, ol = e / kTileR;
+      wf[(static_cast<int64_t>(o0 + ol) * 9 + tap) * D.cin + ci0 + cl] = st[ol * kRowPad + cl * 9 + tap];
+    }
+    if (wdp || ws) {
+      for (int e = threadIdx.x; e < 32 * kTileR; e += kFlatThreads) {  // [ci][tap][o]: o fastest
+        const int ol = e & 31, tap = (e >> 5) % 9, cl = e / kTileR;
+        const __nv_bfloat16 v = st[ol * kRowPad + cl * 9 + tap];
+        const int ci = ci0 + cl, o = o0 + ol;
+        if (wdp) wdp[(static_cast<int64_t>(ci) * 9 + tap) * D.cout + o] = v;
+        if (ws) {
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const int ph = kh == 1 ? 0 : 1, dh = kh == 0 ? 1 : 0;
+          const int pw = kw == 1 ? 0 : 1, dw = kw == 0 ? 1 : 0;
+          ws[((static_cast<int64_t>(ph * 2 + pw) * D.cin + ci) * 4 + (dh * 2 + dw)) * D.cout + o] = v;
+        }
+      }
+    }
+    return;
+  }
+  const int base = (b - D.first_block) * kFlatThreads * kFlatPerThread;
+#pragma unroll
+  for (int k = 0; k < kFlatPerThread; ++k) {
+    const int i = base + k * kFlatThreads + threadIdx.x;
+    if (i >= D.numel) break;
+    const float pn = update(i);
     if (wf) {
       const int o = i / per_o;
       const int r = i - o * per_o;
