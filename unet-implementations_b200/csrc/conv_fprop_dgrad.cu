@@ -28,6 +28,17 @@
 // fixed subset of ring slots so that it observes every phase of its barriers in order), warp 4 = TMEM allocator +
 // single-thread MMA issuer, warps 5..8 = epilogue: tcgen05.ld -> bf16 -> swizzled staging -> TMA store, plus the
 // per-(n,c) sum / sum-of-squares partials of the stored values that InstanceNorm needs (deterministic, no atomics).
+//
+// CTA pairs (template argument CG = 2; the streamed-weight layers).  Two CTAs of a cluster on the two SMs of a TPC work
+// on two M tiles of the same image and the same N tile.  Only the even CTA (the leader) issues MMAs, with
+// tcgen05.mma.cta_group::2 and M = 256: the hardware reads each CTA's own A window and HALF of the weight tile (BN / 2
+// rows) from each CTA's shared memory at the same offsets and writes each CTA's 128 accumulator rows into its own
+// TMEM.  Protocol: TMA loads of both CTAs complete on the leader's full barriers (which expect the bytes of both);
+// tcgen05.commit multicasts every completion (slot free, accumulator ready) to the barriers at the same offset in both
+// CTAs; the peer's epilogue warps release the accumulator buffer with a remote arrive on the leader's barrier (count
+// 8); a cluster barrier after the barrier initialisation and before the TMEM release keeps either CTA from running
+// ahead of, or leaving before, its peer.  Everything else -- producers, rings, epilogue, statistics -- is per CTA and
+// unchanged.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "conv_common.cuh"
